@@ -1,0 +1,676 @@
+// capi.cu -- host runtime behind include/kh_capi.h: owns device memory, streams and the
+// kernel sequence for insert (K2+K3), find (K4), assemble (K5+K6) and pack (K1).
+//
+// Layout in HBM (one handle = one GPU):
+//   table        nbuckets x 32 B, one DRAM sector per bucket (4 x u64 or 2 x u128 slots)
+//   starts       start-node slot values in input order (grow-only)
+//   per insert   start bitmask (n/8 B), per-tile counts/offsets
+//   per assemble link[seg] u64, seglen[seg] u8, tmp[seg][seg_chars], contig_len/pre/off, out
+// Scratch is grow-only and reused across calls so a steady-state step allocates nothing.
+#include <algorithm>
+#include <cstdio>
+#include <cstdlib>
+#include <cstring>
+#include <string>
+
+#include "../../include/kh_capi.h"
+#include "kernels.cuh"
+
+using namespace kh;
+
+namespace {
+
+struct DevBuf {
+    void* p = nullptr;
+    size_t cap = 0;
+};
+
+enum { EV_INS0, EV_INS1, EV_AS0, EV_WALK, EV_RANK, EV_AS1, EV_PACK0, EV_PACK1, EV_CLR0, EV_CLR1, EV_COUNT };
+
+}  // namespace
+
+struct kh_table {
+    int k = 0, W = 1, device = 0, pl = 0, pb = 0, slot_bytes = 8, per_bucket = 4;
+    double lf = 0.5;
+    u64 n_expected = 0, nbuckets = 0;
+    cudaStream_t stream = nullptr, own_stream = nullptr, copy_stream = nullptr;
+    void* table = nullptr;
+    size_t table_bytes = 0;
+    DevBuf starts;
+    u64 n_starts = 0;
+    DevBuf mask, tile_counts, tile_offs, scan_blocks;
+    Counters* d_ctr = nullptr;
+    Counters* h_ctr = nullptr;
+    DevBuf link, seglen, tmp, contig_len, contig_pre, contig_off, out;
+    DevBuf stage[2], text_stage, scratch_a, scratch_b, scratch_c;
+    void* h_out = nullptr; size_t h_out_cap = 0;
+    void* h_off = nullptr; size_t h_off_cap = 0;
+    u32 split_shift = 3, seg_chars = 64;
+    cudaEvent_t ev[EV_COUNT] = {};
+    cudaEvent_t ev_copied[2] = {}, ev_consumed[2] = {};
+    bool have_ins = false, have_as = false, have_pack = false, have_clr = false;
+    kh_stats stats = {};
+    std::string err;
+    int sm_count = 148, walk_blocks_per_sm = 0, rank_blocks_per_sm = 0;
+    u64 last_contig_bytes = 0, last_n_contigs = 0;
+};
+
+namespace {
+
+int fail(kh_table* t, int status, const std::string& msg) {
+    if (t) t->err = msg;
+    return status;
+}
+
+#define KH_CUDA(t, expr)                                                                         \
+    do {                                                                                         \
+        cudaError_t e_ = (expr);                                                                 \
+        if (e_ != cudaSuccess)                                                                   \
+            return fail((t), e_ == cudaErrorMemoryAllocation ? KH_ERR_NOMEM : KH_ERR_CUDA,       \
+                        std::string(#expr) + ": " + cudaGetErrorString(e_));                     \
+    } while (0)
+
+#define KH_TRY(expr)                  \
+    do {                              \
+        const int rc_ = (expr);       \
+        if (rc_ != KH_OK) return rc_; \
+    } while (0)
+
+int ensure(kh_table* t, DevBuf& b, size_t bytes, bool keep = false) {
+    if (bytes <= b.cap && b.p) return KH_OK;
+    const size_t want = std::max<size_t>(256, bytes + bytes / 8);
+    void* np = nullptr;
+    KH_CUDA(t, cudaMalloc(&np, want));
+    if (b.p) {
+        if (keep && b.cap) KH_CUDA(t, cudaMemcpyAsync(np, b.p, b.cap, cudaMemcpyDeviceToDevice, t->stream));
+        KH_CUDA(t, cudaStreamSynchronize(t->stream));
+        KH_CUDA(t, cudaFree(b.p));
+    }
+    b.p = np;
+    b.cap = want;
+    return KH_OK;
+}
+
+int ensure_pinned(kh_table* t, void*& p, size_t& cap, size_t bytes) {
+    if (bytes <= cap && p) return KH_OK;
+    if (p) KH_CUDA(t, cudaFreeHost(p));
+    p = nullptr; cap = 0;
+    const size_t want = std::max<size_t>(4096, bytes + bytes / 8);
+    KH_CUDA(t, cudaHostAlloc(&p, want, cudaHostAllocDefault));
+    cap = want;
+    return KH_OK;
+}
+
+int status_from_errors(kh_table* t, u32 e) {
+    if (e == 0) return KH_OK;
+    if (e & kErrBadInput) return fail(t, KH_ERR_BAD_INPUT, "input contains a base outside ACGT or an extension outside ACGTF");
+    if (e & kErrTableFull) return fail(t, KH_ERR_TABLE_FULL, "hash table is full (more distinct k-mers than slots)");
+    if (e & kErrNotFound) return fail(t, KH_ERR_NOT_FOUND, "Error: k-mer not found in Distributed HashMap.");
+    if (e & kErrCycle) return fail(t, KH_ERR_CYCLE, "a start-rooted chain never reaches forward extension 'F' (cycle)");
+    if (e & kErrConverge) return fail(t, KH_ERR_CONVERGE, "two start nodes reach the same end node (chains are not linear)");
+    return fail(t, KH_ERR_CUDA, "internal error: segment bookkeeping overflow");
+}
+
+// Pull the counters to the host (synchronises the stream).
+int read_counters(kh_table* t) {
+    KH_CUDA(t, cudaMemcpyAsync(t->h_ctr, t->d_ctr, sizeof(Counters), cudaMemcpyDeviceToHost, t->stream));
+    KH_CUDA(t, cudaStreamSynchronize(t->stream));
+    return KH_OK;
+}
+int clear_error_bits(kh_table* t) {
+    KH_CUDA(t, cudaMemsetAsync(&t->d_ctr->errors, 0, sizeof(u32), t->stream));
+    return KH_OK;
+}
+
+// exclusive scan of n u32 -> u64 (out), total -> *total_dev
+int device_scan(kh_table* t, const u32* in, u64 n, u64* out, u64* total_dev) {
+    const u64 nsb = (n + kScanTile - 1) / kScanTile;
+    KH_TRY(ensure(t, t->scan_blocks, (nsb + 1) * sizeof(u64)));
+    u64* bs = static_cast<u64*>(t->scan_blocks.p);
+    scan_reduce_kernel<<<(unsigned)nsb, kScanThreads, 0, t->stream>>>(in, n, bs);
+    scan_spine_kernel<<<1, 1024, 0, t->stream>>>(bs, nsb, total_dev);
+    scan_apply_kernel<<<(unsigned)nsb, kScanThreads, 0, t->stream>>>(in, n, bs, out);
+    KH_CUDA(t, cudaGetLastError());
+    return KH_OK;
+}
+
+__global__ void init_assemble_kernel(Counters* c, u32 first_overflow_seg) {
+    c->next_walker = 0;
+    c->next_seg = first_overflow_seg;
+    c->rank_rounds = 0;
+    c->n_nodes = 0;
+    c->contig_bytes = 0;
+    for (int i = 0; i < 40; ++i) c->flags[i] = 0;
+}
+
+template <int W>
+int insert_device_impl(kh_table* t, const unsigned char* recs, u64 n, bool record_start) {
+    typedef typename Slot<W>::value_t V;
+    if (n == 0) return KH_OK;
+    if (n >= 0xFFF00000ull) return fail(t, KH_ERR_ARG, "at most 2^32-2^20 records per insert call; split the batch");
+    const u64 ntiles = (n + kInsTile - 1) / kInsTile;
+    KH_TRY(ensure(t, t->mask, ntiles * (kInsTile / 32) * sizeof(u32)));
+    KH_TRY(ensure(t, t->tile_counts, ntiles * sizeof(u32)));
+    KH_TRY(ensure(t, t->tile_offs, ntiles * sizeof(u64)));
+    if (record_start) KH_CUDA(t, cudaEventRecord(t->ev[EV_INS0], t->stream));
+    insert_kernel<W><<<(unsigned)ntiles, kInsThreads, (size_t)kInsTile * t->pb, t->stream>>>(
+        recs, n, t->k, static_cast<V*>(t->table), t->nbuckets, static_cast<u32*>(t->mask.p),
+        static_cast<u32*>(t->tile_counts.p), t->d_ctr);
+    KH_CUDA(t, cudaGetLastError());
+    KH_TRY(device_scan(t, static_cast<u32*>(t->tile_counts.p), ntiles, static_cast<u64*>(t->tile_offs.p),
+                       &t->d_ctr->scan_total));
+    KH_TRY(read_counters(t));     // number of new start nodes (sizes the start list) + error bits
+    const u32 e = t->h_ctr->errors;
+    if (e) {
+        clear_error_bits(t);
+        return status_from_errors(t, e);
+    }
+    const u64 fresh = t->h_ctr->scan_total;
+    if (fresh) {
+        KH_TRY(ensure(t, t->starts, (t->n_starts + fresh) * sizeof(V), /*keep=*/true));
+        const u64 threads = ntiles * 32;
+        scatter_starts_kernel<W><<<(unsigned)((threads + 255) / 256), 256, 0, t->stream>>>(
+            recs, n, t->k, static_cast<u32*>(t->mask.p), static_cast<u64*>(t->tile_offs.p), ntiles,
+            static_cast<V*>(t->starts.p), t->n_starts);
+        KH_CUDA(t, cudaGetLastError());
+        t->n_starts += fresh;
+    }
+    KH_CUDA(t, cudaEventRecord(t->ev[EV_INS1], t->stream));
+    t->have_ins = true;
+    return KH_OK;
+}
+
+int insert_device(kh_table* t, const void* recs, u64 n, bool record_start = true) {
+    return t->W == 1 ? insert_device_impl<1>(t, static_cast<const unsigned char*>(recs), n, record_start)
+                     : insert_device_impl<2>(t, static_cast<const unsigned char*>(recs), n, record_start);
+}
+
+int pack_device(kh_table* t, const void* text_dev, u64 n_lines, void* pairs_dev) {
+    if (n_lines == 0) return KH_OK;
+    const u64 nblk = (n_lines + kPackLines - 1) / kPackLines;
+    if (nblk > 0x7FFFFFFFull) return fail(t, KH_ERR_ARG, "too many lines in one pack call");
+    const size_t smem = (((size_t)kPackLines * (t->k + 4) + 15) & ~(size_t)15) + (size_t)kPackLines * t->pb;
+    pack_lines_kernel<<<(unsigned)nblk, kPackLines, smem, t->stream>>>(
+        static_cast<const unsigned char*>(text_dev), n_lines, t->k, static_cast<unsigned char*>(pairs_dev), t->d_ctr);
+    KH_CUDA(t, cudaGetLastError());
+    return KH_OK;
+}
+
+template <int W>
+int assemble_impl(kh_table* t) {
+    typedef typename Slot<W>::value_t V;
+    const u64 n_starts = t->n_starts;
+    const u64 n_split = ((t->nbuckets - 1) >> t->split_shift) + 1;
+    if (n_starts + n_split >= 0xFFF00000ull) return fail(t, KH_ERR_ARG, "too many walk segments for 32-bit ids");
+    if (t->walk_blocks_per_sm == 0) {
+        KH_CUDA(t, cudaOccupancyMaxActiveBlocksPerMultiprocessor(&t->walk_blocks_per_sm, walk_kernel<W>, kWalkThreads, 0));
+        KH_CUDA(t, cudaOccupancyMaxActiveBlocksPerMultiprocessor(&t->rank_blocks_per_sm, rank_kernel, 256, 0));
+        if (t->walk_blocks_per_sm < 1 || t->rank_blocks_per_sm < 1) return fail(t, KH_ERR_CUDA, "kernel does not fit on an SM");
+    }
+    const u64 n_keys = t->h_ctr->n_inserted;     // refreshed by the last insert
+    u64 walkers = n_starts + n_split;
+    unsigned walk_blocks = (unsigned)std::min<u64>((u64)t->sm_count * t->walk_blocks_per_sm,
+                                                    (walkers + kWalkThreads - 1) / kWalkThreads);
+    walk_blocks = std::max(walk_blocks, 1u);
+    const u64 nwarps = (u64)walk_blocks * (kWalkThreads / 32);
+    const u64 seg_cap = walkers + 2 * (n_keys / t->seg_chars + 1) + (u64)kSegBatch * nwarps + 64;
+    if (seg_cap >= 0xFFFFFFF0ull) return fail(t, KH_ERR_ARG, "too many walk segments for 32-bit ids");
+    KH_TRY(ensure(t, t->link, seg_cap * sizeof(u64)));
+    KH_TRY(ensure(t, t->seglen, seg_cap));
+    KH_TRY(ensure(t, t->tmp, seg_cap * (u64)t->seg_chars + 16));
+    KH_TRY(ensure(t, t->contig_len, (n_starts + 1) * sizeof(u32)));
+    KH_TRY(ensure(t, t->contig_pre, (n_starts + 1) * sizeof(u32)));
+    KH_TRY(ensure(t, t->contig_off, (n_starts + 1) * sizeof(u64)));
+    const u64 out_cap = n_keys + n_starts * (u64)(t->k + 1) + 64;
+    KH_TRY(ensure(t, t->out, out_cap));
+
+    KH_CUDA(t, cudaEventRecord(t->ev[EV_AS0], t->stream));
+    init_assemble_kernel<<<1, 1, 0, t->stream>>>(t->d_ctr, (u32)walkers);
+    KH_CUDA(t, cudaMemsetAsync(static_cast<u32*>(t->contig_len.p) + n_starts, 0, sizeof(u32), t->stream));
+
+    WalkParams wp;
+    wp.table = t->table; wp.nbuckets = t->nbuckets; wp.starts = t->starts.p;
+    wp.link = static_cast<u64*>(t->link.p); wp.seglen = static_cast<unsigned char*>(t->seglen.p);
+    wp.tmp = static_cast<unsigned char*>(t->tmp.p); wp.ctr = t->d_ctr;
+    wp.n_starts = (u32)n_starts; wp.n_split = (u32)n_split; wp.split_shift = t->split_shift;
+    wp.seg_chars = t->seg_chars; wp.seg_cap = (u32)seg_cap; wp.k = t->k;
+    walk_kernel<W><<<walk_blocks, kWalkThreads, 0, t->stream>>>(wp);
+    KH_CUDA(t, cudaGetLastError());
+    KH_CUDA(t, cudaEventRecord(t->ev[EV_WALK], t->stream));
+
+    RankParams rp;
+    rp.link = wp.link; rp.seglen = wp.seglen; rp.ctr = t->d_ctr;
+    rp.contig_len = static_cast<u32*>(t->contig_len.p); rp.contig_pre = static_cast<u32*>(t->contig_pre.p);
+    rp.n_starts = (u32)n_starts; rp.seg_cap = (u32)seg_cap; rp.k = t->k; rp.max_rounds = 34;
+    void* rargs[] = {&rp};
+    const unsigned rank_blocks = (unsigned)std::max<u64>(1, std::min<u64>((u64)t->sm_count * t->rank_blocks_per_sm,
+                                                                            (seg_cap + 255) / 256));
+    KH_CUDA(t, cudaLaunchCooperativeKernel((void*)rank_kernel, dim3(rank_blocks), dim3(256), rargs, 0, t->stream));
+    KH_TRY(device_scan(t, rp.contig_len, n_starts + 1, static_cast<u64*>(t->contig_off.p), &t->d_ctr->contig_bytes));
+    KH_CUDA(t, cudaEventRecord(t->ev[EV_RANK], t->stream));
+
+    const u64 seg_threads = seg_cap * 16;
+    emit_segments_kernel<<<(unsigned)((seg_threads + 255) / 256), 256, 0, t->stream>>>(
+        wp.link, wp.seglen, wp.tmp, t->seg_chars, (u32)seg_cap, t->d_ctr, rp.contig_pre,
+        static_cast<u64*>(t->contig_off.p), t->k, out_cap, static_cast<char*>(t->out.p));
+    if (n_starts) {
+        const u64 head_threads = n_starts * (u64)(t->k + 1);
+        emit_heads_kernel<W><<<(unsigned)((head_threads + 255) / 256), 256, 0, t->stream>>>(
+            static_cast<const V*>(t->starts.p), (u32)n_starts, t->k, rp.contig_len,
+            static_cast<u64*>(t->contig_off.p), t->d_ctr, out_cap, static_cast<char*>(t->out.p));
+    }
+    KH_CUDA(t, cudaGetLastError());
+    KH_CUDA(t, cudaEventRecord(t->ev[EV_AS1], t->stream));
+    t->have_as = true;
+
+    KH_TRY(read_counters(t));
+    t->stats.n_contigs = n_starts;
+    t->stats.n_nodes = t->h_ctr->n_nodes;
+    t->stats.contig_bytes = t->h_ctr->contig_bytes;
+    t->stats.n_segments = std::min<u64>(t->h_ctr->next_seg, seg_cap);
+    t->stats.rank_rounds = t->h_ctr->rank_rounds;
+    t->last_contig_bytes = t->h_ctr->contig_bytes;
+    t->last_n_contigs = n_starts;
+    const u32 e = t->h_ctr->errors;
+    if (e) {
+        clear_error_bits(t);
+        return status_from_errors(t, e);
+    }
+    if (t->h_ctr->contig_bytes > out_cap)
+        return fail(t, KH_ERR_CONVERGE, "contigs cover more k-mers than were inserted (chains share nodes)");
+    return KH_OK;
+}
+
+int assemble_device(kh_table* t) { return t->W == 1 ? assemble_impl<1>(t) : assemble_impl<2>(t); }
+
+float elapsed(cudaEvent_t a, cudaEvent_t b) {
+    float ms = 0.f;
+    if (cudaEventElapsedTime(&ms, a, b) != cudaSuccess) { cudaGetLastError(); return 0.f; }
+    return ms;
+}
+
+int env_int(const char* name, int dflt) {
+    const char* v = getenv(name);
+    return (v && *v) ? atoi(v) : dflt;
+}
+
+int set_option(kh_table* t, const std::string& name, int64_t value) {
+    if (name == "split_buckets") {
+        if (value < 1 || value > (1 << 20) || (value & (value - 1))) return fail(t, KH_ERR_ARG, "split_buckets must be a power of two in [1, 2^20]");
+        u32 s = 0;
+        while ((1ll << s) < value) ++s;
+        t->split_shift = s;
+        return KH_OK;
+    }
+    if (name == "seg_chars") {
+        if (value < 8 || value > 248 || (value & 7)) return fail(t, KH_ERR_ARG, "seg_chars must be a multiple of 8 in [8, 248]");
+        t->seg_chars = (u32)value;
+        return KH_OK;
+    }
+    return fail(t, KH_ERR_ARG, "unknown option " + name);
+}
+
+}  // namespace
+
+// ============================================================================ C ABI ======
+extern "C" {
+
+int kh_abi_version(void) { return 1; }
+
+int kh_device_count(void) {
+    int n = 0;
+    if (cudaGetDeviceCount(&n) != cudaSuccess) { cudaGetLastError(); return 0; }
+    return n;
+}
+
+const char* kh_status_string(int s) {
+    switch (s) {
+    case KH_OK: return "ok";
+    case KH_ERR_ARG: return "bad argument";
+    case KH_ERR_CUDA: return "CUDA failure or no CUDA device";
+    case KH_ERR_NOT_FOUND: return "Error: k-mer not found in Distributed HashMap.";
+    case KH_ERR_TABLE_FULL: return "hash table full";
+    case KH_ERR_CYCLE: return "chain never terminates (cycle)";
+    case KH_ERR_BAD_INPUT: return "malformed input";
+    case KH_ERR_CONVERGE: return "chains are not linear (shared end node)";
+    case KH_ERR_NOMEM: return "out of memory";
+    default: return "unknown status";
+    }
+}
+
+uint64_t kh_packed_bytes(int k) { return (uint64_t)((k + 3) / 4); }
+uint64_t kh_pair_bytes(int k) { return (uint64_t)((k + 3) / 4 + 2); }
+
+int kh_create(int k, uint64_t n_expected, double load_factor, int device, kh_table** out) {
+    if (!out) return KH_ERR_ARG;
+    *out = nullptr;
+    if (k < 2 || k > 61 || !(load_factor > 0.0) || load_factor > 1.0) return KH_ERR_ARG;
+    int ndev = 0;
+    if (cudaGetDeviceCount(&ndev) != cudaSuccess || ndev == 0) { cudaGetLastError(); return KH_ERR_CUDA; }
+    if (device < 0 || device >= ndev) return KH_ERR_ARG;
+    kh_table* t = new kh_table();
+    auto bail = [&](int rc) { kh_destroy(t); return rc; };
+    t->k = k; t->device = device; t->lf = load_factor; t->n_expected = n_expected;
+    t->pl = (k + 3) / 4; t->pb = t->pl + 2;
+    t->W = (2 * k + 6 <= 64) ? 1 : 2;
+    t->slot_bytes = t->W == 1 ? 8 : 16;
+    t->per_bucket = 32 / t->slot_bytes;
+    if (cudaSetDevice(device) != cudaSuccess) return bail(KH_ERR_CUDA);
+    cudaDeviceProp prop;
+    if (cudaGetDeviceProperties(&prop, device) != cudaSuccess) return bail(KH_ERR_CUDA);
+    if (prop.major < 9) { fprintf(stderr, "libkh_b200: device %d is sm_%d%d; this library is built for sm_100a only\n", device, prop.major, prop.minor); return bail(KH_ERR_CUDA); }
+    t->sm_count = prop.multiProcessorCount;
+    // One random probe should move one 32-byte sector, not a 64/128-byte L2 fetch.
+    const int gran = env_int("KH_L2_FETCH_BYTES", 32);
+    if (gran > 0) { cudaDeviceSetLimit(cudaLimitMaxL2FetchGranularity, (size_t)gran); cudaGetLastError(); }
+
+    const long double slots = (long double)std::max<uint64_t>(n_expected, 1) / (long double)load_factor;
+    t->nbuckets = std::max<u64>(8, (u64)(slots / t->per_bucket) + 1);
+    t->table_bytes = (size_t)t->nbuckets * 32;
+    int rc = KH_OK;
+    auto ck = [&](cudaError_t e) { if (e != cudaSuccess && rc == KH_OK) { rc = e == cudaErrorMemoryAllocation ? KH_ERR_NOMEM : KH_ERR_CUDA; t->err = cudaGetErrorString(e); } };
+    ck(cudaStreamCreateWithFlags(&t->own_stream, cudaStreamNonBlocking));
+    ck(cudaStreamCreateWithFlags(&t->copy_stream, cudaStreamNonBlocking));
+    t->stream = t->own_stream;
+    ck(cudaMalloc(&t->table, t->table_bytes));
+    ck(cudaMalloc((void**)&t->d_ctr, sizeof(Counters)));
+    ck(cudaHostAlloc((void**)&t->h_ctr, sizeof(Counters), cudaHostAllocDefault));
+    for (auto& e : t->ev) ck(cudaEventCreate(&e));
+    for (auto& e : t->ev_copied) ck(cudaEventCreateWithFlags(&e, cudaEventDisableTiming));
+    for (auto& e : t->ev_consumed) ck(cudaEventCreateWithFlags(&e, cudaEventDisableTiming));
+    if (rc != KH_OK) { fprintf(stderr, "libkh_b200: kh_create: %s\n", t->err.c_str()); return bail(rc); }
+    ck(cudaMemsetAsync(t->table, 0, t->table_bytes, t->stream));
+    ck(cudaMemsetAsync(t->d_ctr, 0, sizeof(Counters), t->stream));
+    ck(cudaStreamSynchronize(t->stream));
+    if (rc != KH_OK) return bail(rc);
+    memset(t->h_ctr, 0, sizeof(Counters));
+    int v = env_int("KH_SPLIT_BUCKETS", 0);
+    if (v > 0 && set_option(t, "split_buckets", v) != KH_OK) fprintf(stderr, "libkh_b200: ignoring KH_SPLIT_BUCKETS=%d\n", v);
+    v = env_int("KH_SEG_CHARS", 0);
+    if (v > 0 && set_option(t, "seg_chars", v) != KH_OK) fprintf(stderr, "libkh_b200: ignoring KH_SEG_CHARS=%d\n", v);
+    t->err.clear();
+    *out = t;
+    return KH_OK;
+}
+
+int kh_destroy(kh_table* t) {
+    if (!t) return KH_OK;
+    cudaSetDevice(t->device);
+    if (t->own_stream) cudaStreamSynchronize(t->own_stream);
+    DevBuf* bufs[] = {&t->starts, &t->mask, &t->tile_counts, &t->tile_offs, &t->scan_blocks, &t->link, &t->seglen,
+                      &t->tmp, &t->contig_len, &t->contig_pre, &t->contig_off, &t->out, &t->stage[0], &t->stage[1],
+                      &t->text_stage, &t->scratch_a, &t->scratch_b, &t->scratch_c};
+    for (DevBuf* b : bufs) if (b->p) cudaFree(b->p);
+    if (t->table) cudaFree(t->table);
+    if (t->d_ctr) cudaFree(t->d_ctr);
+    if (t->h_ctr) cudaFreeHost(t->h_ctr);
+    if (t->h_out) cudaFreeHost(t->h_out);
+    if (t->h_off) cudaFreeHost(t->h_off);
+    for (auto& e : t->ev) if (e) cudaEventDestroy(e);
+    for (auto& e : t->ev_copied) if (e) cudaEventDestroy(e);
+    for (auto& e : t->ev_consumed) if (e) cudaEventDestroy(e);
+    if (t->own_stream) cudaStreamDestroy(t->own_stream);
+    if (t->copy_stream) cudaStreamDestroy(t->copy_stream);
+    cudaGetLastError();
+    delete t;
+    return KH_OK;
+}
+
+int kh_clear(kh_table* t) {
+    if (!t) return KH_ERR_ARG;
+    KH_CUDA(t, cudaSetDevice(t->device));
+    KH_CUDA(t, cudaEventRecord(t->ev[EV_CLR0], t->stream));
+    KH_CUDA(t, cudaMemsetAsync(t->table, 0, t->table_bytes, t->stream));
+    KH_CUDA(t, cudaMemsetAsync(t->d_ctr, 0, sizeof(Counters), t->stream));
+    KH_CUDA(t, cudaEventRecord(t->ev[EV_CLR1], t->stream));
+    t->have_clr = true;
+    t->n_starts = 0;
+    memset(t->h_ctr, 0, sizeof(Counters));
+    t->stats.n_contigs = t->stats.n_nodes = t->stats.contig_bytes = t->stats.n_segments = 0;
+    t->last_contig_bytes = t->last_n_contigs = 0;
+    return KH_OK;
+}
+
+int kh_set_stream(kh_table* t, void* cuda_stream) {
+    if (!t) return KH_ERR_ARG;
+    KH_CUDA(t, cudaSetDevice(t->device));
+    KH_CUDA(t, cudaStreamSynchronize(t->stream));
+    t->stream = cuda_stream ? static_cast<cudaStream_t>(cuda_stream) : t->own_stream;
+    return KH_OK;
+}
+
+int kh_sync(kh_table* t) {
+    if (!t) return KH_ERR_ARG;
+    KH_CUDA(t, cudaSetDevice(t->device));
+    KH_CUDA(t, cudaStreamSynchronize(t->stream));
+    return KH_OK;
+}
+
+int kh_set_option(kh_table* t, const char* name, int64_t value) {
+    if (!t || !name) return KH_ERR_ARG;
+    return set_option(t, name, value);
+}
+
+int kh_pack_lines_device(kh_table* t, const void* text_dev, uint64_t n_lines, void* pairs_dev_out) {
+    if (!t || (n_lines && (!text_dev || !pairs_dev_out))) return KH_ERR_ARG;
+    KH_CUDA(t, cudaSetDevice(t->device));
+    KH_CUDA(t, cudaEventRecord(t->ev[EV_PACK0], t->stream));
+    KH_TRY(pack_device(t, text_dev, n_lines, pairs_dev_out));
+    KH_CUDA(t, cudaEventRecord(t->ev[EV_PACK1], t->stream));
+    t->have_pack = true;
+    return KH_OK;
+}
+
+static const uint64_t kChunkBytes = 64ull << 20;
+
+int kh_pack_lines(kh_table* t, const char* text_host, uint64_t n_lines, void* pairs_host_out) {
+    if (!t || (n_lines && (!text_host || !pairs_host_out))) return KH_ERR_ARG;
+    KH_CUDA(t, cudaSetDevice(t->device));
+    const u64 ll = t->k + 4;
+    const u64 chunk = std::max<u64>(kPackLines, (kChunkBytes / ll) / kPackLines * kPackLines);
+    KH_TRY(ensure(t, t->text_stage, std::min<u64>(n_lines, chunk) * ll));
+    KH_TRY(ensure(t, t->scratch_a, std::min<u64>(n_lines, chunk) * t->pb));
+    KH_CUDA(t, cudaEventRecord(t->ev[EV_PACK0], t->stream));
+    for (u64 l0 = 0; l0 < n_lines; l0 += chunk) {
+        const u64 cnt = std::min<u64>(chunk, n_lines - l0);
+        KH_CUDA(t, cudaMemcpyAsync(t->text_stage.p, text_host + l0 * ll, cnt * ll, cudaMemcpyHostToDevice, t->stream));
+        KH_TRY(pack_device(t, t->text_stage.p, cnt, t->scratch_a.p));
+        KH_CUDA(t, cudaMemcpyAsync(static_cast<char*>(pairs_host_out) + l0 * t->pb, t->scratch_a.p, cnt * t->pb,
+                                   cudaMemcpyDeviceToHost, t->stream));
+    }
+    KH_CUDA(t, cudaEventRecord(t->ev[EV_PACK1], t->stream));
+    t->have_pack = true;
+    KH_TRY(read_counters(t));
+    const u32 e = t->h_ctr->errors;
+    if (e) { clear_error_bits(t); return status_from_errors(t, e); }
+    return KH_OK;
+}
+
+int kh_insert_pairs_device(kh_table* t, const void* pairs_dev, uint64_t n) {
+    if (!t || (n && !pairs_dev)) return KH_ERR_ARG;
+    KH_CUDA(t, cudaSetDevice(t->device));
+    return insert_device(t, pairs_dev, n);
+}
+
+// Host records: double-buffered H2D on a copy stream overlapped with the insert kernels.
+int kh_insert_pairs(kh_table* t, const void* pairs_host, uint64_t n) {
+    if (!t || (n && !pairs_host)) return KH_ERR_ARG;
+    if (n == 0) return KH_OK;
+    KH_CUDA(t, cudaSetDevice(t->device));
+    const u64 chunk = std::max<u64>(kInsTile, (kChunkBytes / t->pb) / kInsTile * kInsTile);
+    const u64 nchunks = (n + chunk - 1) / chunk;
+    for (int i = 0; i < (nchunks > 1 ? 2 : 1); ++i) KH_TRY(ensure(t, t->stage[i], std::min<u64>(n, chunk) * t->pb));
+    const char* src = static_cast<const char*>(pairs_host);
+    auto issue_copy = [&](u64 c) -> int {
+        const u64 off = c * chunk, cnt = std::min<u64>(chunk, n - off);
+        if (c >= 2) KH_CUDA(t, cudaStreamWaitEvent(t->copy_stream, t->ev_consumed[c & 1], 0));
+        KH_CUDA(t, cudaMemcpyAsync(t->stage[c & 1].p, src + off * t->pb, cnt * t->pb, cudaMemcpyHostToDevice, t->copy_stream));
+        KH_CUDA(t, cudaEventRecord(t->ev_copied[c & 1], t->copy_stream));
+        return KH_OK;
+    };
+    KH_CUDA(t, cudaEventRecord(t->ev[EV_INS0], t->stream));
+    // the copy stream must not start before earlier work on the main stream that may still read the staging buffers
+    KH_CUDA(t, cudaEventRecord(t->ev_consumed[0], t->stream));
+    KH_CUDA(t, cudaStreamWaitEvent(t->copy_stream, t->ev_consumed[0], 0));
+    KH_TRY(issue_copy(0));
+    for (u64 c = 0; c < nchunks; ++c) {
+        if (c + 1 < nchunks) KH_TRY(issue_copy(c + 1));
+        const u64 off = c * chunk, cnt = std::min<u64>(chunk, n - off);
+        KH_CUDA(t, cudaStreamWaitEvent(t->stream, t->ev_copied[c & 1], 0));
+        KH_TRY(insert_device(t, t->stage[c & 1].p, cnt, /*record_start=*/false));
+        KH_CUDA(t, cudaEventRecord(t->ev_consumed[c & 1], t->stream));
+    }
+    return KH_OK;
+}
+
+int kh_insert_lines(kh_table* t, const char* text_host, uint64_t n_lines) {
+    if (!t || (n_lines && !text_host)) return KH_ERR_ARG;
+    if (n_lines == 0) return KH_OK;
+    KH_CUDA(t, cudaSetDevice(t->device));
+    const u64 ll = t->k + 4;
+    const u64 chunk = std::max<u64>(kInsTile, (kChunkBytes / ll) / kInsTile * kInsTile);
+    KH_TRY(ensure(t, t->text_stage, std::min<u64>(n_lines, chunk) * ll));
+    KH_TRY(ensure(t, t->scratch_a, std::min<u64>(n_lines, chunk) * t->pb));
+    KH_CUDA(t, cudaEventRecord(t->ev[EV_INS0], t->stream));
+    for (u64 l0 = 0; l0 < n_lines; l0 += chunk) {
+        const u64 cnt = std::min<u64>(chunk, n_lines - l0);
+        KH_CUDA(t, cudaMemcpyAsync(t->text_stage.p, text_host + l0 * ll, cnt * ll, cudaMemcpyHostToDevice, t->stream));
+        KH_TRY(pack_device(t, t->text_stage.p, cnt, t->scratch_a.p));
+        KH_TRY(insert_device(t, t->scratch_a.p, cnt, /*record_start=*/false));
+    }
+    return KH_OK;
+}
+
+int kh_find_device(kh_table* t, const void* pkmers_dev, uint64_t n, void* pairs_dev_out, uint8_t* found_dev_out) {
+    if (!t || (n && (!pkmers_dev || !pairs_dev_out || !found_dev_out))) return KH_ERR_ARG;
+    if (n == 0) return KH_OK;
+    KH_CUDA(t, cudaSetDevice(t->device));
+    const unsigned blocks = (unsigned)((n + 255) / 256);
+    if (t->W == 1)
+        find_kernel<1><<<blocks, 256, 0, t->stream>>>(static_cast<const u64*>(t->table), t->nbuckets, t->k,
+            static_cast<const unsigned char*>(pkmers_dev), n, static_cast<unsigned char*>(pairs_dev_out), found_dev_out);
+    else
+        find_kernel<2><<<blocks, 256, 0, t->stream>>>(static_cast<const u128*>(t->table), t->nbuckets, t->k,
+            static_cast<const unsigned char*>(pkmers_dev), n, static_cast<unsigned char*>(pairs_dev_out), found_dev_out);
+    KH_CUDA(t, cudaGetLastError());
+    return KH_OK;
+}
+
+int kh_find(kh_table* t, const void* pkmers_host, uint64_t n, void* pairs_host_out, uint8_t* found_host_out) {
+    if (!t || (n && (!pkmers_host || !pairs_host_out || !found_host_out))) return KH_ERR_ARG;
+    if (n == 0) return KH_OK;
+    KH_CUDA(t, cudaSetDevice(t->device));
+    KH_TRY(ensure(t, t->scratch_a, n * t->pl));
+    KH_TRY(ensure(t, t->scratch_b, n * t->pb));
+    KH_TRY(ensure(t, t->scratch_c, n));
+    KH_CUDA(t, cudaMemcpyAsync(t->scratch_a.p, pkmers_host, n * t->pl, cudaMemcpyHostToDevice, t->stream));
+    KH_TRY(kh_find_device(t, t->scratch_a.p, n, t->scratch_b.p, static_cast<uint8_t*>(t->scratch_c.p)));
+    KH_CUDA(t, cudaMemcpyAsync(pairs_host_out, t->scratch_b.p, n * t->pb, cudaMemcpyDeviceToHost, t->stream));
+    KH_CUDA(t, cudaMemcpyAsync(found_host_out, t->scratch_c.p, n, cudaMemcpyDeviceToHost, t->stream));
+    KH_CUDA(t, cudaStreamSynchronize(t->stream));
+    return KH_OK;
+}
+
+int kh_assemble_device(kh_table* t, const char** contigs_dev, const uint64_t** offsets_dev,
+                       uint64_t* n_contigs, uint64_t* contig_bytes, uint64_t* n_nodes) {
+    if (!t) return KH_ERR_ARG;
+    KH_CUDA(t, cudaSetDevice(t->device));
+    const int rc = assemble_device(t);
+    if (contigs_dev) *contigs_dev = static_cast<const char*>(t->out.p);
+    if (offsets_dev) *offsets_dev = static_cast<const uint64_t*>(t->contig_off.p);
+    if (n_contigs) *n_contigs = t->stats.n_contigs;
+    if (contig_bytes) *contig_bytes = rc == KH_OK ? t->stats.contig_bytes : 0;
+    if (n_nodes) *n_nodes = t->stats.n_nodes;
+    return rc;
+}
+
+int kh_assemble(kh_table* t, const char** contigs_host, const uint64_t** offsets_host,
+                uint64_t* n_contigs, uint64_t* contig_bytes, uint64_t* n_nodes) {
+    if (!t) return KH_ERR_ARG;
+    KH_CUDA(t, cudaSetDevice(t->device));
+    // size the pinned landing buffers before the timed work so steady-state calls allocate nothing
+    const u64 cap_guess = t->h_ctr->n_inserted + t->n_starts * (u64)(t->k + 1) + 64;
+    KH_TRY(ensure_pinned(t, t->h_out, t->h_out_cap, cap_guess));
+    KH_TRY(ensure_pinned(t, t->h_off, t->h_off_cap, (t->n_starts + 1) * sizeof(u64)));
+    const int rc = assemble_device(t);
+    if (n_contigs) *n_contigs = t->stats.n_contigs;
+    if (n_nodes) *n_nodes = t->stats.n_nodes;
+    if (contig_bytes) *contig_bytes = 0;
+    if (contigs_host) *contigs_host = static_cast<const char*>(t->h_out);
+    if (offsets_host) *offsets_host = static_cast<const uint64_t*>(t->h_off);
+    if (rc != KH_OK) return rc;
+    const u64 bytes = t->stats.contig_bytes;
+    if (bytes) KH_CUDA(t, cudaMemcpyAsync(t->h_out, t->out.p, bytes, cudaMemcpyDeviceToHost, t->stream));
+    KH_CUDA(t, cudaMemcpyAsync(t->h_off, t->contig_off.p, (t->n_starts + 1) * sizeof(u64), cudaMemcpyDeviceToHost, t->stream));
+    KH_CUDA(t, cudaStreamSynchronize(t->stream));
+    if (contig_bytes) *contig_bytes = bytes;
+    return KH_OK;
+}
+
+int kh_get_stats(kh_table* t, kh_stats* out) {
+    if (!t || !out) return KH_ERR_ARG;
+    KH_CUDA(t, cudaSetDevice(t->device));
+    KH_CUDA(t, cudaStreamSynchronize(t->stream));
+    kh_stats& s = t->stats;
+    s.n_buckets = t->nbuckets;
+    s.n_slots = t->nbuckets * t->per_bucket;
+    s.n_inserted = t->h_ctr->n_inserted;
+    s.n_duplicates = t->h_ctr->n_duplicates;
+    s.n_starts = t->n_starts;
+    s.slot_bits = t->W == 1 ? 64 : 128;
+    if (t->have_ins) s.ms_insert = elapsed(t->ev[EV_INS0], t->ev[EV_INS1]);
+    if (t->have_as) {
+        s.ms_assemble = elapsed(t->ev[EV_AS0], t->ev[EV_AS1]);
+        s.ms_walk = elapsed(t->ev[EV_AS0], t->ev[EV_WALK]);
+        s.ms_rank = elapsed(t->ev[EV_WALK], t->ev[EV_RANK]);
+        s.ms_emit = elapsed(t->ev[EV_RANK], t->ev[EV_AS1]);
+    }
+    if (t->have_pack) s.ms_pack = elapsed(t->ev[EV_PACK0], t->ev[EV_PACK1]);
+    if (t->have_clr) s.ms_clear = elapsed(t->ev[EV_CLR0], t->ev[EV_CLR1]);
+    *out = s;
+    return KH_OK;
+}
+
+const char* kh_last_error(kh_table* t) { return t ? t->err.c_str() : "null handle"; }
+
+int kh_host_alloc(void** ptr, uint64_t bytes) {
+    if (!ptr) return KH_ERR_ARG;
+    if (cudaHostAlloc(ptr, bytes ? bytes : 1, cudaHostAllocDefault) != cudaSuccess) { cudaGetLastError(); *ptr = nullptr; return KH_ERR_NOMEM; }
+    return KH_OK;
+}
+int kh_host_free(void* ptr) {
+    if (ptr && cudaFreeHost(ptr) != cudaSuccess) { cudaGetLastError(); return KH_ERR_CUDA; }
+    return KH_OK;
+}
+
+int kh_measure_random_sector_rate(int device, uint64_t footprint_bytes, uint64_t n_probes, double* sectors_per_s) {
+    if (!sectors_per_s || footprint_bytes < 4096) return KH_ERR_ARG;
+    if (cudaSetDevice(device) != cudaSuccess) { cudaGetLastError(); return KH_ERR_CUDA; }
+    cudaDeviceProp prop;
+    if (cudaGetDeviceProperties(&prop, device) != cudaSuccess) return KH_ERR_CUDA;
+    const int gran = env_int("KH_L2_FETCH_BYTES", 32);
+    if (gran > 0) { cudaDeviceSetLimit(cudaLimitMaxL2FetchGranularity, (size_t)gran); cudaGetLastError(); }
+    void* buf = nullptr; u64* sink = nullptr;
+    if (cudaMalloc(&buf, footprint_bytes) != cudaSuccess) { cudaGetLastError(); return KH_ERR_NOMEM; }
+    cudaMalloc((void**)&sink, 8);
+    cudaMemset(buf, 1, footprint_bytes);
+    const unsigned blocks = (unsigned)prop.multiProcessorCount * 8;
+    const u64 threads = (u64)blocks * 256;
+    const u64 per = std::max<u64>(4, (n_probes / threads + 3) / 4 * 4);
+    cudaEvent_t a, b;
+    cudaEventCreate(&a); cudaEventCreate(&b);
+    random_sector_kernel<<<blocks, 256>>>(static_cast<const u64*>(buf), footprint_bytes / 32, per, sink);   // warm-up
+    cudaEventRecord(a);
+    random_sector_kernel<<<blocks, 256>>>(static_cast<const u64*>(buf), footprint_bytes / 32, per, sink);
+    cudaEventRecord(b);
+    const cudaError_t e = cudaEventSynchronize(b);
+    float ms = 0.f;
+    cudaEventElapsedTime(&ms, a, b);
+    cudaEventDestroy(a); cudaEventDestroy(b);
+    cudaFree(buf); cudaFree(sink);
+    if (e != cudaSuccess || ms <= 0.f) { cudaGetLastError(); return KH_ERR_CUDA; }
+    *sectors_per_s = (double)(per * threads) / (ms * 1e-3);
+    return KH_OK;
+}
+
+}  // extern "C"

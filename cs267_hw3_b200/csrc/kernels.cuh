@@ -1,0 +1,677 @@
+// kernels.cuh -- the sm_100a kernels of the k-mer hash / contig traversal path.
+//
+//   K1 pack_lines_kernel     text lines -> kmer_pair records          (read_kmers.hpp:72-76, packing.hpp:50-92)
+//   K2 insert_kernel         records -> open-addressing table, + start-node bitmask
+//                                                                      (hash_map.hpp:55-72, kmer_hash.cpp:27-31)
+//   K3 scatter_starts_kernel bitmask -> start list in file order       (kmer_hash.cpp:27-31)
+//   K4 find_kernel           batch lookup                              (hash_map.hpp:83-92)
+//   K5 walk_kernel           one lane per walk segment                 (kmer_hash.cpp:38-55, kmer_t.hpp:51-53)
+//      rank_kernel           pointer jumping over the segment list
+//   K6 emit_*_kernel         contig text                               (read_kmers.hpp:81-92)
+//
+// All of it is HBM-bound integer work: no tensor cores, no floating point.
+#pragma once
+#include <cooperative_groups.h>
+
+#include "slot.cuh"
+
+namespace kh {
+namespace cg = cooperative_groups;
+
+constexpr u32 kFullMask = 0xFFFFFFFFu;
+
+__device__ __forceinline__ u32 lane_id() { return threadIdx.x & 31u; }
+__device__ __forceinline__ u64 warp_sum_u64(u64 x) {
+#pragma unroll
+    for (int d = 16; d > 0; d >>= 1) x += __shfl_xor_sync(kFullMask, x, d);
+    return x;
+}
+
+// Cooperative copy global -> shared of `bytes` bytes (16-byte vectors when aligned).
+__device__ __forceinline__ void stage_in(unsigned char* s_dst, const unsigned char* g_src, u32 bytes) {
+    if ((reinterpret_cast<uintptr_t>(g_src) & 15u) == 0) {
+        const u32 nv = bytes >> 4;
+        const uint4* s4 = reinterpret_cast<const uint4*>(g_src);
+        uint4* d4 = reinterpret_cast<uint4*>(s_dst);
+        for (u32 i = threadIdx.x; i < nv; i += blockDim.x) d4[i] = load128_stream(s4 + i);
+        for (u32 i = (nv << 4) + threadIdx.x; i < bytes; i += blockDim.x) s_dst[i] = g_src[i];
+    } else {
+        for (u32 i = threadIdx.x; i < bytes; i += blockDim.x) s_dst[i] = g_src[i];
+    }
+}
+__device__ __forceinline__ void stage_out(unsigned char* g_dst, const unsigned char* s_src, u32 bytes) {
+    if ((reinterpret_cast<uintptr_t>(g_dst) & 15u) == 0) {
+        const u32 nv = bytes >> 4;
+        const uint4* s4 = reinterpret_cast<const uint4*>(s_src);
+        uint4* d4 = reinterpret_cast<uint4*>(g_dst);
+        for (u32 i = threadIdx.x; i < nv; i += blockDim.x) d4[i] = s4[i];
+        for (u32 i = (nv << 4) + threadIdx.x; i < bytes; i += blockDim.x) g_dst[i] = s_src[i];
+    } else {
+        for (u32 i = threadIdx.x; i < bytes; i += blockDim.x) g_dst[i] = s_src[i];
+    }
+}
+
+// =========================================================================================
+// K1  pack: (K+4)-byte text lines -> reference kmer_pair bytes
+// =========================================================================================
+constexpr int kPackLines = 256;   // lines per block; 256*(K+4) is a multiple of 16 for every K
+
+__global__ void __launch_bounds__(kPackLines)
+pack_lines_kernel(const unsigned char* __restrict__ text, u64 n_lines, int k,
+                  unsigned char* __restrict__ pairs, Counters* ctr) {
+    extern __shared__ __align__(16) unsigned char smem[];
+    const int ll = k + 4, pl = (k + 3) >> 2, pb = pl + 2;
+    unsigned char* s_in = smem;
+    unsigned char* s_out = smem + (((u32)kPackLines * ll + 15u) & ~15u);
+    const u64 line0 = (u64)blockIdx.x * kPackLines;
+    const u32 cnt = (u32)min((u64)kPackLines, n_lines - line0);
+    stage_in(s_in, text + line0 * ll, cnt * ll);
+    __syncthreads();
+    if (threadIdx.x < cnt) {
+        const unsigned char* line = s_in + threadIdx.x * ll;
+        unsigned char* rec = s_out + threadIdx.x * pb;
+        bool ok = true;
+        for (int q = 0; q < pl; ++q) {
+            u32 v = 0;
+#pragma unroll
+            for (int j = 0; j < 4; ++j) {
+                const int idx = 4 * q + j;
+                u32 code = 0;                       // packing.hpp:85-91: the tail is padded with 'A'
+                if (idx < k) {
+                    const unsigned char c = line[idx];
+                    ok = ok && is_base(c);
+                    code = base_code_fast(c);
+                }
+                v = (v << 2) | code;
+            }
+            rec[q] = (unsigned char)v;
+        }
+        const unsigned char b = line[k + 1], f = line[k + 2];   // byte k is a separator nobody reads
+        ok = ok && ext_code(b) != kExtBad && ext_code(f) != kExtBad;
+        rec[pl] = b;
+        rec[pl + 1] = f;
+        if (!ok) atomicOr(&ctr->errors, kErrBadInput);
+    }
+    __syncthreads();
+    stage_out(pairs + line0 * pb, s_out, cnt * pb);
+}
+
+// =========================================================================================
+// K2  insert (+ the start-node bitmask K3 consumes)
+// =========================================================================================
+constexpr int kInsThreads = 256;
+constexpr int kInsPerThread = 4;
+constexpr int kInsTile = kInsThreads * kInsPerThread;    // 1024 records per block
+
+enum { kInsInserted = 0, kInsDuplicate = 1, kInsFull = 2 };
+
+// Claim the first empty slot of the probe sequence starting at bucket b (q = preloaded bucket b).
+// Slots inside a bucket fill in order and are never released, so a reader may stop at the first
+// empty slot.  First writer wins on a duplicate key.
+template <int W>
+__device__ __forceinline__ int insert_one(typename Slot<W>::value_t* table, u64 nbuckets, u64 b,
+                                          typename Slot<W>::value_t v, u64 (&q)[4]) {
+    typedef Slot<W> S;
+    for (u64 tries = 0; tries < nbuckets; ++tries) {
+#pragma unroll
+        for (int i = 0; i < S::kPerBucket; ++i) {
+            typename S::value_t cur = S::from_bucket(q, i);
+            if (S::empty(cur)) {
+                cur = S::cas(table + b * S::kPerBucket + i, S::zero(), v);
+                if (S::empty(cur)) return kInsInserted;
+            }
+            if (S::same_key(cur, v)) return kInsDuplicate;
+        }
+        b = (b + 1 == nbuckets) ? 0 : b + 1;
+        load256_cg(table + b * S::kPerBucket, q);
+    }
+    return kInsFull;
+}
+
+template <int W>
+__global__ void __launch_bounds__(kInsThreads)
+insert_kernel(const unsigned char* __restrict__ recs, u64 n, int k,
+              typename Slot<W>::value_t* table, u64 nbuckets,
+              u32* __restrict__ start_mask, u32* __restrict__ tile_starts, Counters* ctr) {
+    typedef Slot<W> S;
+    typedef typename S::value_t V;
+    extern __shared__ __align__(16) unsigned char s_rec[];
+    __shared__ u32 s_starts, s_inserted, s_dups, s_err;
+    const int pl = (k + 3) >> 2, pb = pl + 2;
+    const u64 rec0 = (u64)blockIdx.x * kInsTile;
+    const u32 cnt = (u32)min((u64)kInsTile, n - rec0);
+    if (threadIdx.x == 0) { s_starts = 0; s_inserted = 0; s_dups = 0; s_err = 0; }
+    stage_in(s_rec, recs + rec0 * pb, cnt * pb);
+    __syncthreads();
+
+    V v[kInsPerThread];
+    u64 b[kInsPerThread];
+    u64 q[kInsPerThread][4];
+    bool live[kInsPerThread];
+    u32 err = 0, starts = 0;
+#pragma unroll
+    for (int r = 0; r < kInsPerThread; ++r) {
+        const u32 j = threadIdx.x + r * kInsThreads;
+        live[r] = j < cnt;
+        bool ok = true;
+        v[r] = S::zero();
+        if (live[r]) v[r] = S::from_record(s_rec + j * pb, k, pl, ok);
+        if (!ok) { err |= kErrBadInput; live[r] = false; }
+        b[r] = live[r] ? bucket_of(S::hash(v[r]), nbuckets) : 0;
+        if (live[r]) load256_cg(table + b[r] * S::kPerBucket, q[r]);      // 4 independent sector reads in flight
+        // kmer_hash.cpp:27-31: remember which records start a contig, by position in the input
+        const u32 m = __ballot_sync(kFullMask, live[r] && S::back(v[r]) == kExtF);
+        const u64 word = (rec0 + (u64)r * kInsThreads + (threadIdx.x & ~31u)) >> 5;
+        if (lane_id() == 0 && (word << 5) < n) { start_mask[word] = m; starts += __popc(m); }
+    }
+    u32 inserted = 0, dups = 0;
+#pragma unroll
+    for (int r = 0; r < kInsPerThread; ++r) {
+        if (!live[r]) continue;
+        const int rc = insert_one<W>(table, nbuckets, b[r], v[r], q[r]);
+        inserted += (rc == kInsInserted);
+        dups += (rc == kInsDuplicate);
+        if (rc == kInsFull) err |= kErrTableFull;
+    }
+    // block totals -> one atomic each
+    inserted = __reduce_add_sync(kFullMask, inserted);
+    dups = __reduce_add_sync(kFullMask, dups);
+    err = __reduce_or_sync(kFullMask, err);
+    if (lane_id() == 0) {
+        if (starts) atomicAdd(&s_starts, starts);
+        if (inserted) atomicAdd(&s_inserted, inserted);
+        if (dups) atomicAdd(&s_dups, dups);
+        if (err) atomicOr(&s_err, err);
+    }
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        tile_starts[blockIdx.x] = s_starts;
+        if (s_inserted) atomicAdd(&ctr->n_inserted, (u64)s_inserted);
+        if (s_dups) atomicAdd(&ctr->n_duplicates, (u64)s_dups);
+        if (s_err) atomicOr(&ctr->errors, s_err);
+    }
+}
+
+// =========================================================================================
+// exclusive scan of u32 counts -> u64 offsets (three small kernels)
+// =========================================================================================
+constexpr int kScanThreads = 256;
+constexpr int kScanPerThread = 8;
+constexpr int kScanTile = kScanThreads * kScanPerThread;   // 2048
+
+__device__ __forceinline__ u64 block_exclusive_scan(u64 x, u64* s_warp, u64& block_total) {
+    // inclusive warp scan
+    u64 inc = x;
+#pragma unroll
+    for (int d = 1; d < 32; d <<= 1) {
+        const u64 y = __shfl_up_sync(kFullMask, inc, d);
+        if (lane_id() >= (u32)d) inc += y;
+    }
+    const u32 warp = threadIdx.x >> 5, nwarps = blockDim.x >> 5;
+    if (lane_id() == 31) s_warp[warp] = inc;
+    __syncthreads();
+    if (warp == 0) {
+        u64 w = lane_id() < nwarps ? s_warp[lane_id()] : 0;
+        u64 winc = w;
+#pragma unroll
+        for (int d = 1; d < 32; d <<= 1) {
+            const u64 y = __shfl_up_sync(kFullMask, winc, d);
+            if (lane_id() >= (u32)d) winc += y;
+        }
+        if (lane_id() < nwarps) s_warp[lane_id()] = winc - w;      // exclusive warp bases
+        if (lane_id() == 31) s_warp[32] = winc;                    // block total
+    }
+    __syncthreads();
+    block_total = s_warp[32];
+    const u64 r = s_warp[warp] + inc - x;
+    __syncthreads();
+    return r;
+}
+
+__global__ void __launch_bounds__(kScanThreads)
+scan_reduce_kernel(const u32* __restrict__ in, u64 n, u64* __restrict__ block_sums) {
+    __shared__ u64 s_warp[33];
+    const u64 base = (u64)blockIdx.x * kScanTile;
+    u64 sum = 0;
+#pragma unroll
+    for (int j = 0; j < kScanPerThread; ++j) {
+        const u64 i = base + (u64)j * kScanThreads + threadIdx.x;
+        if (i < n) sum += in[i];
+    }
+    u64 total;
+    block_exclusive_scan(sum, s_warp, total);
+    if (threadIdx.x == 0) block_sums[blockIdx.x] = total;
+}
+
+// one block: exclusive scan of block_sums in place; total -> *total_out
+__global__ void __launch_bounds__(1024)
+scan_spine_kernel(u64* block_sums, u64 nblocks, u64* total_out) {
+    __shared__ u64 s_warp[33];
+    u64 carry = 0;
+    for (u64 base = 0; base < nblocks; base += blockDim.x) {
+        const u64 i = base + threadIdx.x;
+        const u64 x = i < nblocks ? block_sums[i] : 0;
+        u64 total;
+        const u64 ex = block_exclusive_scan(x, s_warp, total);
+        if (i < nblocks) block_sums[i] = carry + ex;
+        carry += total;
+    }
+    if (threadIdx.x == 0) *total_out = carry;
+}
+
+__global__ void __launch_bounds__(kScanThreads)
+scan_apply_kernel(const u32* __restrict__ in, u64 n, const u64* __restrict__ block_sums, u64* __restrict__ out) {
+    __shared__ u64 s_warp[33];
+    const u64 base = (u64)blockIdx.x * kScanTile + (u64)threadIdx.x * kScanPerThread;   // contiguous per thread
+    u32 x[kScanPerThread];
+    u64 sum = 0;
+#pragma unroll
+    for (int j = 0; j < kScanPerThread; ++j) {
+        x[j] = (base + j < n) ? in[base + j] : 0u;
+        sum += x[j];
+    }
+    u64 total;
+    u64 run = block_sums[blockIdx.x] + block_exclusive_scan(sum, s_warp, total);
+#pragma unroll
+    for (int j = 0; j < kScanPerThread; ++j) {
+        if (base + j < n) out[base + j] = run;
+        run += x[j];
+    }
+}
+
+// =========================================================================================
+// K3  start nodes: bitmask + per-tile offsets -> slot values in input order
+// =========================================================================================
+// One warp per insert tile (kInsTile records = 32 mask words).
+template <int W>
+__global__ void __launch_bounds__(256)
+scatter_starts_kernel(const unsigned char* __restrict__ recs, u64 n, int k,
+                      const u32* __restrict__ start_mask, const u64* __restrict__ tile_offsets, u64 ntiles,
+                      typename Slot<W>::value_t* __restrict__ starts_out, u64 out_base) {
+    typedef Slot<W> S;
+    const u64 tile = ((u64)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+    if (tile >= ntiles) return;
+    const int pl = (k + 3) >> 2, pb = pl + 2;
+    const u64 word = tile * (kInsTile / 32) + lane_id();
+    const u64 nwords = (n + 31) >> 5;
+    u32 m = word < nwords ? start_mask[word] : 0u;
+    // exclusive prefix of popcounts across the warp
+    u32 inc = __popc(m);
+    const u32 mine = inc;
+#pragma unroll
+    for (int d = 1; d < 32; d <<= 1) {
+        const u32 y = __shfl_up_sync(kFullMask, inc, d);
+        if (lane_id() >= (u32)d) inc += y;
+    }
+    u64 dst = out_base + tile_offsets[tile] + (inc - mine);
+    while (m) {
+        const int bit = __ffs(m) - 1;
+        m &= m - 1;
+        const u64 rec = (word << 5) + bit;
+        bool ok;
+        unsigned char tmp[18];
+        const unsigned char* src = recs + rec * pb;
+        for (int i = 0; i < pb; ++i) tmp[i] = src[i];
+        starts_out[dst++] = S::from_record(tmp, k, pl, ok);
+    }
+}
+
+// =========================================================================================
+// K4  lookup
+// =========================================================================================
+template <int W>
+__device__ __forceinline__ bool lookup(const typename Slot<W>::value_t* __restrict__ table, u64 nbuckets,
+                                       typename Slot<W>::value_t keybits, typename Slot<W>::value_t& found,
+                                       u64& bucket, int& slot) {
+    typedef Slot<W> S;
+    u64 b = bucket_of(S::hash(keybits), nbuckets);
+    for (u64 tries = 0; tries < nbuckets; ++tries) {
+        u64 q[4];
+        load256_nc(table + b * S::kPerBucket, q);
+#pragma unroll
+        for (int i = 0; i < S::kPerBucket; ++i) {
+            const typename S::value_t cur = S::from_bucket(q, i);
+            if (S::empty(cur)) return false;          // buckets fill in order: first hole ends the probe
+            if (S::same_key(cur, keybits)) { found = cur; bucket = b; slot = i; return true; }
+        }
+        b = (b + 1 == nbuckets) ? 0 : b + 1;
+    }
+    return false;
+}
+
+template <int W>
+__global__ void __launch_bounds__(256)
+find_kernel(const typename Slot<W>::value_t* __restrict__ table, u64 nbuckets, int k,
+            const unsigned char* __restrict__ pkmers, u64 n,
+            unsigned char* __restrict__ pairs_out, unsigned char* __restrict__ found_out) {
+    typedef Slot<W> S;
+    const u64 i = (u64)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    const int pl = (k + 3) >> 2, pb = pl + 2;
+    unsigned char key[16];
+    for (int j = 0; j < pl; ++j) key[j] = pkmers[i * pl + j];
+    typename S::value_t hit;
+    u64 b; int s;
+    const bool ok = lookup<W>(table, nbuckets, S::from_packed(key, k, pl), hit, b, s);
+    unsigned char rec[18];
+    for (int j = 0; j < pb; ++j) rec[j] = 0;
+    if (ok) S::to_record(hit, k, pl, rec);
+    for (int j = 0; j < pb; ++j) pairs_out[i * pb + j] = rec[j];
+    found_out[i] = ok ? 1 : 0;
+}
+
+// =========================================================================================
+// K5  walk: every k-mer is visited exactly once, by the lane that owns its segment
+// =========================================================================================
+// Walkers are (a) the start nodes, ids [0, n_starts), and (b) every `split_buckets`-th bucket's
+// first slot ("splitters"), ids [n_starts, n_starts + n_split).  A walker follows successors
+// (kmer_hash.cpp:44-51) and stops at forward ext 'F' or when the successor sits in a splitter
+// slot -- that node belongs to the splitter's own walker.  So a chain of any length is cut into
+// independent pieces of geometric length and no contig serialises on one lane; rank_kernel then
+// stitches the pieces with pointer jumping.  Each piece's forward-extension characters go to
+// tmp[seg * seg_chars ...]; a piece longer than seg_chars continues in an overflow segment.
+//
+//   link[seg] = (next segment id << 32) | chars in this segment     (kLinkTail: ends the contig)
+struct WalkParams {
+    const void* table;
+    u64 nbuckets;
+    const void* starts;
+    u64* link;
+    unsigned char* seglen;
+    unsigned char* tmp;
+    Counters* ctr;
+    u32 n_starts;
+    u32 n_split;
+    u32 split_shift;      // split_buckets = 1 << split_shift
+    u32 seg_chars;        // multiple of 8
+    u32 seg_cap;          // capacity of link/seglen/tmp in segments
+    int k;
+};
+
+constexpr u32 kWalkBatch = 128;     // walker ids a warp takes per global atomic
+constexpr u32 kSegBatch = 32;       // overflow segment ids a warp takes per global atomic
+constexpr int kWalkThreads = 256;
+
+template <int W>
+__global__ void __launch_bounds__(kWalkThreads)
+walk_kernel(const WalkParams p) {
+    typedef Slot<W> S;
+    typedef typename S::value_t V;
+    const V* __restrict__ table = static_cast<const V*>(p.table);
+    const V* __restrict__ starts = static_cast<const V*>(p.starts);
+    const u32 total = p.n_starts + p.n_split;
+    const u32 lane = lane_id();
+    const u32 lt_mask = (1u << lane) - 1u;
+    const u64 split_mask = (1ull << p.split_shift) - 1ull;
+
+    // warp-uniform pools
+    u32 w_next = 0, w_end = 0;      // walker ids
+    bool exhausted = false;
+    u32 o_next = 0, o_end = 0;      // overflow segment ids
+
+    // lane state
+    bool active = false;
+    V cur = S::zero(), chk = S::zero();
+    u32 seg = 0, n = 0, steps = 0, limit = 256;
+    u64 acc = 0;
+
+    auto close = [&](u32 next) {
+        if (n & 7u) *reinterpret_cast<u64*>(p.tmp + (u64)seg * p.seg_chars + (n & ~7u)) = acc;
+        p.seglen[seg] = (unsigned char)n;
+        p.link[seg] = ((u64)next << 32) | (next == kLinkTail ? 0u : n);
+        active = false;
+    };
+
+    for (;;) {
+        __syncwarp();
+        // ---- hand out new walkers to idle lanes ----
+        const u32 idle = __ballot_sync(kFullMask, !active);
+        if (idle && !exhausted) {
+            if (w_next == w_end) {
+                u32 base = 0;
+                if (lane == 0) base = atomicAdd(&p.ctr->next_walker, kWalkBatch);
+                base = __shfl_sync(kFullMask, base, 0);
+                w_next = min(base, total);
+                w_end = min(base + kWalkBatch, total);    // base + batch cannot wrap: total < 2^32 - batch*grid
+                exhausted = (w_next == w_end);
+            }
+            const u32 avail = w_end - w_next;
+            const u32 rank = __popc(idle & lt_mask);
+            if (!active && rank < avail) {
+                const u32 w = w_next + rank;
+                seg = w; n = 0; acc = 0; steps = 0; limit = 256;
+                if (w < p.n_starts) {
+                    cur = starts[w];
+                    active = true;
+                } else {
+                    const u64 b = (u64)(w - p.n_starts) << p.split_shift;
+                    cur = S::load_one_nc(table + b * S::kPerBucket);
+                    if (S::empty(cur)) p.link[seg] = (u64)kLinkUnused << 32;
+                    else active = true;
+                }
+                chk = cur;
+            }
+            w_next += min((u32)__popc(idle), avail);
+        }
+        if (__ballot_sync(kFullMask, active) == 0) {
+            if (exhausted) break;
+            continue;
+        }
+        // ---- lanes whose segment buffer is full move to an overflow segment ----
+        const u32 full = __ballot_sync(kFullMask, active && n == p.seg_chars && S::fwd(cur) != kExtF);
+        if (full) {
+            const u32 want = __popc(full);
+            if (o_end - o_next < want) {
+                // return nothing: leftover ids of the old pool are marked unused below
+                for (u32 id = o_next + lane; id < o_end; id += 32) p.link[id] = (u64)kLinkUnused << 32;
+                u32 base = 0;
+                if (lane == 0) base = atomicAdd(&p.ctr->next_seg, kSegBatch);
+                base = __shfl_sync(kFullMask, base, 0);
+                o_next = base; o_end = base + kSegBatch;
+            }
+            if (full & (1u << lane)) {
+                const u32 ns = o_next + __popc(full & lt_mask);
+                if (ns >= p.seg_cap) {            // cannot happen when seg_cap is sized as in capi.cu
+                    atomicOr(&p.ctr->errors, kErrInternal);
+                    close(kLinkTail);
+                } else {
+                    close(ns);
+                    active = true; seg = ns; n = 0; acc = 0;
+                }
+            }
+            o_next += want;
+        }
+        // ---- one step of kmer_hash.cpp:44-51 per active lane ----
+        if (active) {
+            const u32 f = S::fwd(cur);
+            if (f == kExtF) {
+                close(kLinkTail);
+            } else {
+                acc |= (u64)ext_char(f) << (8u * (n & 7u));         // extract_contig: read_kmers.hpp:86-90
+                ++n;
+                if ((n & 7u) == 0) {
+                    *reinterpret_cast<u64*>(p.tmp + (u64)seg * p.seg_chars + n - 8) = acc;
+                    acc = 0;
+                }
+                V nxt; u64 b; int s;
+                if (!lookup<W>(table, p.nbuckets, S::next_key(cur, p.k), nxt, b, s)) {
+                    atomicOr(&p.ctr->errors, kErrNotFound);         // kmer_hash.cpp:47-49
+                    close(kLinkTail);
+                } else if (s == 0 && (b & split_mask) == 0) {
+                    close(p.n_starts + (u32)(b >> p.split_shift));  // the splitter's walker takes over
+                } else {
+                    cur = nxt;
+                    // Brent: a splitter-free cycle would never end this segment
+                    if (S::same_key(cur, chk)) {
+                        atomicOr(&p.ctr->errors, kErrCycle);
+                        close(kLinkTail);
+                    } else if (++steps == limit) {
+                        chk = cur; steps = 0; limit <<= 1;
+                    }
+                }
+            }
+        }
+    }
+    // ids left in this warp's overflow pool were never used
+    for (u32 id = o_next + lane; id < o_end; id += 32)
+        if (id < p.seg_cap) p.link[id] = (u64)kLinkUnused << 32;
+}
+
+// =========================================================================================
+// rank: pointer jumping over segments, contig lengths, tail claims (cooperative launch)
+// =========================================================================================
+// Invariant: link[i] = (p, s) means "s characters lie between the start of segment i and the
+// start of segment p".  Jumping replaces (p, s) by (link[p].p, s + link[p].s); any stale value
+// read for link[p] is still a valid such pair, so the update is safe in place without double
+// buffering.  A segment is final once its p is a tail.
+struct RankParams {
+    u64* link;
+    const unsigned char* seglen;
+    Counters* ctr;
+    u32* contig_len;      // K + chars + 1 ('\n') per contig
+    u32* contig_pre;      // characters before the tail segment starts
+    u32 n_starts;
+    u32 seg_cap;
+    int k;
+    int max_rounds;
+};
+
+__device__ __forceinline__ u64 ld_cg64(const u64* p) { return __ldcg(p); }
+
+__global__ void __launch_bounds__(256)
+rank_kernel(const RankParams p) {
+    cg::grid_group grid = cg::this_grid();
+    const u64 gtid = (u64)blockIdx.x * blockDim.x + threadIdx.x;
+    const u64 gsize = (u64)gridDim.x * blockDim.x;
+    const u32 nseg = min(p.ctr->next_seg, p.seg_cap);
+    int round = 0;
+    for (; round < p.max_rounds; ++round) {
+        bool changed = false;
+        for (u64 i = gtid; i < nseg; i += gsize) {
+            const u64 li = ld_cg64(p.link + i);
+            const u32 pi = (u32)(li >> 32);
+            if (pi >= kLinkClaimed) continue;
+            const u64 lp = ld_cg64(p.link + pi);
+            const u32 pp = (u32)(lp >> 32);
+            if (pp == kLinkTail) continue;                   // final
+            if (pp >= kLinkClaimed) { atomicOr(&p.ctr->errors, kErrInternal); continue; }
+            __stcg(p.link + i, ((u64)pp << 32) | (u32)((u32)li + (u32)lp));
+            changed = true;
+        }
+        if (changed) p.ctr->flags[round] = 1;
+        grid.sync();
+        if (__ldcg(&p.ctr->flags[round]) == 0) break;
+    }
+    if (gtid == 0) p.ctr->rank_rounds = (u32)min(round + 1, p.max_rounds);
+    grid.sync();
+    // ---- contig lengths (kmer_hash.cpp:38-55: one contig per start node) ----
+    u64 nodes = 0;
+    for (u64 c = gtid; c < p.n_starts; c += gsize) {
+        const u64 lc = ld_cg64(p.link + c);
+        const u32 pc = (u32)(lc >> 32);
+        u32 tail = (u32)c, pre = 0;
+        bool ok = true;
+        if (pc != kLinkTail) {
+            tail = pc; pre = (u32)lc;
+            ok = pc < kLinkClaimed && (u32)(ld_cg64(p.link + pc) >> 32) == kLinkTail;
+        }
+        if (!ok) {      // still open after max_rounds: the chain runs into a cycle (kmer_hash.cpp:44 never exits)
+            atomicOr(&p.ctr->errors, kErrCycle);
+            p.contig_pre[c] = 0; p.contig_len[c] = 0;
+            continue;
+        }
+        const u32 chars = pre + p.seglen[tail];
+        p.contig_pre[c] = pre;
+        p.contig_len[c] = (u32)p.k + chars + 1u;
+        nodes += (u64)chars + 1u;
+    }
+    nodes = warp_sum_u64(nodes);
+    if (lane_id() == 0 && nodes) atomicAdd(&p.ctr->n_nodes, nodes);
+    grid.sync();
+    // ---- each contig claims its tail so segments can find their contig ----
+    for (u64 c = gtid; c < p.n_starts; c += gsize) {
+        if (p.contig_len[c] == 0) continue;
+        const u32 pc = (u32)(ld_cg64(p.link + c) >> 32);
+        const u32 tail = (pc == kLinkTail) ? (u32)c : pc;
+        const u64 want = (u64)kLinkTail << 32;
+        const u64 old = atomicCAS(p.link + tail, want, ((u64)kLinkClaimed << 32) | (u32)c);
+        if (old != want) atomicOr(&p.ctr->errors, kErrConverge);   // two starts, one end: not linear chains
+    }
+}
+
+// =========================================================================================
+// K6  emit
+// =========================================================================================
+// 16 lanes per segment: copy its characters to contig_off[c] + K + position.
+__global__ void __launch_bounds__(256)
+emit_segments_kernel(const u64* __restrict__ link, const unsigned char* __restrict__ seglen,
+                     const unsigned char* __restrict__ tmp, u32 seg_chars, u32 seg_cap, Counters* ctr,
+                     const u32* __restrict__ contig_pre, const u64* __restrict__ contig_off,
+                     int k, u64 out_cap, char* __restrict__ out) {
+    // never write when the layout is not trustworthy (host reports the error)
+    if (ctr->contig_bytes > out_cap || (ctr->errors & (kErrConverge | kErrCycle | kErrInternal))) return;
+    const u64 t = (u64)blockIdx.x * blockDim.x + threadIdx.x;
+    const u64 seg = t >> 4;
+    const u32 sub = (u32)(t & 15u);
+    const u32 nseg = min(ctr->next_seg, seg_cap);
+    if (seg >= nseg) return;
+    const u64 li = link[seg];
+    const u32 pi = (u32)(li >> 32);
+    if (pi == kLinkUnused || pi == kLinkTail) return;        // never walked / not on any start-rooted chain
+    u32 c, pos;
+    if (pi == kLinkClaimed) {
+        c = (u32)li;
+        pos = contig_pre[c];
+    } else {
+        const u64 lt = link[pi];
+        if ((u32)(lt >> 32) != kLinkClaimed) return;         // chain without a start node: ignored like the reference
+        c = (u32)lt;
+        const u32 pre = contig_pre[c];
+        if ((u32)li > pre) { if (sub == 0) atomicOr(&ctr->errors, kErrConverge); return; }
+        pos = pre - (u32)li;
+    }
+    const u32 len = seglen[seg];
+    char* dst = out + contig_off[c] + (u64)k + pos;
+    const unsigned char* src = tmp + seg * (u64)seg_chars;
+    for (u32 j = sub; j < len; j += 16) dst[j] = (char)src[j];
+}
+
+// first k-mer of each contig + trailing newline (read_kmers.hpp:84, kmer_hash.cpp:66)
+template <int W>
+__global__ void __launch_bounds__(256)
+emit_heads_kernel(const typename Slot<W>::value_t* __restrict__ starts, u32 n_starts, int k,
+                  const u32* __restrict__ contig_len, const u64* __restrict__ contig_off,
+                  const Counters* __restrict__ ctr, u64 out_cap, char* __restrict__ out) {
+    typedef Slot<W> S;
+    if (ctr->contig_bytes > out_cap || (ctr->errors & (kErrConverge | kErrCycle | kErrInternal))) return;
+    const u64 t = (u64)blockIdx.x * blockDim.x + threadIdx.x;
+    const u64 c = t / (u32)(k + 1);
+    const u32 j = (u32)(t - c * (u32)(k + 1));
+    if (c >= n_starts) return;
+    const u32 len = contig_len[c];
+    if (len == 0) return;
+    if (j < (u32)k) out[contig_off[c] + j] = (char)ext_char(S::base_at(starts[c], k, (int)j));
+    else out[contig_off[c] + len - 1] = '\n';
+}
+
+// =========================================================================================
+// roofline helper: independent random 32-byte sector reads
+// =========================================================================================
+__global__ void __launch_bounds__(256)
+random_sector_kernel(const u64* __restrict__ buf, u64 nsectors, u64 probes_per_thread, u64* sink) {
+    const u64 tid = (u64)blockIdx.x * blockDim.x + threadIdx.x;
+    u64 x = 0, state = fmix64(tid + 0x1234567ull);
+    for (u64 i = 0; i < probes_per_thread; i += 4) {
+        u64 q[4][4];
+#pragma unroll
+        for (int j = 0; j < 4; ++j) {
+            state = state * 6364136223846793005ull + 1442695040888963407ull;
+            load256_nc(buf + 4 * bucket_of(fmix64(state), nsectors), q[j]);
+        }
+#pragma unroll
+        for (int j = 0; j < 4; ++j) x ^= q[j][0] ^ q[j][1] ^ q[j][2] ^ q[j][3];
+    }
+    if (x == 0x9E3779B97F4A7C15ull) *sink = x;    // keep the loads alive
+}
+
+}  // namespace kh

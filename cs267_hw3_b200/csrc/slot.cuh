@@ -1,0 +1,255 @@
+// slot.cuh -- device-side key/slot format and the memory primitives every kernel shares.
+//
+// A table slot holds one reference `kmer_pair` (kmer_t.hpp:6-8) as a single integer so
+// that ONE compare-and-swap publishes key and value together:
+//
+//     slot = (key << 6) | (backward_code << 3) | (forward_code + 1)
+//
+//   key           the k-mer as a right-justified base-4 number, first base most
+//                 significant -- the same ordering as pkmer_t::data read big-endian
+//                 (packing.hpp:50-92), minus the A-padding of the last byte
+//   codes         A=0 C=1 G=2 T=3 F=4; forward is stored +1 so an occupied slot is
+//                 never 0, and 0 means empty
+//
+// 2K+6 <= 64 for K <= 29 -> 64-bit slots (Slot<1>), 4 per 32-byte bucket;
+// 2K+6 <= 128 for K <= 61 -> 128-bit slots (Slot<2>), 2 per 32-byte bucket.
+// A bucket is exactly one 32-byte DRAM sector and is always read with one 256-bit load.
+//
+// kmer_pair::next_kmer() (kmer_t.hpp:51-53: unpack, substr(1)+fwd, repack) becomes
+// ((key << 2) | fwd) & (4^K - 1) on this representation.
+#pragma once
+#include <cstdint>
+#include <cuda_runtime.h>
+
+namespace kh {
+
+typedef unsigned long long u64;
+typedef unsigned int u32;
+
+constexpr u32 kExtF = 4;           // code of 'F'
+constexpr u32 kExtBad = 7;
+
+struct alignas(16) u128 {
+    u64 lo, hi;
+};
+
+__host__ __device__ __forceinline__ u32 ext_code(unsigned char c) {
+    switch (c) {
+    case 'A': return 0;
+    case 'C': return 1;
+    case 'G': return 2;
+    case 'T': return 3;
+    case 'F': return kExtF;
+    default: return kExtBad;
+    }
+}
+__host__ __device__ __forceinline__ unsigned char ext_char(u32 code) {
+    // "ACGTF" packed little-endian
+    return (unsigned char)((0x4654474341ull >> (8 * code)) & 0xFF);
+}
+// base letter -> 2-bit code without a table: (c>>1)&3 maps A,C,G,T to 0,1,3,2
+__host__ __device__ __forceinline__ u32 base_code_fast(unsigned char c) {
+    const u32 x = (c >> 1) & 3u;
+    return x ^ (x >> 1);
+}
+__host__ __device__ __forceinline__ bool is_base(unsigned char c) {
+    return c == 'A' || c == 'C' || c == 'G' || c == 'T';
+}
+
+__host__ __device__ __forceinline__ u64 fmix64(u64 z) {
+    z ^= z >> 33; z *= 0xFF51AFD7ED558CCDull;
+    z ^= z >> 33; z *= 0xC4CEB9FE1A85EC53ull;
+    z ^= z >> 33;
+    return z;
+}
+
+// ---- raw memory primitives -------------------------------------------------------------
+// One 32-byte sector in one instruction (LDG.E.256 on sm_100a).
+__device__ __forceinline__ void load256_nc(const void* p, u64 (&q)[4]) {   // read-only data, no L1 allocation
+    asm volatile("ld.global.nc.L1::no_allocate.v4.u64 {%0,%1,%2,%3}, [%4];"
+                 : "=l"(q[0]), "=l"(q[1]), "=l"(q[2]), "=l"(q[3]) : "l"(p));
+}
+__device__ __forceinline__ void load256_cg(const void* p, u64 (&q)[4]) {   // coherent at L2 (table being built)
+    asm volatile("ld.global.cg.v4.u64 {%0,%1,%2,%3}, [%4];"
+                 : "=l"(q[0]), "=l"(q[1]), "=l"(q[2]), "=l"(q[3]) : "l"(p) : "memory");
+}
+__device__ __forceinline__ uint4 load128_stream(const uint4* p) {           // streaming input, read once
+    uint4 r;
+    asm volatile("ld.global.nc.L1::no_allocate.v4.u32 {%0,%1,%2,%3}, [%4];"
+                 : "=r"(r.x), "=r"(r.y), "=r"(r.z), "=r"(r.w) : "l"(p));
+    return r;
+}
+__device__ __forceinline__ u128 cas128(u128* addr, u128 cmp, u128 val) {    // ATOMG.E.CAS.128
+    u128 old;
+    asm volatile("{\n\t.reg .b128 c, v, o;\n\t"
+                 "mov.b128 c, {%2, %3};\n\tmov.b128 v, {%4, %5};\n\t"
+                 "atom.global.cas.b128 o, [%6], c, v;\n\t"
+                 "mov.b128 {%0, %1}, o;\n\t}"
+                 : "=l"(old.lo), "=l"(old.hi)
+                 : "l"(cmp.lo), "l"(cmp.hi), "l"(val.lo), "l"(val.hi), "l"(addr) : "memory");
+    return old;
+}
+
+// ---- slot traits -------------------------------------------------------------------------
+template <int W> struct Slot;
+
+template <> struct Slot<1> {
+    typedef u64 value_t;
+    static constexpr int kPerBucket = 4;
+    static constexpr int kBits = 64;
+
+    static __host__ __device__ __forceinline__ value_t zero() { return 0ull; }
+    static __host__ __device__ __forceinline__ bool empty(value_t v) { return v == 0ull; }
+    static __host__ __device__ __forceinline__ u32 fwd(value_t v) { return (u32)(v & 7u) - 1u; }
+    static __host__ __device__ __forceinline__ u32 back(value_t v) { return (u32)(v >> 3) & 7u; }
+    static __host__ __device__ __forceinline__ bool same_key(value_t a, value_t b) { return ((a ^ b) >> 6) == 0ull; }
+    static __host__ __device__ __forceinline__ bool equal(value_t a, value_t b) { return a == b; }
+    static __host__ __device__ __forceinline__ u64 hash(value_t v) { return fmix64(v >> 6); }
+    static __host__ __device__ __forceinline__ u64 owner_hash(value_t v) { return fmix64((v >> 6) ^ 0x9E3779B97F4A7C15ull); }
+    static __device__ __forceinline__ value_t from_bucket(const u64 (&q)[4], int i) { return q[i]; }
+
+    // kmer_pair bytes -> slot.  pl = (k+3)/4.
+    static __host__ __device__ __forceinline__ value_t from_record(const unsigned char* rec, int k, int pl, bool& ok) {
+        u64 be = 0;
+        for (int i = 0; i < pl; ++i) be = (be << 8) | rec[i];
+        const u64 key = be >> (8 * pl - 2 * k);
+        const u32 b = ext_code(rec[pl]), f = ext_code(rec[pl + 1]);
+        ok = (b != kExtBad) && (f != kExtBad);
+        return (key << 6) | ((u64)(b & 7u) << 3) | (u64)((f + 1u) & 7u);
+    }
+    // packed k-mer bytes (pkmer_t) -> key bits only (ext field 0)
+    static __host__ __device__ __forceinline__ value_t from_packed(const unsigned char* p, int k, int pl) {
+        u64 be = 0;
+        for (int i = 0; i < pl; ++i) be = (be << 8) | p[i];
+        return (be >> (8 * pl - 2 * k)) << 6;
+    }
+    static __host__ __device__ __forceinline__ void to_record(value_t v, int k, int pl, unsigned char* rec) {
+        const u64 be = (v >> 6) << (8 * pl - 2 * k);
+        for (int i = 0; i < pl; ++i) rec[i] = (unsigned char)(be >> (8 * (pl - 1 - i)));
+        rec[pl] = ext_char(back(v));
+        rec[pl + 1] = ext_char(fwd(v));
+    }
+    // key bits of kmer[1:] + fwd  (ext field 0)
+    static __host__ __device__ __forceinline__ value_t next_key(value_t v, int k) {
+        const u64 mask = ((2 * k + 6) >= 64) ? ~0ull : ((1ull << (2 * k + 6)) - 1ull);
+        return ((((v & ~63ull) << 2) | ((u64)fwd(v) << 6)) & mask);
+    }
+    // 2-bit code of base i (0 = first)
+    static __host__ __device__ __forceinline__ u32 base_at(value_t v, int k, int i) {
+        return (u32)(v >> (6 + 2 * (k - 1 - i))) & 3u;
+    }
+    static __device__ __forceinline__ value_t cas(value_t* addr, value_t expect, value_t val) {
+        return atomicCAS(addr, expect, val);
+    }
+    static __device__ __forceinline__ value_t load_one_nc(const value_t* p) { return __ldg(p); }
+};
+
+template <> struct Slot<2> {
+    typedef u128 value_t;
+    static constexpr int kPerBucket = 2;
+    static constexpr int kBits = 128;
+
+    static __host__ __device__ __forceinline__ value_t zero() { return u128{0ull, 0ull}; }
+    static __host__ __device__ __forceinline__ bool empty(value_t v) { return (v.lo | v.hi) == 0ull; }
+    static __host__ __device__ __forceinline__ u32 fwd(value_t v) { return (u32)(v.lo & 7u) - 1u; }
+    static __host__ __device__ __forceinline__ u32 back(value_t v) { return (u32)(v.lo >> 3) & 7u; }
+    static __host__ __device__ __forceinline__ bool same_key(value_t a, value_t b) {
+        return (((a.lo ^ b.lo) >> 6) | (a.hi ^ b.hi)) == 0ull;
+    }
+    static __host__ __device__ __forceinline__ bool equal(value_t a, value_t b) { return a.lo == b.lo && a.hi == b.hi; }
+    static __host__ __device__ __forceinline__ u64 hash(value_t v) {
+        return fmix64((v.lo >> 6) ^ fmix64(v.hi + 0x9E3779B97F4A7C15ull));
+    }
+    static __host__ __device__ __forceinline__ u64 owner_hash(value_t v) {
+        return fmix64((v.lo >> 6) + 0xD6E8FEB86659FD93ull + fmix64(v.hi ^ 0xA0761D6478BD642Full));
+    }
+    static __device__ __forceinline__ value_t from_bucket(const u64 (&q)[4], int i) { return u128{q[2 * i], q[2 * i + 1]}; }
+
+    static __host__ __device__ __forceinline__ value_t shl(value_t v, int s) {   // 0 <= s < 64
+        if (s == 0) return v;
+        return u128{v.lo << s, (v.hi << s) | (v.lo >> (64 - s))};
+    }
+    static __host__ __device__ __forceinline__ value_t shr(value_t v, int s) {   // 0 <= s < 64
+        if (s == 0) return v;
+        return u128{(v.lo >> s) | (v.hi << (64 - s)), v.hi >> s};
+    }
+    static __host__ __device__ __forceinline__ value_t be_bytes(const unsigned char* p, int pl) {
+        u128 x{0ull, 0ull};
+        for (int i = 0; i < pl; ++i) {
+            x.hi = (x.hi << 8) | (x.lo >> 56);
+            x.lo = (x.lo << 8) | p[i];
+        }
+        return x;
+    }
+    static __host__ __device__ __forceinline__ value_t from_record(const unsigned char* rec, int k, int pl, bool& ok) {
+        u128 v = shl(shr(be_bytes(rec, pl), 8 * pl - 2 * k), 6);
+        const u32 b = ext_code(rec[pl]), f = ext_code(rec[pl + 1]);
+        ok = (b != kExtBad) && (f != kExtBad);
+        v.lo |= ((u64)(b & 7u) << 3) | (u64)((f + 1u) & 7u);
+        return v;
+    }
+    static __host__ __device__ __forceinline__ value_t from_packed(const unsigned char* p, int k, int pl) {
+        return shl(shr(be_bytes(p, pl), 8 * pl - 2 * k), 6);
+    }
+    static __host__ __device__ __forceinline__ void to_record(value_t v, int k, int pl, unsigned char* rec) {
+        const u128 be = shl(shr(v, 6), 8 * pl - 2 * k);
+        for (int i = 0; i < pl; ++i) {
+            const int sh = 8 * (pl - 1 - i);
+            rec[i] = (unsigned char)(sh >= 64 ? (be.hi >> (sh - 64)) : (be.lo >> sh));
+        }
+        rec[pl] = ext_char(back(v));
+        rec[pl + 1] = ext_char(fwd(v));
+    }
+    static __host__ __device__ __forceinline__ value_t next_key(value_t v, int k) {
+        u128 n = shl(u128{v.lo & ~63ull, v.hi}, 2);
+        n.lo |= (u64)fwd(v) << 6;
+        const int bits = 2 * k + 6;            // 66..128 for K in 30..61
+        if (bits < 128) n.hi &= (1ull << (bits - 64)) - 1ull;
+        return n;
+    }
+    static __host__ __device__ __forceinline__ u32 base_at(value_t v, int k, int i) {
+        const int sh = 6 + 2 * (k - 1 - i);
+        return (u32)(sh >= 64 ? (v.hi >> (sh - 64)) : (v.lo >> sh)) & 3u;
+    }
+    static __device__ __forceinline__ value_t cas(value_t* addr, value_t expect, value_t val) {
+        return cas128(addr, expect, val);
+    }
+    static __device__ __forceinline__ value_t load_one_nc(const value_t* p) {
+        const uint4 r = load128_stream(reinterpret_cast<const uint4*>(p));
+        return u128{(u64)r.x | ((u64)r.y << 32), (u64)r.z | ((u64)r.w << 32)};
+    }
+};
+
+// hash -> bucket without requiring a power-of-two table (load-factor sweeps need exact sizes)
+__host__ __device__ __forceinline__ u64 bucket_of(u64 h, u64 nbuckets) {
+#ifdef __CUDA_ARCH__
+    return __umul64hi(h, nbuckets);
+#else
+    return (u64)(((unsigned __int128)h * nbuckets) >> 64);
+#endif
+}
+
+// Error bits accumulated on the device (Counters::errors)
+enum : u32 {
+    kErrNotFound = 1u, kErrTableFull = 2u, kErrCycle = 4u, kErrBadInput = 8u,
+    kErrConverge = 16u, kErrInternal = 32u
+};
+
+constexpr u32 kLinkTail = 0xFFFFFFFFu;      // segment ends a contig (forward ext 'F')
+constexpr u32 kLinkUnused = 0xFFFFFFFEu;    // id never walked
+constexpr u32 kLinkClaimed = 0xFFFFFFFDu;   // tail claimed by a contig; low word = contig id
+
+struct Counters {
+    u32 next_walker;
+    u32 next_seg;
+    u32 errors;
+    u32 rank_rounds;
+    u64 n_inserted;
+    u64 n_duplicates;
+    u64 scan_total;       // result of the last device scan (start nodes of the last insert call)
+    u64 n_nodes;
+    u64 contig_bytes;
+    u32 flags[40];
+};
+
+}  // namespace kh

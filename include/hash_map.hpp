@@ -1,0 +1,103 @@
+// hash_map.hpp -- DistributedHashMap with the reference's constructor and member functions
+// (hash_map.hpp:50-52, 55, 83, 110), backed by the B200 table behind kh_capi.h instead of a
+// per-rank std::unordered_map + UPC++ RPCs.  Also the upstream-starter spelling the
+// assignment text uses (README.md:85-99): HashMap(size), insert(kmer_pair), find(pkmer_t, ...).
+//
+// Error behaviour mirrors the reference: find returns bool; failures of the device layer
+// surface as std::runtime_error (the reference throws std::runtime_error as well,
+// kmer_hash.cpp:48, 102).
+//
+// New, batch-oriented members (no counterpart in the reference, used by src/kmer_hash.cpp):
+// insert_all(const kmer_pair*, n) and assemble().
+#pragma once
+
+#include <cstdlib>
+#include <stdexcept>
+#include <string>
+#include <vector>
+
+#include "kh_capi.h"
+#include "kmer_t.hpp"
+
+class DistributedHashMap {
+    kh_table* table_ = nullptr;
+    size_t table_size_;
+    int rank_id_, world_size_;
+
+    void check(int status, const char* what) const {
+        if (status == KH_OK) return;
+        const char* detail = table_ ? kh_last_error(table_) : "";
+        throw std::runtime_error(std::string(detail && *detail ? detail : kh_status_string(status)) + " [" + what + "]");
+    }
+
+  public:
+    // table_size is a slot count; the reference passes 2 * n_kmers (kmer_hash.cpp:109), i.e. load
+    // factor 0.5.  KH_LOAD_FACTOR / KH_DEVICE in the environment override the defaults without
+    // touching the positional interface.
+    DistributedHashMap(size_t table_size, int rank_id, int world_size)
+        : table_size_(table_size), rank_id_(rank_id), world_size_(world_size) {
+        double lf = 0.5;
+        if (const char* e = std::getenv("KH_LOAD_FACTOR")) lf = std::atof(e);
+        int dev = rank_id;
+        if (const char* e = std::getenv("KH_DEVICE")) dev = std::atoi(e);
+        const int ndev = kh_device_count();
+        if (ndev <= 0) throw std::runtime_error("DistributedHashMap: no CUDA device (libkh_b200 has no CPU fallback)");
+        check(kh_create(KMER_LEN, table_size / 2, lf, dev % ndev, &table_), "kh_create");
+    }
+    ~DistributedHashMap() { kh_destroy(table_); }
+    DistributedHashMap(const DistributedHashMap&) = delete;
+    DistributedHashMap& operator=(const DistributedHashMap&) = delete;
+
+    // hash_map.hpp:55-80.  Also records which items are start nodes (backward ext 'F'), in order,
+    // which the reference does right after insert_all (kmer_hash.cpp:27-31).
+    void insert_all(const std::vector<kmer_pair>& items) { insert_all(items.data(), items.size()); }
+    void insert_all(const kmer_pair* items, size_t n) { check(kh_insert_pairs(table_, items, n), "insert_all"); }
+
+    // hash_map.hpp:83-107.  The key is the k-mer as a string of KMER_LEN letters.
+    bool find(const std::string& key, kmer_pair& result) {
+        if (key.size() != static_cast<size_t>(KMER_LEN)) return false;
+        return find(pkmer_t(key), result);
+    }
+    bool find(const pkmer_t& key, kmer_pair& result) {
+        kmer_pair hit;
+        uint8_t found = 0;
+        check(kh_find(table_, key.data, 1, &hit, &found), "find");
+        if (found) result = hit;
+        return found != 0;
+    }
+    // hash_map.hpp:110-113: progress + barrier in the reference; here: wait for the device.
+    void process_requests() { check(kh_sync(table_), "process_requests"); }
+
+    // assemble_contigs + extract_contig for every start node seen by insert_all, in order
+    // (kmer_hash.cpp:38-55, read_kmers.hpp:81-92).  Throws the reference's
+    // "Error: k-mer not found in Distributed HashMap." on a missing successor.
+    std::vector<std::string> assemble(uint64_t* n_nodes = nullptr) {
+        const char* text = nullptr;
+        const uint64_t* offs = nullptr;
+        uint64_t nc = 0, bytes = 0, nodes = 0;
+        check(kh_assemble(table_, &text, &offs, &nc, &bytes, &nodes), "assemble");
+        std::vector<std::string> contigs;
+        contigs.reserve(nc);
+        for (uint64_t c = 0; c < nc; ++c) contigs.emplace_back(text + offs[c], offs[c + 1] - offs[c] - 1);
+        if (n_nodes) *n_nodes = nodes;
+        return contigs;
+    }
+
+    size_t size() const { return table_size_; }
+    kh_table* handle() { return table_; }
+};
+
+// Upstream-starter interface (README.md:85-99).
+class HashMap {
+    DistributedHashMap impl_;
+
+  public:
+    explicit HashMap(size_t size) : impl_(size, 0, 1) {}
+    bool insert(const kmer_pair& kmer) {
+        impl_.insert_all(&kmer, 1);
+        return true;
+    }
+    bool find(const pkmer_t& key_kmer, kmer_pair& val_kmer) { return impl_.find(key_kmer, val_kmer); }
+    size_t size() const noexcept { return impl_.size(); }
+    DistributedHashMap& distributed() { return impl_; }
+};

@@ -1,0 +1,143 @@
+/* kh_capi.h -- C ABI of the B200 k-mer hash table + contig traversal library
+ * (libkh_b200.so, built from cs267_hw3_b200/csrc/ for sm_100a).
+ *
+ * This is the drop-in boundary for ONE stage of fractalclockwork/CS267_HW3: the timed
+ * region of kmer_hash.cpp:129-137 (insert all k-mers, find the start nodes, walk every
+ * contig) plus the packing that feeds it.  Plain C: opaque handle, pointers and sizes,
+ * int status codes, no C++ types, no exceptions, no torch types.  The C++ headers in
+ * include/ (hash_map.hpp, kmer_t.hpp, ...) and the kmer_hash CLI are thin host code
+ * over these calls; INTEGRATION.md shows the binding a reference maintainer would add.
+ *
+ * Record format on the wire is the reference's own `kmer_pair` bytes (kmer_t.hpp:6-8):
+ *   (K+3)/4 packed bytes  -- 2 bits per base, A=0 C=1 G=2 T=3, first base in bits 7..6
+ *                            of byte 0, tail padded with A (packing.hpp:50-92)
+ *   1 byte backward ext, 1 byte forward ext, ASCII in {A,C,G,T,F} (kmer_t.hpp:43-45)
+ * i.e. 7 / 10 / 15 bytes for K = 19 / 31 / 51, alignment 1.  The device-side slot
+ * format is private.  Supported K: 2..61 (64-bit slots up to K=29, 128-bit above).
+ *
+ * There is no CPU fallback: every entry point that computes needs a CUDA device and
+ * returns KH_ERR_CUDA without one.
+ *
+ * Threading: a handle is not re-entrant; use one handle per host thread / per GPU.
+ * Unless stated otherwise calls are synchronous with respect to the host for their
+ * host-visible results; *_device variants only enqueue work on the handle's stream.
+ */
+#ifndef KH_CAPI_H
+#define KH_CAPI_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+typedef struct kh_table kh_table;
+
+enum kh_status {
+    KH_OK = 0,
+    KH_ERR_ARG = 1,          /* bad argument (null pointer, unsupported K, ...) */
+    KH_ERR_CUDA = 2,         /* CUDA runtime failure, or no device; see kh_last_error */
+    KH_ERR_NOT_FOUND = 3,    /* a successor k-mer is missing: kmer_hash.cpp:47-49
+                                "Error: k-mer not found in Distributed HashMap." */
+    KH_ERR_TABLE_FULL = 4,   /* more distinct k-mers than slots */
+    KH_ERR_CYCLE = 5,        /* a start-rooted chain never reaches forward ext 'F'
+                                (the reference would spin forever, kmer_hash.cpp:44) */
+    KH_ERR_BAD_INPUT = 6,    /* base outside ACGT / ext outside ACGTF / malformed line
+                                (undefined behaviour in the reference, packing.hpp:52-70) */
+    KH_ERR_CONVERGE = 7,     /* two start nodes reach the same end node (not a set of
+                                linear chains; violates README.md:33-35) */
+    KH_ERR_NOMEM = 8         /* device or pinned-host allocation failed */
+};
+
+/* Per-handle counters and stage times of the most recent calls (milliseconds are CUDA-event
+ * times on the handle's stream). */
+typedef struct kh_stats {
+    uint64_t n_slots;          /* table capacity in slots                                   */
+    uint64_t n_buckets;        /* 32-byte buckets (4 x 64-bit or 2 x 128-bit slots)         */
+    uint64_t n_inserted;       /* records accepted since create/clear (duplicates excluded) */
+    uint64_t n_duplicates;     /* records whose k-mer was already present (first one kept;
+                                  the reference keeps the last, hash_map.hpp:34 -- identical
+                                  for the unique inputs README.md:33-35 guarantees)         */
+    uint64_t n_starts;         /* records seen with backward ext 'F'                        */
+    uint64_t n_contigs;        /* last assemble                                             */
+    uint64_t n_nodes;          /* last assemble: k-mers on emitted contigs                  */
+    uint64_t contig_bytes;     /* last assemble: bytes of contig text incl. '\n' each       */
+    uint64_t n_segments;       /* last assemble: walk segments (start + splitter + overflow)*/
+    uint32_t rank_rounds;      /* last assemble: pointer-jumping rounds                     */
+    uint32_t slot_bits;        /* 64 or 128                                                 */
+    float ms_insert;           /* last insert call: insert kernel + start-node compaction   */
+    float ms_assemble;         /* last assemble: walk + rank + emit                         */
+    float ms_walk, ms_rank, ms_emit;
+    float ms_pack;             /* last kh_pack_lines* call                                  */
+    float ms_clear;            /* last kh_clear                                             */
+} kh_stats;
+
+int kh_abi_version(void);                 /* bumps when this header changes incompatibly */
+int kh_device_count(void);                /* 0 when no CUDA device is usable             */
+const char* kh_status_string(int status);
+uint64_t kh_pair_bytes(int k);            /* sizeof(kmer_pair) for this K: (K+3)/4 + 2   */
+uint64_t kh_packed_bytes(int k);          /* sizeof(pkmer_t): (K+3)/4                    */
+
+/* Replaces DistributedHashMap::DistributedHashMap(size_t,int,int) (hash_map.hpp:50-52) and
+ * the sizing in kmer_hash.cpp:107-109 (table = n_kmers / load_factor; the reference uses
+ * load factor 0.5).  `device` is the CUDA ordinal that owns this table. */
+int kh_create(int k, uint64_t n_expected, double load_factor, int device, kh_table** out);
+int kh_destroy(kh_table* t);
+/* Empty the table and forget the start nodes (a fresh DistributedHashMap). Stream-ordered. */
+int kh_clear(kh_table* t);
+/* Run on an existing CUDA stream (cudaStream_t) instead of the handle's own. */
+int kh_set_stream(kh_table* t, void* cuda_stream);
+int kh_sync(kh_table* t);
+/* Tuning knobs (also read from the environment at create: KH_SPLIT_BUCKETS, KH_SEG_CHARS):
+ *   "split_buckets": every split_buckets-th bucket's first slot ends a walk segment
+ *   "seg_chars"    : capacity of one segment's character buffer (multiple of 8, <= 248) */
+int kh_set_option(kh_table* t, const char* name, int64_t value);
+
+/* K1 -- replaces the parse loop of read_kmers (read_kmers.hpp:72-76) + kmer_pair::init
+ * (kmer_t.hpp:67-76) + packKmer/packFourMer (packing.hpp:50-92): n_lines fixed-width lines of
+ * K+4 bytes -> n_lines kmer_pair records. */
+int kh_pack_lines(kh_table* t, const char* text_host, uint64_t n_lines, void* pairs_host_out);
+int kh_pack_lines_device(kh_table* t, const void* text_dev, uint64_t n_lines, void* pairs_dev_out);
+
+/* K2+K3 -- replaces initialize_kmers (kmer_hash.cpp:21-33): DistributedHashMap::insert_all
+ * (hash_map.hpp:55-80) plus the order-preserving scan for backward ext == 'F'
+ * (kmer_hash.cpp:27-31).  May be called repeatedly; start nodes accumulate in call order. */
+int kh_insert_pairs(kh_table* t, const void* pairs_host, uint64_t n);
+int kh_insert_pairs_device(kh_table* t, const void* pairs_dev, uint64_t n);
+/* read_kmers + initialize_kmers in one call, straight from text lines (K1 then K2+K3). */
+int kh_insert_lines(kh_table* t, const char* text_host, uint64_t n_lines);
+
+/* K4 as a batch -- replaces DistributedHashMap::find (hash_map.hpp:83-107): n packed k-mers
+ * (pkmer_t bytes) -> n kmer_pair records and n found flags (1/0; the record is zeroed on a miss). */
+int kh_find(kh_table* t, const void* pkmers_host, uint64_t n, void* pairs_host_out, uint8_t* found_host_out);
+int kh_find_device(kh_table* t, const void* pkmers_dev, uint64_t n, void* pairs_dev_out, uint8_t* found_dev_out);
+
+/* K3-K6 -- replaces assemble_contigs (kmer_hash.cpp:38-55) + extract_contig
+ * (read_kmers.hpp:81-92): one contig per start node, in start-node order, each rendered as
+ * its first k-mer's K characters followed by every forward extension != 'F', then '\n'
+ * (exactly the bytes output_results writes per contig, kmer_hash.cpp:64-67).
+ *   *contigs        : contig text, contig_bytes long  (host / device memory owned by the handle,
+ *                     valid until the next assemble, clear or destroy)
+ *   *offsets        : n_contigs+1 byte offsets into it
+ * Returns KH_ERR_NOT_FOUND / KH_ERR_CYCLE / KH_ERR_CONVERGE as described above. */
+int kh_assemble(kh_table* t, const char** contigs_host, const uint64_t** offsets_host,
+                uint64_t* n_contigs, uint64_t* contig_bytes, uint64_t* n_nodes);
+int kh_assemble_device(kh_table* t, const char** contigs_dev, const uint64_t** offsets_dev,
+                       uint64_t* n_contigs, uint64_t* contig_bytes, uint64_t* n_nodes);
+
+int kh_get_stats(kh_table* t, kh_stats* out);
+const char* kh_last_error(kh_table* t);
+
+/* Pinned host memory for callers that want full-speed host<->device copies. */
+int kh_host_alloc(void** ptr, uint64_t bytes);
+int kh_host_free(void* ptr);
+
+/* Micro-benchmark used by bench.py for the roofline denominators: `n_probes` independent
+ * random 32-byte sector reads over a `footprint_bytes` buffer; returns sectors per second. */
+int kh_measure_random_sector_rate(int device, uint64_t footprint_bytes, uint64_t n_probes, double* sectors_per_s);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* KH_CAPI_H */

@@ -1,0 +1,123 @@
+// kmer_hash -- the reference's command line (kmer_hash.cpp:84-152) on the B200 library.
+//
+//   kmer_hash_<K> kmer_file [verbose|test [prefix]]
+//
+// Same positional arguments, same stdout lines, same `<prefix>_<rank>.dat` output (one contig
+// per line, in start-node order) that scripts/check_it.sh:47-55 sorts and diffs, same
+// exceptions on a K mismatch or a missing k-mer.  One process drives one GPU, so it runs as
+// "rank 0 of 1"; the GPU and the load factor come from the environment (KH_DEVICE,
+// KH_LOAD_FACTOR) because the positional interface has no room for them.
+//
+// Stage mapping
+//   read_kmers (untimed, kmer_hash.cpp:122)      -> file read + K1 pack on the GPU (kh_pack_lines)
+//   initialize_kmers (timed, :131)               -> kh_insert_pairs   (records start in HOST memory,
+//                                                   exactly like the reference's std::vector<kmer_pair>)
+//   assemble_contigs (timed, :135)               -> kh_assemble       (contigs end in HOST memory)
+//   output_results (untimed, :147)               -> one fwrite of the contig text
+#include <chrono>
+#include <cstdio>
+#include <cstdlib>
+#include <stdexcept>
+#include <string>
+#include <vector>
+
+#include "butil.hpp"
+#include "hash_map.hpp"
+#include "kmer_t.hpp"
+#include "read_kmers.hpp"
+
+namespace {
+
+void must(int status, kh_table* t, const char* what) {
+    if (status == KH_OK) return;
+    const char* detail = t ? kh_last_error(t) : "";
+    throw std::runtime_error(std::string(detail && *detail ? detail : kh_status_string(status)) + " [" + what + "]");
+}
+
+// Whole file -> n kmer_pair records in pinned host memory, packed by the GPU (K1).
+kmer_pair* read_and_pack(kh_table* t, const std::string& fname, size_t n_kmers) {
+    const size_t line_len = KMER_LEN + 4;
+    FILE* f = fopen(fname.c_str(), "r");
+    if (f == nullptr) throw std::runtime_error("read_kmers: could not open " + fname);
+    void* text = nullptr;
+    void* pairs = nullptr;
+    must(kh_host_alloc(&text, line_len * n_kmers), t, "pinned text buffer");
+    must(kh_host_alloc(&pairs, sizeof(kmer_pair) * n_kmers), t, "pinned record buffer");
+    const size_t got = fread(text, 1, line_len * n_kmers, f);
+    fclose(f);
+    if (got != line_len * n_kmers)
+        throw std::runtime_error("read_kmers: " + fname + " is not " + std::to_string(n_kmers) + " lines of " +
+                                 std::to_string(line_len) + " bytes");
+    must(kh_pack_lines(t, static_cast<const char*>(text), n_kmers, pairs), t, "pack_lines");
+    kh_host_free(text);
+    return static_cast<kmer_pair*>(pairs);
+}
+
+}  // namespace
+
+int main(int argc, char** argv) {
+    if (argc < 2) {
+        BUtil::print("Usage: srun -N nodes -n ranks ./kmer_hash kmer_file [verbose|test [prefix]]\n");
+        exit(1);
+    }
+    const std::string kmer_fname = argv[1];
+    const std::string run_type = argc >= 3 ? argv[2] : "";
+    std::string test_prefix = "test";
+    if (run_type == "test" && argc >= 4) test_prefix = argv[3];
+
+    const int ks = kmer_size(kmer_fname);
+    if (ks != KMER_LEN) {
+        throw std::runtime_error("Error: " + kmer_fname + " contains " + std::to_string(ks) +
+                                 "-mers, while this binary is compiled for " + std::to_string(KMER_LEN) +
+                                 "-mers. Modify packing.hpp and recompile.");
+    }
+
+    const size_t n_kmers = line_count(kmer_fname);
+    const size_t hash_table_size = n_kmers * 2;      // load factor 0.5 (kmer_hash.cpp:108-109)
+    const int rank_id = 0;
+
+    if (run_type == "verbose")
+        BUtil::print("Initializing hash table of size %lu for %lu kmers.\n", hash_table_size, n_kmers);
+
+    DistributedHashMap hashmap(hash_table_size, rank_id, 1);
+    kh_table* t = hashmap.handle();
+
+    kmer_pair* kmers = read_and_pack(t, kmer_fname, n_kmers);
+    if (run_type == "verbose") BUtil::print("Finished reading kmers.\n");
+    must(kh_sync(t), t, "sync");
+
+    using clock = std::chrono::high_resolution_clock;
+    const auto start_time = clock::now();
+    hashmap.insert_all(kmers, n_kmers);                        // initialize_kmers
+    hashmap.process_requests();
+    const auto insert_time = clock::now();
+
+    const char* contig_text = nullptr;
+    const uint64_t* offsets = nullptr;
+    uint64_t n_contigs = 0, contig_bytes = 0, n_nodes = 0;
+    must(kh_assemble(t, &contig_text, &offsets, &n_contigs, &contig_bytes, &n_nodes), t, "assemble_contigs");
+    const auto end_time = clock::now();
+
+    const double insert_duration = std::chrono::duration<double>(insert_time - start_time).count();
+    const double assembly_duration = std::chrono::duration<double>(end_time - insert_time).count();
+    const double total_duration = std::chrono::duration<double>(end_time - start_time).count();
+
+    if (run_type != "test") {
+        BUtil::print("Finished inserting in %lf sec\n", insert_duration);
+        BUtil::print("Assembled in %lf total\n", total_duration);
+    } else {
+        const std::string out_name = test_prefix + "_" + std::to_string(rank_id) + ".dat";
+        FILE* out = fopen(out_name.c_str(), "w");
+        if (out == nullptr) throw std::runtime_error("output_results: could not open " + out_name);
+        if (contig_bytes && fwrite(contig_text, 1, contig_bytes, out) != contig_bytes)
+            throw std::runtime_error("output_results: short write to " + out_name);
+        fclose(out);
+        // same line as kmer_hash.cpp:71-78, including its quirks: "start nodes" is a literal 0
+        // and the slot labelled "read" carries the assembly time
+        BUtil::print("Rank %d reconstructed %d contigs with %d nodes from %d start nodes. "
+                     "(%lf read, %lf insert, %lf total)\n",
+                     rank_id, (int)n_contigs, (int)n_nodes, 0, assembly_duration, insert_duration, total_duration);
+    }
+    kh_host_free(kmers);
+    return 0;
+}
