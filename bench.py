@@ -267,11 +267,11 @@ def run_b200_arm(args, k: int, workload: str) -> dict | None:
     verified = bool(n_nodes == n and n_contigs == c and nodes == n and kmergen.digest_lines(buf) == exp_digest)
 
     # end-to-end through host buffers
-    for _ in range(min(args.warmup, 2)):
+    for _ in range(0 if args.no_e2e else min(args.warmup, 2)):
         step_e2e()
     torch.cuda.synchronize()
     e2e_ms = []
-    for _ in range(max(1, min(args.steps, 5))):
+    for _ in range(1 if args.no_e2e else max(1, min(args.steps, 5))):
         e0, e1, (buf, offs, nodes) = step_e2e()
         torch.cuda.synchronize()
         e2e_ms.append(e0.elapsed_time(e1))
@@ -335,6 +335,7 @@ def main():
     ap.add_argument("--n", type=int, default=0, help="override the number of k-mers (contigs scale along)")
     ap.add_argument("--load-factor", type=float, default=0.5)
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-e2e", action="store_true", help="skip the host-buffer leg (profiling runs)")
     args = ap.parse_args()
     args.warmup = max(args.warmup, 3) if args.impl == "b200" else args.warmup
     workload = args.workload or ("chr14_k19" if args.gpus == 1 else "chr14_k51")

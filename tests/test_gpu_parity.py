@@ -244,7 +244,7 @@ def _cycle_text(k, tail_len, cyc_len, seed):
             break
     lines = []
     for i, km in enumerate(kmers):
-        back = "F" if i == 0 else s[i - 1]
+        back = s[i - 1] if i > 0 else ("F" if tail_len > 0 else cyc[-1])   # a start node only when there is a tail
         fwd = s[i + k]                        # never 'F': the chain runs into the cycle and stays there
         lines.append(f"{km} {back}{fwd}\n")
     rng.shuffle(lines)
@@ -293,18 +293,31 @@ def test_bad_extension_in_records(kh):
         assert e.value.status == kh.KH_ERR_BAD_INPUT
 
 
-def test_converging_chains_are_refused(kh):
-    # two start nodes whose chains share an end node: outside the input contract (README.md:33-35)
+def test_converging_chains(kh):
+    """Two start nodes whose chains share a suffix: outside the input contract (README.md:33-35).  The
+    reference emits the shared suffix twice.  This library either does exactly the same (no walk-segment
+    boundary falls on the shared part) or refuses with KH_ERR_CONVERGE -- it never emits anything else."""
     k = 11
     a = "ACGGTCATTGCAAGTCCGATAGG"
     b = "T" + a[6:6 + k - 1]                   # second start that feeds into a's 7th k-mer
     lines = [f"{a[i:i + k]} {'F' if i == 0 else a[i - 1]}{'F' if i + k == len(a) else a[i + k]}\n" for i in range(len(a) - k + 1)]
     lines.append(f"{b} F{a[6 + k - 1]}\n")
-    with kh.KmerHashTable(k, 64) as tab:
-        tab.insert_lines("".join(lines).encode())
-        with pytest.raises(kh.KhError) as e:
-            tab.assemble()
-        assert e.value.status == kh.KH_ERR_CONVERGE
+    text = "".join(lines).encode()
+    want = oracle.assemble_text(text, k)[0]
+    assert want == (a + "\n" + b + a[6 + k - 1:] + "\n").encode()
+    outcomes = set()
+    for split in (1, 2, 8, 1 << 20):
+        with kh.KmerHashTable(k, 64) as tab:
+            tab.set_option("split_buckets", split)
+            tab.insert_lines(text)
+            try:
+                buf, _, _ = tab.assemble()
+                assert buf.tobytes() == want
+                outcomes.add("same")
+            except kh.KhError as e:
+                assert e.status == kh.KH_ERR_CONVERGE
+                outcomes.add("refused")
+    assert "refused" in outcomes               # split_buckets=1 puts a segment boundary on the shared part
 
 
 # ---------------------------------------------------------------- scale -------------------
