@@ -1,0 +1,66 @@
+"""GPU: the kmer_hash_<K> command line end to end, the way scripts/check_it.sh uses it."""
+import os
+import re
+import subprocess
+
+import pytest
+
+import oracle
+from conftest import ROOT
+from tools import kmergen
+
+pytestmark = pytest.mark.gpu
+
+
+@pytest.fixture(scope="module")
+def bins():
+    from cs267_hw3_b200 import build
+    return dict(zip((19, 31, 51), build.build_cli()))
+
+
+@pytest.mark.parametrize("k,n,c", [(19, 200000, 300), (31, 100000, 900), (51, 150000, 1500)])
+def test_check_script_passes(bins, tmp_path, k, n, c):
+    """tools/check.sh = scripts/check_it.sh:32,47-59 around our binary: sorted output == solution."""
+    gen = os.path.join(ROOT, "tools", "gen_kmers")
+    if not os.path.exists(gen):
+        kmergen.build()
+    inp = tmp_path / "synth.txt"
+    subprocess.run([gen, str(k), str(n), str(c), str(inp), "--seed", "11"], check=True, capture_output=True)
+    r = subprocess.run([os.path.join(ROOT, "tools", "check.sh"), str(inp)], cwd=tmp_path, capture_output=True, text=True)
+    assert r.returncode == 0, r.stdout + r.stderr
+    assert f"PASSED: {inp}" in r.stdout
+    # the metrics line of test mode, format of kmer_hash.cpp:71-78
+    assert re.search(rf"Rank 0 reconstructed {c} contigs with {n} nodes from 0 start nodes\. "
+                     r"\(\d+\.\d{6} read, \d+\.\d{6} insert, \d+\.\d{6} total\)", r.stdout)
+
+
+def test_cli_output_equals_reference_bytes(bins, tmp_path):
+    """Same file the unmodified reference writes (start-node order, not just the sorted set)."""
+    k = 19
+    d = kmergen.Dataset(k, 60000, 200, seed=21)
+    inp = tmp_path / "in.txt"
+    d.text().tofile(inp)
+    subprocess.run([bins[k], str(inp), "test", "mine"], cwd=tmp_path, check=True, capture_output=True)
+    mine = (tmp_path / "mine_0.dat").read_bytes()
+    assert mine == d.expected()[0]
+    if oracle.ref_binary(k):
+        assert mine == oracle.run_reference(k, str(inp), str(tmp_path))
+
+
+def test_cli_timing_lines(bins, tmp_path):
+    d = kmergen.Dataset(51, 50000, 100, seed=22)
+    inp = tmp_path / "in.txt"
+    d.text().tofile(inp)
+    r = subprocess.run([bins[51], str(inp), "verbose"], cwd=tmp_path, capture_output=True, text=True, check=True)
+    lines = r.stdout.strip().split("\n")
+    assert lines[0] == "Initializing hash table of size 100000 for 50000 kmers."     # kmer_hash.cpp:115
+    assert lines[1] == "Finished reading kmers."                                      # :124
+    assert re.fullmatch(r"Finished inserting in \d+\.\d{6} sec", lines[2])            # :144
+    assert re.fullmatch(r"Assembled in \d+\.\d{6} total", lines[3])                   # :145
+
+
+def test_cli_missing_kmer_aborts_like_the_reference(bins, tmp_path):
+    inp = tmp_path / "bad.txt"
+    inp.write_bytes(b"ACGTACGTACGTACGTACG FC\n")
+    r = subprocess.run([bins[19], str(inp), "test"], cwd=tmp_path, capture_output=True, text=True)
+    assert r.returncode == -6 and "Error: k-mer not found in Distributed HashMap." in r.stderr   # kmer_hash.cpp:47-49
