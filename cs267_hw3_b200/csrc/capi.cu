@@ -8,6 +8,7 @@
 //   per assemble link[seg] u64, seglen[seg] u8, tmp[seg][seg_chars], contig_len/pre/off, out
 // Scratch is grow-only and reused across calls so a steady-state step allocates nothing.
 #include <algorithm>
+#include <cmath>
 #include <cstdio>
 #include <cstdlib>
 #include <cstring>
@@ -39,6 +40,12 @@ struct kh_table {
     DevBuf starts;
     u64 n_starts = 0;
     DevBuf mask, tile_counts, tile_offs, scan_blocks;
+    DevBuf part_hist, part_base, part_cursor, grouped;
+    int partition_mode = -1;          // -1 auto, 0 never, 1 always (KH_PARTITION)
+    u64 part_bytes = 16ull << 20;     // table bytes per partition (KH_PART_MB)
+    bool part_attr_set = false;
+    int ins_mode = 1;                 // KH_INS_MODE: 0 read-then-CAS, 1 CAS-first
+    int warm_ahead = 1;               // KH_WARM_AHEAD: table regions prefetched ahead of the inserts (0 = off)
     Counters* d_ctr = nullptr;
     Counters* h_ctr = nullptr;
     DevBuf link, seglen, tmp, contig_len, contig_pre, contig_off, out;
@@ -143,19 +150,69 @@ __global__ void init_assemble_kernel(Counters* c, u32 first_overflow_seg) {
     for (int i = 0; i < 40; ++i) c->flags[i] = 0;
 }
 
+static size_t partition_smem(int W, u32 nparts, int pb) {
+    const size_t un = std::max<size_t>((size_t)kPartTile * (W == 1 ? 8 : 16), (size_t)kPartTile * pb);
+    return ((12 * (size_t)nparts + 2 * kPartTile + 15) & ~(size_t)15) + un;
+}
+
 template <int W>
 int insert_device_impl(kh_table* t, const unsigned char* recs, u64 n, bool record_start) {
     typedef typename Slot<W>::value_t V;
     if (n == 0) return KH_OK;
     if (n >= 0xFFF00000ull) return fail(t, KH_ERR_ARG, "at most 2^32-2^20 records per insert call; split the batch");
     const u64 ntiles = (n + kInsTile - 1) / kInsTile;
-    KH_TRY(ensure(t, t->mask, ntiles * (kInsTile / 32) * sizeof(u32)));
-    KH_TRY(ensure(t, t->tile_counts, ntiles * sizeof(u32)));
-    KH_TRY(ensure(t, t->tile_offs, ntiles * sizeof(u64)));
+    KH_TRY(ensure(t, t->mask, (ntiles + 1) * (kInsTile / 32) * sizeof(u32)));
+    KH_TRY(ensure(t, t->tile_counts, (ntiles + 1) * sizeof(u32)));
+    KH_TRY(ensure(t, t->tile_offs, (ntiles + 1) * sizeof(u64)));
+    // Tables larger than L2 get their records grouped by table region first (see kernels.cuh K2p).
+    const bool part = t->partition_mode == 1 || (t->partition_mode < 0 && t->table_bytes > (64ull << 20) && n >= (1u << 16));
+    u32 part_shift = 0, nparts = 1, bpp = 1;
+    u64 part_cap = 0;
+    if (part) {
+        while ((32ull << part_shift) < t->part_bytes) ++part_shift;
+        while (((t->nbuckets - 1) >> part_shift) + 1 > (u64)kMaxParts) ++part_shift;
+        nparts = (u32)(((t->nbuckets - 1) >> part_shift) + 1);
+        // a partition's expected share of n plus 6 sigma plus slack, rounded to whole insert tiles
+        const double share = (double)n * (double)std::min<u64>(t->nbuckets, 1ull << part_shift) / (double)t->nbuckets;
+        part_cap = (u64)(share + 6.0 * std::sqrt(share + 1.0) + 64.0);
+        part_cap = (part_cap + kInsTile - 1) / kInsTile * kInsTile;
+        bpp = (u32)(part_cap / kInsTile);
+        KH_TRY(ensure(t, t->part_cursor, kMaxParts * sizeof(u32)));
+        KH_TRY(ensure(t, t->grouped, (u64)nparts * part_cap * sizeof(V)));
+        if (!t->part_attr_set) {
+            KH_CUDA(t, cudaFuncSetAttribute(partition_kernel<W>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                            (int)partition_smem(W, kMaxParts, 18)));
+            t->part_attr_set = true;
+        }
+    }
     if (record_start) KH_CUDA(t, cudaEventRecord(t->ev[EV_INS0], t->stream));
-    insert_kernel<W><<<(unsigned)ntiles, kInsThreads, (size_t)kInsTile * t->pb, t->stream>>>(
-        recs, n, t->k, static_cast<V*>(t->table), t->nbuckets, static_cast<u32*>(t->mask.p),
-        static_cast<u32*>(t->tile_counts.p), t->d_ctr);
+    if (!part) {
+        insert_kernel<W><<<(unsigned)ntiles, kInsThreads, (size_t)kInsTile * t->pb, t->stream>>>(
+            recs, n, t->k, static_cast<V*>(t->table), t->nbuckets, static_cast<u32*>(t->mask.p),
+            static_cast<u32*>(t->tile_counts.p), t->d_ctr);
+    } else {
+        KH_CUDA(t, cudaMemsetAsync(t->part_cursor.p, 0, kMaxParts * sizeof(u32), t->stream));
+        const u32 ahead = (u32)std::max(0, t->warm_ahead);
+        if (ahead) {
+            const u64 warm_buckets = std::min<u64>(t->nbuckets, (u64)ahead << part_shift);
+            warm_kernel<<<(unsigned)t->sm_count * 4, 256, 0, t->stream>>>(static_cast<const char*>(t->table),
+                                                                         (warm_buckets * 32 + 127) >> 7);
+        }
+        const u64 pblocks = (n + kPartTile - 1) / kPartTile;
+        partition_kernel<W><<<(unsigned)pblocks, kPartThreads, partition_smem(W, nparts, t->pb), t->stream>>>(
+            recs, n, t->k, t->nbuckets, part_shift, nparts, part_cap, static_cast<u32*>(t->part_cursor.p),
+            static_cast<V*>(t->grouped.p), static_cast<V*>(t->table), static_cast<u32*>(t->mask.p),
+            static_cast<u32*>(t->tile_counts.p), t->d_ctr);
+        const unsigned iblocks = nparts * bpp;
+        if (t->ins_mode == 0)
+            insert_slots_kernel<W, 0><<<iblocks, kInsThreads, 0, t->stream>>>(
+                static_cast<const V*>(t->grouped.p), static_cast<const u32*>(t->part_cursor.p), part_cap, bpp, nparts,
+                part_shift, ahead, static_cast<V*>(t->table), t->nbuckets, t->d_ctr);
+        else
+            insert_slots_kernel<W, 1><<<iblocks, kInsThreads, 0, t->stream>>>(
+                static_cast<const V*>(t->grouped.p), static_cast<const u32*>(t->part_cursor.p), part_cap, bpp, nparts,
+                part_shift, ahead, static_cast<V*>(t->table), t->nbuckets, t->d_ctr);
+    }
     KH_CUDA(t, cudaGetLastError());
     KH_TRY(device_scan(t, static_cast<u32*>(t->tile_counts.p), ntiles, static_cast<u64*>(t->tile_offs.p),
                        &t->d_ctr->scan_total));
@@ -249,8 +306,7 @@ int assemble_impl(kh_table* t) {
     KH_TRY(device_scan(t, rp.contig_len, n_starts + 1, static_cast<u64*>(t->contig_off.p), &t->d_ctr->contig_bytes));
     KH_CUDA(t, cudaEventRecord(t->ev[EV_RANK], t->stream));
 
-    const u64 seg_threads = seg_cap * 16;
-    emit_segments_kernel<<<(unsigned)((seg_threads + 255) / 256), 256, 0, t->stream>>>(
+    emit_segments_kernel<<<(unsigned)((seg_cap + 255) / 256), 256, 0, t->stream>>>(
         wp.link, wp.seglen, wp.tmp, t->seg_chars, (u32)seg_cap, t->d_ctr, rp.contig_pre,
         static_cast<u64*>(t->contig_off.p), t->k, out_cap, static_cast<char*>(t->out.p));
     if (n_starts) {
@@ -386,6 +442,11 @@ int kh_create(int k, uint64_t n_expected, double load_factor, int device, kh_tab
     memset(t->h_ctr, 0, sizeof(Counters));
     int v = env_int("KH_SPLIT_BUCKETS", 0);
     if (v > 0 && set_option(t, "split_buckets", v) != KH_OK) fprintf(stderr, "libkh_b200: ignoring KH_SPLIT_BUCKETS=%d\n", v);
+    t->partition_mode = env_int("KH_PARTITION", -1);
+    t->ins_mode = env_int("KH_INS_MODE", 1);
+    t->warm_ahead = env_int("KH_WARM_AHEAD", 1);
+    v = env_int("KH_PART_MB", 0);
+    if (v > 0) t->part_bytes = (u64)v << 20;
     v = env_int("KH_SEG_CHARS", 0);
     if (v > 0 && set_option(t, "seg_chars", v) != KH_OK) fprintf(stderr, "libkh_b200: ignoring KH_SEG_CHARS=%d\n", v);
     t->err.clear();
@@ -398,7 +459,7 @@ int kh_destroy(kh_table* t) {
     cudaSetDevice(t->device);
     if (t->own_stream) cudaStreamSynchronize(t->own_stream);
     DevBuf* bufs[] = {&t->starts, &t->mask, &t->tile_counts, &t->tile_offs, &t->scan_blocks, &t->link, &t->seglen,
-                      &t->tmp, &t->contig_len, &t->contig_pre, &t->contig_off, &t->out, &t->stage[0], &t->stage[1],
+                      &t->tmp, &t->part_hist, &t->part_base, &t->part_cursor, &t->grouped, &t->contig_len, &t->contig_pre, &t->contig_off, &t->out, &t->stage[0], &t->stage[1],
                       &t->text_stage, &t->scratch_a, &t->scratch_b, &t->scratch_c};
     for (DevBuf* b : bufs) if (b->p) cudaFree(b->p);
     if (t->table) cudaFree(t->table);

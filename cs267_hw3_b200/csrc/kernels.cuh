@@ -192,15 +192,8 @@ insert_kernel(const unsigned char* __restrict__ recs, u64 n, int k,
     }
 }
 
-// =========================================================================================
-// exclusive scan of u32 counts -> u64 offsets (three small kernels)
-// =========================================================================================
-constexpr int kScanThreads = 256;
-constexpr int kScanPerThread = 8;
-constexpr int kScanTile = kScanThreads * kScanPerThread;   // 2048
-
+// block-wide exclusive scan helper (also used by the scan kernels below)
 __device__ __forceinline__ u64 block_exclusive_scan(u64 x, u64* s_warp, u64& block_total) {
-    // inclusive warp scan
     u64 inc = x;
 #pragma unroll
     for (int d = 1; d < 32; d <<= 1) {
@@ -218,8 +211,8 @@ __device__ __forceinline__ u64 block_exclusive_scan(u64 x, u64* s_warp, u64& blo
             const u64 y = __shfl_up_sync(kFullMask, winc, d);
             if (lane_id() >= (u32)d) winc += y;
         }
-        if (lane_id() < nwarps) s_warp[lane_id()] = winc - w;      // exclusive warp bases
-        if (lane_id() == 31) s_warp[32] = winc;                    // block total
+        if (lane_id() < nwarps) s_warp[lane_id()] = winc - w;
+        if (lane_id() == 31) s_warp[32] = winc;
     }
     __syncthreads();
     block_total = s_warp[32];
@@ -227,6 +220,248 @@ __device__ __forceinline__ u64 block_exclusive_scan(u64 x, u64* s_warp, u64& blo
     __syncthreads();
     return r;
 }
+
+// =========================================================================================
+// K2p  partitioned insert: prep (histogram + start bitmask) -> partition -> insert_slots
+// =========================================================================================
+// Random CAS traffic over a multi-GB table is bound by DRAM row activations (~16 G read+CAS/s
+// measured, profiles/r01_random_access_probe_occ8.txt); the same traffic against an L2-resident
+// region runs at >50-120 G/s.  So for tables larger than L2 the records are first grouped by
+// table region ("partition" = 2^part_shift consecutive buckets, ~16 MB of table) with one streaming
+// counting-sort pass; the insert kernel then sweeps the grouped array front to back, and the blocks
+// in flight at any moment touch only a couple of regions.  The table semantics are unchanged
+// (same buckets, same probing) -- only the order of insertion differs.
+constexpr int kMaxParts = 1024;
+constexpr int kPartThreads = 256;
+constexpr int kPartPerThread = 8;
+constexpr int kPartTile = kPartThreads * kPartPerThread;     // 2048 records per block
+
+// pass 1: block-local counting sort by partition, coalesced runs into per-partition buffers of fixed
+// capacity (no histogram pass: a partition's expected share is known from the uniform hash; space is
+// reserved with one atomicAdd per (block, partition); a record that does not fit -- never in practice
+// -- is inserted directly).  Also produces the start bitmask / per-tile start counts that
+// scatter_starts_kernel consumes (tiles of kInsTile records, identical to insert_kernel's).
+template <int W>
+__global__ void __launch_bounds__(kPartThreads)
+partition_kernel(const unsigned char* __restrict__ recs, u64 n, int k, u64 nbuckets, u32 part_shift, u32 nparts,
+                 u64 part_cap, u32* __restrict__ cursor, typename Slot<W>::value_t* __restrict__ grouped,
+                 typename Slot<W>::value_t* table, u32* __restrict__ start_mask, u32* __restrict__ tile_starts,
+                 Counters* ctr) {
+    typedef Slot<W> S;
+    typedef typename S::value_t V;
+    extern __shared__ __align__(16) unsigned char s_raw[];
+    // layout: hist u32[nparts] | off u32[nparts] | gbase u32[nparts] | part id per sorted position u16[kPartTile]
+    //         | union { record bytes (phase 1), sorted slots (phase 3) }
+    u32* s_hist = reinterpret_cast<u32*>(s_raw);
+    u32* s_off = s_hist + nparts;
+    u32* s_gbase = s_off + nparts;
+    unsigned short* s_pid = reinterpret_cast<unsigned short*>(s_raw + 12 * (size_t)nparts);
+    unsigned char* s_union = s_raw + ((12 * (size_t)nparts + 2 * kPartTile + 15) & ~(size_t)15);
+    unsigned char* s_rec = s_union;
+    V* s_sorted = reinterpret_cast<V*>(s_union);
+    __shared__ u64 s_warp[33];
+    __shared__ u32 s_starts[kPartTile / kInsTile], s_err, s_direct_ins, s_direct_dup;
+    const int pl = (k + 3) >> 2, pb = pl + 2;
+    const u64 rec0 = (u64)blockIdx.x * kPartTile;
+    const u32 cnt = (u32)min((u64)kPartTile, n - rec0);
+    for (u32 i = threadIdx.x; i < nparts; i += blockDim.x) s_hist[i] = 0;
+    if (threadIdx.x < kPartTile / kInsTile) s_starts[threadIdx.x] = 0;
+    if (threadIdx.x == 0) { s_err = 0; s_direct_ins = 0; s_direct_dup = 0; }
+    stage_in(s_rec, recs + rec0 * pb, cnt * pb);
+    __syncthreads();
+    V v[kPartPerThread];
+    u32 pid[kPartPerThread], rk[kPartPerThread];
+    u32 err = 0;
+#pragma unroll
+    for (int r = 0; r < kPartPerThread; ++r) {
+        const u32 j = threadIdx.x + r * kPartThreads;
+        bool ok = true, live = j < cnt;
+        pid[r] = 0xFFFFFFFFu;
+        v[r] = S::zero();
+        if (live) v[r] = S::from_record(s_rec + j * pb, k, pl, ok);
+        if (!ok) { err |= kErrBadInput; live = false; }
+        if (live) {
+            pid[r] = (u32)(bucket_of(S::hash(v[r]), nbuckets) >> part_shift);
+            rk[r] = atomicAdd(&s_hist[pid[r]], 1u);
+        }
+        // kmer_hash.cpp:27-31: which records start a contig, by position in the input
+        const u32 m = __ballot_sync(kFullMask, live && S::back(v[r]) == kExtF);
+        const u64 first = rec0 + (u64)r * kPartThreads + (threadIdx.x & ~31u);
+        if (lane_id() == 0 && first < n) {
+            start_mask[first >> 5] = m;
+            if (m) atomicAdd(&s_starts[(r * kPartThreads + threadIdx.x) / kInsTile], (u32)__popc(m));
+        }
+    }
+    err = __reduce_or_sync(kFullMask, err);
+    if (lane_id() == 0 && err) atomicOr(&s_err, err);
+    __syncthreads();
+    // block-local exclusive scan of the histogram (nparts <= 1024 = 4 per thread) + global reservations
+    {
+        u32 h[4], sum = 0;
+#pragma unroll
+        for (int q = 0; q < 4; ++q) {
+            const u32 i = threadIdx.x * 4 + q;
+            h[q] = i < nparts ? s_hist[i] : 0u;
+            sum += h[q];
+        }
+        u64 total;
+        u64 run = block_exclusive_scan((u64)sum, s_warp, total);
+#pragma unroll
+        for (int q = 0; q < 4; ++q) {
+            const u32 i = threadIdx.x * 4 + q;
+            if (i < nparts) {
+                s_off[i] = (u32)run;
+                s_gbase[i] = h[q] ? atomicAdd(&cursor[i], h[q]) : 0u;
+            }
+            run += h[q];
+        }
+    }
+    __syncthreads();
+#pragma unroll
+    for (int r = 0; r < kPartPerThread; ++r) {
+        if (pid[r] != 0xFFFFFFFFu) {
+            const u32 pos = s_off[pid[r]] + rk[r];
+            s_sorted[pos] = v[r];
+            s_pid[pos] = (unsigned short)pid[r];
+        }
+    }
+    __syncthreads();
+    const u32 good = s_off[nparts - 1] + s_hist[nparts - 1];
+    for (u32 pos = threadIdx.x; pos < good; pos += blockDim.x) {
+        const u32 p = s_pid[pos];
+        const u64 at = (u64)s_gbase[p] + (pos - s_off[p]);
+        if (at < part_cap) {
+            grouped[(u64)p * part_cap + at] = s_sorted[pos];
+        } else {                                           // partition buffer full: insert right here
+            const V val = s_sorted[pos];
+            const u64 b = bucket_of(S::hash(val), nbuckets);
+            u64 q[4];
+            load256_cg(table + b * S::kPerBucket, q);
+            const int rc = insert_one<W>(table, nbuckets, b, val, q);
+            if (rc == kInsInserted) atomicAdd(&s_direct_ins, 1u);
+            else if (rc == kInsDuplicate) atomicAdd(&s_direct_dup, 1u);
+            else atomicOr(&s_err, kErrTableFull);
+        }
+    }
+    __syncthreads();
+    if (threadIdx.x < kPartTile / kInsTile) {
+        const u64 tile = (u64)blockIdx.x * (kPartTile / kInsTile) + threadIdx.x;
+        if (tile * kInsTile < n) tile_starts[tile] = s_starts[threadIdx.x];
+    }
+    if (threadIdx.x == 0) {
+        if (s_err) atomicOr(&ctr->errors, s_err);
+        if (s_direct_ins) atomicAdd(&ctr->n_inserted, (u64)s_direct_ins);
+        if (s_direct_dup) atomicAdd(&ctr->n_duplicates, (u64)s_direct_dup);
+    }
+}
+
+// sequential L2 warm-up of the first table regions (the rest is warmed by insert_slots_kernel itself)
+__global__ void __launch_bounds__(256)
+warm_kernel(const char* __restrict__ base, u64 nlines) {
+    for (u64 l = (u64)blockIdx.x * blockDim.x + threadIdx.x; l < nlines; l += (u64)gridDim.x * blockDim.x)
+        asm volatile("prefetch.global.L2 [%0];" ::"l"(base + (l << 7)));
+}
+
+// pass 3: insert pre-converted slot values (grouped by partition, so the table traffic is L2-resident).
+// MODE 0: read the bucket, then CAS the first empty slot.  MODE 1: CAS slot 0 of the home bucket blind
+// (4 independent atomics in flight per thread) and fall back to read + CAS only when it is taken.
+template <int W, int MODE>
+__global__ void __launch_bounds__(kInsThreads)
+insert_slots_kernel(const typename Slot<W>::value_t* __restrict__ grouped, const u32* __restrict__ cursor,
+                    u64 part_cap, u32 blocks_per_part, u32 nparts, u32 part_shift, u32 warm_ahead,
+                    typename Slot<W>::value_t* table, u64 nbuckets, Counters* ctr) {
+    typedef Slot<W> S;
+    typedef typename S::value_t V;
+    __shared__ u32 s_inserted, s_dups, s_err;
+    if (threadIdx.x == 0) { s_inserted = 0; s_dups = 0; s_err = 0; }
+    __syncthreads();
+    const u32 part = blockIdx.x / blocks_per_part, jblk = blockIdx.x % blocks_per_part;
+    const u64 n = min((u64)cursor[part], part_cap);         // records grouped into this partition
+    const V* __restrict__ slots = grouped + (u64)part * part_cap;
+    const u64 base = (u64)jblk * kInsTile;
+    // Warm the table region `warm_ahead` partitions ahead of this block's own with sequential L2
+    // prefetches: a first touch by a random CAS costs a DRAM row activation each (the 41 G/s ceiling),
+    // a sequential sweep of the same region costs streaming bandwidth.  Non-destructive, so no ordering
+    // between blocks is needed.  Each block of partition p warms its share of region p + warm_ahead.
+    if (warm_ahead && part + warm_ahead < nparts) {
+        const u32 tp = part + warm_ahead;
+        const u64 b0 = (u64)tp << part_shift, b1 = min(nbuckets, ((u64)tp + 1) << part_shift);
+        const u64 nlines = ((b1 - b0) * 32 + 127) >> 7;
+        const u64 per = (nlines + blocks_per_part - 1) / blocks_per_part;
+        const u64 l0 = (u64)jblk * per, l1 = min(nlines, l0 + per);
+        const char* region = reinterpret_cast<const char*>(table) + b0 * 32;
+        for (u64 l = l0 + threadIdx.x; l < l1; l += blockDim.x)
+            asm volatile("prefetch.global.L2 [%0];" ::"l"(region + (l << 7)));
+    }
+    if (base >= n) return;
+    V v[kInsPerThread];
+    u64 b[kInsPerThread];
+    bool live[kInsPerThread];
+    u32 inserted = 0, dups = 0, err = 0;
+    if (MODE == 0) {
+        u64 q[kInsPerThread][4];
+#pragma unroll
+        for (int r = 0; r < kInsPerThread; ++r) {
+            const u64 i = base + (u64)r * kInsThreads + threadIdx.x;
+            live[r] = i < n;
+            v[r] = live[r] ? slots[i] : S::zero();
+            b[r] = live[r] ? bucket_of(S::hash(v[r]), nbuckets) : 0;
+            if (live[r]) load256_cg(table + b[r] * S::kPerBucket, q[r]);
+        }
+#pragma unroll
+        for (int r = 0; r < kInsPerThread; ++r) {
+            if (!live[r]) continue;
+            const int rc = insert_one<W>(table, nbuckets, b[r], v[r], q[r]);
+            inserted += (rc == kInsInserted);
+            dups += (rc == kInsDuplicate);
+            if (rc == kInsFull) err |= kErrTableFull;
+        }
+    } else {
+        V old[kInsPerThread];
+#pragma unroll
+        for (int r = 0; r < kInsPerThread; ++r) {
+            const u64 i = base + (u64)r * kInsThreads + threadIdx.x;
+            live[r] = i < n;
+            v[r] = live[r] ? slots[i] : S::zero();
+            b[r] = live[r] ? bucket_of(S::hash(v[r]), nbuckets) : 0;
+            old[r] = S::zero();
+            if (live[r]) old[r] = S::cas(table + b[r] * S::kPerBucket, S::zero(), v[r]);
+        }
+#pragma unroll
+        for (int r = 0; r < kInsPerThread; ++r) {
+            if (!live[r]) continue;
+            if (S::empty(old[r])) { ++inserted; continue; }
+            if (S::same_key(old[r], v[r])) { ++dups; continue; }
+            u64 q[4];
+            load256_cg(table + b[r] * S::kPerBucket, q);     // slot 0 is occupied by another key: general path
+            const int rc = insert_one<W>(table, nbuckets, b[r], v[r], q);
+            inserted += (rc == kInsInserted);
+            dups += (rc == kInsDuplicate);
+            if (rc == kInsFull) err |= kErrTableFull;
+        }
+    }
+    inserted = __reduce_add_sync(kFullMask, inserted);
+    dups = __reduce_add_sync(kFullMask, dups);
+    err = __reduce_or_sync(kFullMask, err);
+    if (lane_id() == 0) {
+        if (inserted) atomicAdd(&s_inserted, inserted);
+        if (dups) atomicAdd(&s_dups, dups);
+        if (err) atomicOr(&s_err, err);
+    }
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        if (s_inserted) atomicAdd(&ctr->n_inserted, (u64)s_inserted);
+        if (s_dups) atomicAdd(&ctr->n_duplicates, (u64)s_dups);
+        if (s_err) atomicOr(&ctr->errors, s_err);
+    }
+}
+
+// =========================================================================================
+// exclusive scan of u32 counts -> u64 offsets (three small kernels)
+// =========================================================================================
+constexpr int kScanThreads = 256;
+constexpr int kScanPerThread = 8;
+constexpr int kScanTile = kScanThreads * kScanPerThread;   // 2048
 
 __global__ void __launch_bounds__(kScanThreads)
 scan_reduce_kernel(const u32* __restrict__ in, u64 n, u64* __restrict__ block_sums) {
@@ -602,7 +837,9 @@ rank_kernel(const RankParams p) {
 // =========================================================================================
 // K6  emit
 // =========================================================================================
-// 16 lanes per segment: copy its characters to contig_off[c] + K + position.
+// One thread resolves one segment's destination (32 independent metadata chains in flight per warp:
+// link -> tail link -> contig_pre/off), then the warp copies the segments' characters cooperatively,
+// one coalesced byte-run per segment, to contig_off[c] + K + position.
 __global__ void __launch_bounds__(256)
 emit_segments_kernel(const u64* __restrict__ link, const unsigned char* __restrict__ seglen,
                      const unsigned char* __restrict__ tmp, u32 seg_chars, u32 seg_cap, Counters* ctr,
@@ -610,30 +847,46 @@ emit_segments_kernel(const u64* __restrict__ link, const unsigned char* __restri
                      int k, u64 out_cap, char* __restrict__ out) {
     // never write when the layout is not trustworthy (host reports the error)
     if (ctr->contig_bytes > out_cap || (ctr->errors & (kErrConverge | kErrCycle | kErrInternal))) return;
-    const u64 t = (u64)blockIdx.x * blockDim.x + threadIdx.x;
-    const u64 seg = t >> 4;
-    const u32 sub = (u32)(t & 15u);
+    const u64 seg = (u64)blockIdx.x * blockDim.x + threadIdx.x;
     const u32 nseg = min(ctr->next_seg, seg_cap);
-    if (seg >= nseg) return;
-    const u64 li = link[seg];
-    const u32 pi = (u32)(li >> 32);
-    if (pi == kLinkUnused || pi == kLinkTail) return;        // never walked / not on any start-rooted chain
-    u32 c, pos;
-    if (pi == kLinkClaimed) {
-        c = (u32)li;
-        pos = contig_pre[c];
-    } else {
-        const u64 lt = link[pi];
-        if ((u32)(lt >> 32) != kLinkClaimed) return;         // chain without a start node: ignored like the reference
-        c = (u32)lt;
-        const u32 pre = contig_pre[c];
-        if ((u32)li > pre) { if (sub == 0) atomicOr(&ctr->errors, kErrConverge); return; }
-        pos = pre - (u32)li;
+    u32 len = 0;
+    u64 dst = 0;
+    if (seg < nseg) {
+        const u64 li = link[seg];
+        const u32 pi = (u32)(li >> 32);
+        if (pi != kLinkUnused && pi != kLinkTail) {         // never walked / not on any start-rooted chain
+            bool ok = true;
+            u32 c = 0, pos = 0;
+            if (pi == kLinkClaimed) {
+                c = (u32)li;
+                pos = contig_pre[c];
+            } else {
+                const u64 lt = link[pi];
+                if ((u32)(lt >> 32) != kLinkClaimed) {
+                    ok = false;                             // chain without a start node: ignored like the reference
+                } else {
+                    c = (u32)lt;
+                    const u32 pre = contig_pre[c];
+                    if ((u32)li > pre) { atomicOr(&ctr->errors, kErrConverge); ok = false; }
+                    else pos = pre - (u32)li;
+                }
+            }
+            if (ok) {
+                len = seglen[seg];
+                dst = contig_off[c] + (u64)k + pos;
+            }
+        }
     }
-    const u32 len = seglen[seg];
-    char* dst = out + contig_off[c] + (u64)k + pos;
-    const unsigned char* src = tmp + seg * (u64)seg_chars;
-    for (u32 j = sub; j < len; j += 16) dst[j] = (char)src[j];
+    u32 todo = __ballot_sync(kFullMask, len > 0);
+    const u64 seg0 = seg - lane_id();
+    while (todo) {
+        const int src_lane = __ffs(todo) - 1;
+        todo &= todo - 1;
+        const u32 n = __shfl_sync(kFullMask, len, src_lane);
+        const u64 d = __shfl_sync(kFullMask, dst, src_lane);
+        const unsigned char* src = tmp + (seg0 + src_lane) * (u64)seg_chars;
+        for (u32 j = lane_id(); j < n; j += 32) out[d + j] = (char)src[j];
+    }
 }
 
 // first k-mer of each contig + trailing newline (read_kmers.hpp:84, kmer_hash.cpp:66)
