@@ -28,6 +28,10 @@ ABI_SYMBOLS = [
     "kh_pack_lines", "kh_pack_lines_device", "kh_insert_pairs", "kh_insert_pairs_device", "kh_insert_lines",
     "kh_find", "kh_find_device", "kh_assemble", "kh_assemble_device", "kh_get_stats", "kh_last_error",
     "kh_host_alloc", "kh_host_free", "kh_measure_random_sector_rate",
+    # sharded (multi-GPU) path
+    "kh_slot_bytes", "kh_shard_init", "kh_shard_export", "kh_shard_connect", "kh_shard_connect_local",
+    "kh_shard_owner_partition", "kh_insert_slots_device", "kh_shard_phase", "kh_shard_result",
+    "kh_device_alloc", "kh_device_free", "kh_copy_to_host", "kh_copy_device",
 ]
 
 

@@ -16,6 +16,7 @@
 
 #include "../../include/kh_capi.h"
 #include "kernels.cuh"
+#include "sharded.cuh"
 
 using namespace kh;
 
@@ -60,6 +61,15 @@ struct kh_table {
     std::string err;
     int sm_count = 148, walk_blocks_per_sm = 0, rank_blocks_per_sm = 0;
     u64 last_contig_bytes = 0, last_n_contigs = 0;
+    // ---- sharded (multi-GPU) mode ----
+    bool shard_on = false;
+    Peers peers = {};
+    void* ipc_opened[kMaxRanks][6] = {};
+    u64 shard_n_local_max = 0, shard_n_total = 0, shard_seg_cap = 0, shard_out_cap = 0;
+    u32 shard_n_split = 0;
+    DevBuf owner_ctr;                 // u64[3*kMaxRanks]: counts | base | cursor
+    DevBuf changed_flag;              // u32
+    unsigned shard_walk_blocks = 0;
 };
 
 namespace {
@@ -368,6 +378,188 @@ int set_option(kh_table* t, const std::string& name, int64_t value) {
 
 }  // namespace
 
+// ============================================================================ sharded ====
+enum { SH_TABLE, SH_LINK, SH_SEGLEN, SH_PRE, SH_OFF, SH_OUT, SH_NBUF };
+
+int shard_require(kh_table* t) {
+    if (!t->shard_on) return fail(t, KH_ERR_ARG, "handle is not in sharded mode (call kh_shard_init first)");
+    return KH_OK;
+}
+
+template <int W>
+int shard_init_impl(kh_table* t, int rank, int world, u64 n_local_max, u64 n_total) {
+    typedef typename Slot<W>::value_t V;
+    if (world < 1 || world > kMaxRanks || rank < 0 || rank >= world) return fail(t, KH_ERR_ARG, "1 <= world <= 8 and 0 <= rank < world");
+    t->shard_n_local_max = n_local_max; t->shard_n_total = n_total;
+    t->shard_n_split = (u32)(((t->nbuckets - 1) >> t->split_shift) + 1);
+    int bps = 0;
+    KH_CUDA(t, cudaOccupancyMaxActiveBlocksPerMultiprocessor(&bps, walk_sharded_kernel<W>, kWalkThreads, 0));
+    if (bps < 1) return fail(t, KH_ERR_CUDA, "walk_sharded_kernel does not fit on an SM");
+    t->shard_walk_blocks = (unsigned)(t->sm_count * bps);
+    const u64 nwarps = (u64)t->shard_walk_blocks * (kWalkThreads / 32);
+    const u64 seg_cap = (u64)t->shard_n_split + n_local_max + 2 * (n_total / t->seg_chars + 1) + (u64)kSegBatch * nwarps + 64;
+    if (seg_cap >= (u64)kLocalMask - 16) return fail(t, KH_ERR_ARG, "too many walk segments per GPU for 28-bit local ids");
+    t->shard_seg_cap = seg_cap;
+    t->shard_out_cap = n_total + n_local_max * (u64)(t->k + 1) + 64;
+    const u64 ntiles = (n_local_max + kInsTile - 1) / kInsTile + 1;
+    KH_TRY(ensure(t, t->link, seg_cap * sizeof(u64)));
+    KH_TRY(ensure(t, t->seglen, seg_cap));
+    KH_TRY(ensure(t, t->tmp, seg_cap * (u64)t->seg_chars + 16));
+    KH_TRY(ensure(t, t->contig_len, (n_local_max + 1) * sizeof(u32)));
+    KH_TRY(ensure(t, t->contig_pre, (n_local_max + 1) * sizeof(u32)));
+    KH_TRY(ensure(t, t->contig_off, (n_local_max + 1) * sizeof(u64)));
+    KH_TRY(ensure(t, t->out, t->shard_out_cap));
+    KH_TRY(ensure(t, t->starts, (n_local_max + 1) * sizeof(V)));
+    KH_TRY(ensure(t, t->mask, ntiles * (kInsTile / 32) * sizeof(u32)));
+    KH_TRY(ensure(t, t->tile_counts, ntiles * sizeof(u32)));
+    KH_TRY(ensure(t, t->tile_offs, ntiles * sizeof(u64)));
+    KH_TRY(ensure(t, t->scan_blocks, ((std::max(ntiles, n_local_max + 1) + kScanTile - 1) / kScanTile + 2) * sizeof(u64)));
+    KH_TRY(ensure(t, t->grouped, (n_local_max + 1) * sizeof(V)));
+    KH_TRY(ensure(t, t->owner_ctr, 3 * kMaxRanks * sizeof(u64)));
+    KH_TRY(ensure(t, t->changed_flag, 16));
+    Peers& pe = t->peers;
+    memset(&pe, 0, sizeof(pe));
+    pe.world = world; pe.rank = rank;
+    pe.table[rank] = t->table; pe.nbuckets[rank] = t->nbuckets;
+    pe.link[rank] = static_cast<u64*>(t->link.p); pe.seglen[rank] = static_cast<unsigned char*>(t->seglen.p);
+    pe.contig_pre[rank] = static_cast<u32*>(t->contig_pre.p); pe.contig_off[rank] = static_cast<u64*>(t->contig_off.p);
+    pe.out[rank] = static_cast<char*>(t->out.p); pe.out_cap[rank] = t->shard_out_cap;
+    t->shard_on = true;
+    return KH_OK;
+}
+
+template <int W>
+int shard_owner_partition_impl(kh_table* t, const unsigned char* recs, u64 n, const void** slots_out, u64* counts_out) {
+    typedef typename Slot<W>::value_t V;
+    const int world = t->peers.world;
+    if (n > t->shard_n_local_max) return fail(t, KH_ERR_ARG, "more records than kh_shard_init reserved (n_local_max)");
+    u64* octr = static_cast<u64*>(t->owner_ctr.p);
+    for (int w = 0; w < kMaxRanks; ++w) counts_out[w] = 0;
+    *slots_out = t->grouped.p;
+    if (n == 0) return KH_OK;
+    const u64 ntiles = (n + kInsTile - 1) / kInsTile;
+    KH_CUDA(t, cudaEventRecord(t->ev[EV_INS0], t->stream));
+    KH_CUDA(t, cudaMemsetAsync(octr, 0, 3 * kMaxRanks * sizeof(u64), t->stream));
+    owner_count_kernel<W><<<(unsigned)ntiles, kInsThreads, (size_t)kInsTile * t->pb, t->stream>>>(
+        recs, n, t->k, world, static_cast<u32*>(t->mask.p), static_cast<u32*>(t->tile_counts.p), octr, t->d_ctr);
+    KH_CUDA(t, cudaGetLastError());
+    KH_TRY(device_scan(t, static_cast<u32*>(t->tile_counts.p), ntiles, static_cast<u64*>(t->tile_offs.p), &t->d_ctr->scan_total));
+    u64 host_counts[kMaxRanks];
+    KH_CUDA(t, cudaMemcpyAsync(host_counts, octr, sizeof(host_counts), cudaMemcpyDeviceToHost, t->stream));
+    KH_TRY(read_counters(t));
+    const u32 e = t->h_ctr->errors;
+    if (e) { clear_error_bits(t); return status_from_errors(t, e); }
+    u64 base[kMaxRanks], run = 0;
+    for (int w = 0; w < kMaxRanks; ++w) { base[w] = run; run += host_counts[w]; counts_out[w] = host_counts[w]; }
+    KH_CUDA(t, cudaMemcpyAsync(octr + kMaxRanks, base, sizeof(base), cudaMemcpyHostToDevice, t->stream));
+    owner_scatter_kernel<W><<<(unsigned)ntiles, kInsThreads, (size_t)kInsTile * t->pb, t->stream>>>(
+        recs, n, t->k, world, octr + kMaxRanks, octr + 2 * kMaxRanks, static_cast<V*>(t->grouped.p));
+    const u64 fresh = t->h_ctr->scan_total;
+    if (t->n_starts + fresh > t->shard_n_local_max) return fail(t, KH_ERR_ARG, "more start nodes than reserved");
+    if (fresh) {
+        scatter_starts_kernel<W><<<(unsigned)((ntiles * 32 + 255) / 256), 256, 0, t->stream>>>(
+            recs, n, t->k, static_cast<u32*>(t->mask.p), static_cast<u64*>(t->tile_offs.p), ntiles,
+            static_cast<V*>(t->starts.p), t->n_starts);
+        t->n_starts += fresh;
+    }
+    KH_CUDA(t, cudaGetLastError());
+    KH_CUDA(t, cudaStreamSynchronize(t->stream));    // base[] lives on this stack frame
+    return KH_OK;
+}
+
+template <int W>
+int insert_slots_impl(kh_table* t, const void* slots, u64 n) {
+    typedef typename Slot<W>::value_t V;
+    if (n == 0) return KH_OK;
+    insert_slots_direct_kernel<W><<<(unsigned)((n + kInsTile - 1) / kInsTile), kInsThreads, 0, t->stream>>>(
+        static_cast<const V*>(slots), n, static_cast<V*>(t->table), t->nbuckets, t->d_ctr);
+    KH_CUDA(t, cudaGetLastError());
+    KH_CUDA(t, cudaEventRecord(t->ev[EV_INS1], t->stream));
+    t->have_ins = true;
+    return KH_OK;
+}
+
+template <int W>
+int shard_phase_impl(kh_table* t, int phase, int* flag_out) {
+    typedef typename Slot<W>::value_t V;
+    const Peers& pe = t->peers;
+    const u32 n_starts = (u32)t->n_starts, n_split = t->shard_n_split;
+    const unsigned gb = (unsigned)t->sm_count * 8;
+    if (flag_out) *flag_out = 0;
+    switch (phase) {
+    case 0: {   // walk
+        KH_CUDA(t, cudaEventRecord(t->ev[EV_AS0], t->stream));
+        init_assemble_kernel<<<1, 1, 0, t->stream>>>(t->d_ctr, n_split + n_starts);
+        KH_CUDA(t, cudaMemsetAsync(static_cast<u32*>(t->contig_len.p) + n_starts, 0, sizeof(u32), t->stream));
+        ShardWalkParams wp;
+        wp.peers = pe; wp.starts = t->starts.p;
+        wp.link = static_cast<u64*>(t->link.p); wp.seglen = static_cast<unsigned char*>(t->seglen.p);
+        wp.tmp = static_cast<unsigned char*>(t->tmp.p); wp.ctr = t->d_ctr;
+        wp.n_starts = n_starts; wp.n_split = n_split; wp.split_shift = t->split_shift;
+        wp.seg_chars = t->seg_chars; wp.seg_cap = (u32)t->shard_seg_cap; wp.k = t->k;
+        const u64 walkers = (u64)n_starts + n_split;
+        const unsigned blocks = (unsigned)std::max<u64>(1, std::min<u64>(t->shard_walk_blocks, (walkers + kWalkThreads - 1) / kWalkThreads));
+        walk_sharded_kernel<W><<<blocks, kWalkThreads, 0, t->stream>>>(wp);
+        KH_CUDA(t, cudaGetLastError());
+        KH_CUDA(t, cudaEventRecord(t->ev[EV_WALK], t->stream));
+        return KH_OK;
+    }
+    case 1: {   // one pointer-jumping round
+        u32* flag = static_cast<u32*>(t->changed_flag.p);
+        KH_CUDA(t, cudaMemsetAsync(flag, 0, sizeof(u32), t->stream));
+        rank_round_sharded_kernel<<<gb, 256, 0, t->stream>>>(pe, static_cast<u64*>(t->link.p), (u32)t->shard_seg_cap, t->d_ctr, flag);
+        KH_CUDA(t, cudaGetLastError());
+        u32 h = 0;
+        KH_CUDA(t, cudaMemcpyAsync(&h, flag, sizeof(u32), cudaMemcpyDeviceToHost, t->stream));
+        KH_CUDA(t, cudaStreamSynchronize(t->stream));
+        if (flag_out) *flag_out = (int)h;
+        t->stats.rank_rounds += 1;
+        return KH_OK;
+    }
+    case 2:     // contig lengths
+        contig_lengths_sharded_kernel<<<gb, 256, 0, t->stream>>>(pe, static_cast<u64*>(t->link.p), n_split, n_starts, t->k,
+            static_cast<u32*>(t->contig_len.p), static_cast<u32*>(t->contig_pre.p), t->d_ctr);
+        KH_CUDA(t, cudaGetLastError());
+        return KH_OK;
+    case 3:     // claim tails
+        claim_tails_sharded_kernel<<<gb, 256, 0, t->stream>>>(pe, static_cast<u64*>(t->link.p), n_split, n_starts,
+            static_cast<u32*>(t->contig_len.p), t->d_ctr);
+        KH_CUDA(t, cudaGetLastError());
+        return KH_OK;
+    case 4:     // offsets of the local contigs
+        KH_TRY(device_scan(t, static_cast<u32*>(t->contig_len.p), (u64)n_starts + 1, static_cast<u64*>(t->contig_off.p), &t->d_ctr->contig_bytes));
+        KH_CUDA(t, cudaEventRecord(t->ev[EV_RANK], t->stream));
+        return KH_OK;
+    case 5: {   // emit
+        emit_segments_sharded_kernel<<<(unsigned)((t->shard_seg_cap + 255) / 256), 256, 0, t->stream>>>(
+            pe, static_cast<u64*>(t->link.p), static_cast<unsigned char*>(t->seglen.p), static_cast<unsigned char*>(t->tmp.p),
+            t->seg_chars, (u32)t->shard_seg_cap, t->d_ctr, t->k);
+        if (n_starts) {
+            const u64 head_threads = (u64)n_starts * (u64)(t->k + 1);
+            emit_heads_kernel<W><<<(unsigned)((head_threads + 255) / 256), 256, 0, t->stream>>>(
+                static_cast<const V*>(t->starts.p), n_starts, t->k, static_cast<u32*>(t->contig_len.p),
+                static_cast<u64*>(t->contig_off.p), t->d_ctr, t->shard_out_cap, static_cast<char*>(t->out.p));
+        }
+        KH_CUDA(t, cudaGetLastError());
+        KH_CUDA(t, cudaEventRecord(t->ev[EV_AS1], t->stream));
+        t->have_as = true;
+        return KH_OK;
+    }
+    case 6: {   // collect counters (after the final barrier)
+        KH_TRY(read_counters(t));
+        t->stats.n_contigs = n_starts;
+        t->stats.n_nodes = t->h_ctr->n_nodes;
+        t->stats.contig_bytes = t->h_ctr->contig_bytes;
+        t->stats.n_segments = std::min<u64>(t->h_ctr->next_seg, t->shard_seg_cap);
+        if (flag_out) *flag_out = (int)t->h_ctr->errors;
+        if (t->h_ctr->errors) clear_error_bits(t);
+        return KH_OK;
+    }
+    default:
+        return fail(t, KH_ERR_ARG, "unknown shard phase");
+    }
+}
+
 // ============================================================================ C ABI ======
 extern "C" {
 
@@ -462,6 +654,9 @@ int kh_destroy(kh_table* t) {
                       &t->tmp, &t->part_hist, &t->part_base, &t->part_cursor, &t->grouped, &t->contig_len, &t->contig_pre, &t->contig_off, &t->out, &t->stage[0], &t->stage[1],
                       &t->text_stage, &t->scratch_a, &t->scratch_b, &t->scratch_c};
     for (DevBuf* b : bufs) if (b->p) cudaFree(b->p);
+    for (auto& row : t->ipc_opened) for (void* q : row) if (q) cudaIpcCloseMemHandle(q);
+    if (t->owner_ctr.p) cudaFree(t->owner_ctr.p);
+    if (t->changed_flag.p) cudaFree(t->changed_flag.p);
     if (t->table) cudaFree(t->table);
     if (t->d_ctr) cudaFree(t->d_ctr);
     if (t->h_ctr) cudaFreeHost(t->h_ctr);
@@ -488,6 +683,7 @@ int kh_clear(kh_table* t) {
     t->n_starts = 0;
     memset(t->h_ctr, 0, sizeof(Counters));
     t->stats.n_contigs = t->stats.n_nodes = t->stats.contig_bytes = t->stats.n_segments = 0;
+    t->stats.rank_rounds = 0;
     t->last_contig_bytes = t->last_n_contigs = 0;
     return KH_OK;
 }
@@ -731,6 +927,134 @@ int kh_measure_random_sector_rate(int device, uint64_t footprint_bytes, uint64_t
     cudaFree(buf); cudaFree(sink);
     if (e != cudaSuccess || ms <= 0.f) { cudaGetLastError(); return KH_ERR_CUDA; }
     *sectors_per_s = (double)(per * threads) / (ms * 1e-3);
+    return KH_OK;
+}
+
+
+// ---------------------------------------------------------------- sharded (multi-GPU) ------
+int kh_shard_init(kh_table* t, int rank, int world, uint64_t n_local_max, uint64_t n_total) {
+    if (!t) return KH_ERR_ARG;
+    KH_CUDA(t, cudaSetDevice(t->device));
+    return t->W == 1 ? shard_init_impl<1>(t, rank, world, n_local_max, n_total)
+                     : shard_init_impl<2>(t, rank, world, n_local_max, n_total);
+}
+
+int kh_shard_export(kh_table* t, void* handles_out, uint64_t* meta_out) {
+    if (!t || !handles_out || !meta_out) return KH_ERR_ARG;
+    KH_TRY(shard_require(t));
+    KH_CUDA(t, cudaSetDevice(t->device));
+    void* bufs[SH_NBUF] = {t->table, t->link.p, t->seglen.p, t->contig_pre.p, t->contig_off.p, t->out.p};
+    cudaIpcMemHandle_t* h = static_cast<cudaIpcMemHandle_t*>(handles_out);
+    for (int i = 0; i < SH_NBUF; ++i) KH_CUDA(t, cudaIpcGetMemHandle(&h[i], bufs[i]));
+    meta_out[0] = t->nbuckets;
+    meta_out[1] = t->shard_out_cap;
+    return KH_OK;
+}
+
+int kh_shard_connect(kh_table* t, const void* all_handles, const uint64_t* all_meta) {
+    if (!t || !all_handles || !all_meta) return KH_ERR_ARG;
+    KH_TRY(shard_require(t));
+    KH_CUDA(t, cudaSetDevice(t->device));
+    Peers& pe = t->peers;
+    const cudaIpcMemHandle_t* h = static_cast<const cudaIpcMemHandle_t*>(all_handles);
+    for (int r = 0; r < pe.world; ++r) {
+        if (r == pe.rank) continue;
+        void* p[SH_NBUF];
+        for (int i = 0; i < SH_NBUF; ++i) {
+            KH_CUDA(t, cudaIpcOpenMemHandle(&p[i], h[r * SH_NBUF + i], cudaIpcMemLazyEnablePeerAccess));
+            t->ipc_opened[r][i] = p[i];
+        }
+        pe.table[r] = p[SH_TABLE]; pe.nbuckets[r] = all_meta[2 * r];
+        pe.link[r] = static_cast<u64*>(p[SH_LINK]); pe.seglen[r] = static_cast<unsigned char*>(p[SH_SEGLEN]);
+        pe.contig_pre[r] = static_cast<u32*>(p[SH_PRE]); pe.contig_off[r] = static_cast<u64*>(p[SH_OFF]);
+        pe.out[r] = static_cast<char*>(p[SH_OUT]); pe.out_cap[r] = all_meta[2 * r + 1];
+    }
+    return KH_OK;
+}
+
+// All ranks live in this process (tests on one GPU, or one process driving several GPUs with peer
+// access enabled): wire the peers up from their handles directly.
+int kh_shard_connect_local(kh_table* t, kh_table* const* peers, int world) {
+    if (!t || !peers) return KH_ERR_ARG;
+    KH_TRY(shard_require(t));
+    if (world != t->peers.world) return fail(t, KH_ERR_ARG, "world does not match kh_shard_init");
+    Peers& pe = t->peers;
+    for (int r = 0; r < world; ++r) {
+        const kh_table* q = peers[r];
+        if (!q || !q->shard_on || q->k != t->k) return fail(t, KH_ERR_ARG, "peer handle is not an initialised shard of the same K");
+        if (q->device != t->device) {
+            int can = 0;
+            cudaDeviceCanAccessPeer(&can, t->device, q->device);
+            if (!can) return fail(t, KH_ERR_CUDA, "no peer access between the GPUs");
+            cudaSetDevice(t->device);
+            const cudaError_t e = cudaDeviceEnablePeerAccess(q->device, 0);
+            if (e != cudaSuccess && e != cudaErrorPeerAccessAlreadyEnabled) return fail(t, KH_ERR_CUDA, cudaGetErrorString(e));
+            cudaGetLastError();
+        }
+        pe.table[r] = q->table; pe.nbuckets[r] = q->nbuckets;
+        pe.link[r] = static_cast<u64*>(q->link.p); pe.seglen[r] = static_cast<unsigned char*>(q->seglen.p);
+        pe.contig_pre[r] = static_cast<u32*>(q->contig_pre.p); pe.contig_off[r] = static_cast<u64*>(q->contig_off.p);
+        pe.out[r] = static_cast<char*>(q->out.p); pe.out_cap[r] = q->shard_out_cap;
+    }
+    return KH_OK;
+}
+
+int kh_shard_owner_partition(kh_table* t, const void* pairs_dev, uint64_t n, const void** slots_dev_out, uint64_t* counts_out) {
+    if (!t || !slots_dev_out || !counts_out || (n && !pairs_dev)) return KH_ERR_ARG;
+    KH_TRY(shard_require(t));
+    KH_CUDA(t, cudaSetDevice(t->device));
+    return t->W == 1 ? shard_owner_partition_impl<1>(t, static_cast<const unsigned char*>(pairs_dev), n, slots_dev_out, reinterpret_cast<u64*>(counts_out))
+                     : shard_owner_partition_impl<2>(t, static_cast<const unsigned char*>(pairs_dev), n, slots_dev_out, reinterpret_cast<u64*>(counts_out));
+}
+
+int kh_insert_slots_device(kh_table* t, const void* slots_dev, uint64_t n) {
+    if (!t || (n && !slots_dev)) return KH_ERR_ARG;
+    KH_CUDA(t, cudaSetDevice(t->device));
+    return t->W == 1 ? insert_slots_impl<1>(t, slots_dev, n) : insert_slots_impl<2>(t, slots_dev, n);
+}
+
+int kh_shard_phase(kh_table* t, int phase, int* flag_out) {
+    if (!t) return KH_ERR_ARG;
+    KH_TRY(shard_require(t));
+    KH_CUDA(t, cudaSetDevice(t->device));
+    return t->W == 1 ? shard_phase_impl<1>(t, phase, flag_out) : shard_phase_impl<2>(t, phase, flag_out);
+}
+
+int kh_shard_result(kh_table* t, const char** contigs_dev, const uint64_t** offsets_dev,
+                    uint64_t* n_contigs, uint64_t* contig_bytes, uint64_t* n_nodes) {
+    if (!t) return KH_ERR_ARG;
+    KH_TRY(shard_require(t));
+    if (contigs_dev) *contigs_dev = static_cast<const char*>(t->out.p);
+    if (offsets_dev) *offsets_dev = static_cast<const uint64_t*>(t->contig_off.p);
+    if (n_contigs) *n_contigs = t->stats.n_contigs;
+    if (contig_bytes) *contig_bytes = t->stats.contig_bytes;
+    if (n_nodes) *n_nodes = t->stats.n_nodes;
+    return KH_OK;
+}
+
+uint64_t kh_slot_bytes(int k) { return (2 * k + 6 <= 64) ? 8 : 16; }
+
+// device -> host copy on the handle's stream, synchronous (tests / result collection)
+int kh_copy_to_host(kh_table* t, void* dst_host, const void* src_dev, uint64_t bytes) {
+    if (!t || (bytes && (!dst_host || !src_dev))) return KH_ERR_ARG;
+    KH_CUDA(t, cudaSetDevice(t->device));
+    if (bytes) KH_CUDA(t, cudaMemcpyAsync(dst_host, src_dev, bytes, cudaMemcpyDeviceToHost, t->stream));
+    KH_CUDA(t, cudaStreamSynchronize(t->stream));
+    return KH_OK;
+}
+int kh_copy_device(kh_table* t, void* dst_dev, const void* src_dev, uint64_t bytes) {
+    if (!t || (bytes && (!dst_dev || !src_dev))) return KH_ERR_ARG;
+    KH_CUDA(t, cudaSetDevice(t->device));
+    if (bytes) KH_CUDA(t, cudaMemcpyAsync(dst_dev, src_dev, bytes, cudaMemcpyDefault, t->stream));
+    return KH_OK;
+}
+int kh_device_alloc(void** ptr, uint64_t bytes) {
+    if (!ptr) return KH_ERR_ARG;
+    if (cudaMalloc(ptr, bytes ? bytes : 1) != cudaSuccess) { cudaGetLastError(); *ptr = nullptr; return KH_ERR_NOMEM; }
+    return KH_OK;
+}
+int kh_device_free(void* ptr) {
+    if (ptr && cudaFree(ptr) != cudaSuccess) { cudaGetLastError(); return KH_ERR_CUDA; }
     return KH_OK;
 }
 

@@ -1,0 +1,452 @@
+// sharded.cuh -- kernels of the multi-GPU (hash-sharded) path.
+//
+// Replaces the UPC++ side of the reference: owner = hash(key) % ranks
+// (hash_map.hpp:28-30), one batched RPC per destination for inserts (hash_map.hpp:38-46, 64-77)
+// and one blocking RPC round trip per remote lookup (hash_map.hpp:93-100).
+//
+//   K7 owner_count / owner_scatter   records -> slot values grouped by owning GPU (+ start bitmask);
+//                                    the groups travel with one NCCL all-to-all (torch.distributed)
+//   K2 insert_slots_direct           insert received slot values into the local shard
+//   K8 walk_sharded                  like walk_kernel, but a successor lookup reads the OWNER's table
+//                                    directly through its NVLink peer mapping: the one-sided analogue of
+//                                    the reference's find() RPC, with ~300k lookups in flight per GPU
+//                                    instead of one blocking round trip per rank
+//      rank_round / lengths / claim  pointer jumping over segment lists that live on different GPUs
+//      emit_*_sharded                each GPU copies its segments' characters into the output buffer
+//                                    of the GPU that owns the contig's start node (peer stores)
+//
+// Global segment id = (rank << kRankShift) | local id.  Local ids: [0, n_split) splitters of the
+// local shard, [n_split, n_split + n_starts) start nodes parsed by this rank, then overflow.
+#pragma once
+#include "kernels.cuh"
+
+namespace kh {
+
+constexpr int kMaxRanks = 8;
+constexpr u32 kRankShift = 28;
+constexpr u32 kLocalMask = (1u << kRankShift) - 1u;
+
+struct Peers {
+    const void* table[kMaxRanks];
+    u64 nbuckets[kMaxRanks];
+    u64* link[kMaxRanks];
+    unsigned char* seglen[kMaxRanks];
+    u32* contig_pre[kMaxRanks];
+    u64* contig_off[kMaxRanks];
+    char* out[kMaxRanks];
+    u64 out_cap[kMaxRanks];
+    int world, rank;
+};
+
+template <int W>
+__device__ __forceinline__ u32 owner_of(typename Slot<W>::value_t v, int world) {
+    return (u32)__umul64hi(Slot<W>::owner_hash(v), (u64)world);
+}
+
+// ---- K7: group records by owner ---------------------------------------------------------
+// pass 1: per-owner counts + start bitmask / per-tile start counts (same tiles as insert_kernel)
+template <int W>
+__global__ void __launch_bounds__(kInsThreads)
+owner_count_kernel(const unsigned char* __restrict__ recs, u64 n, int k, int world,
+                   u32* __restrict__ start_mask, u32* __restrict__ tile_starts, u64* __restrict__ owner_counts,
+                   Counters* ctr) {
+    typedef Slot<W> S;
+    typedef typename S::value_t V;
+    extern __shared__ __align__(16) unsigned char s_rec[];
+    __shared__ u32 s_cnt[kMaxRanks], s_starts, s_err;
+    const int pl = (k + 3) >> 2, pb = pl + 2;
+    const u64 rec0 = (u64)blockIdx.x * kInsTile;
+    const u32 cnt = (u32)min((u64)kInsTile, n - rec0);
+    if (threadIdx.x < kMaxRanks) s_cnt[threadIdx.x] = 0;
+    if (threadIdx.x == 0) { s_starts = 0; s_err = 0; }
+    stage_in(s_rec, recs + rec0 * pb, cnt * pb);
+    __syncthreads();
+    u32 err = 0, starts = 0;
+#pragma unroll
+    for (int r = 0; r < kInsPerThread; ++r) {
+        const u32 j = threadIdx.x + r * kInsThreads;
+        bool live = j < cnt, ok = true;
+        V v = S::zero();
+        if (live) v = S::from_record(s_rec + j * pb, k, pl, ok);
+        if (!ok) { err |= kErrBadInput; live = false; }
+        const u32 o = live ? owner_of<W>(v, world) : 0u;
+        // warp-aggregate per owner (world <= 8)
+        for (int w = 0; w < world; ++w) {
+            const u32 m = __ballot_sync(kFullMask, live && o == (u32)w);
+            if (lane_id() == 0 && m) atomicAdd(&s_cnt[w], (u32)__popc(m));
+        }
+        const u32 m = __ballot_sync(kFullMask, live && S::back(v) == kExtF);
+        const u64 word = (rec0 + (u64)r * kInsThreads + (threadIdx.x & ~31u)) >> 5;
+        if (lane_id() == 0 && (word << 5) < n) { start_mask[word] = m; starts += __popc(m); }
+    }
+    err = __reduce_or_sync(kFullMask, err);
+    if (lane_id() == 0) {
+        if (starts) atomicAdd(&s_starts, starts);
+        if (err) atomicOr(&s_err, err);
+    }
+    __syncthreads();
+    if (threadIdx.x < (u32)world && s_cnt[threadIdx.x]) atomicAdd(&owner_counts[threadIdx.x], (u64)s_cnt[threadIdx.x]);
+    if (threadIdx.x == 0) {
+        tile_starts[blockIdx.x] = s_starts;
+        if (s_err) atomicOr(&ctr->errors, s_err);
+    }
+}
+
+// pass 2: scatter slot values to their owner's group (owner_base = exclusive prefix of the counts)
+template <int W>
+__global__ void __launch_bounds__(kInsThreads)
+owner_scatter_kernel(const unsigned char* __restrict__ recs, u64 n, int k, int world,
+                     const u64* __restrict__ owner_base, u64* __restrict__ owner_cursor,
+                     typename Slot<W>::value_t* __restrict__ grouped) {
+    typedef Slot<W> S;
+    typedef typename S::value_t V;
+    extern __shared__ __align__(16) unsigned char s_rec[];
+    __shared__ u32 s_cnt[kMaxRanks];
+    __shared__ u64 s_base[kMaxRanks];
+    const int pl = (k + 3) >> 2, pb = pl + 2;
+    const u64 rec0 = (u64)blockIdx.x * kInsTile;
+    const u32 cnt = (u32)min((u64)kInsTile, n - rec0);
+    if (threadIdx.x < kMaxRanks) s_cnt[threadIdx.x] = 0;
+    stage_in(s_rec, recs + rec0 * pb, cnt * pb);
+    __syncthreads();
+    V v[kInsPerThread];
+    u32 own[kInsPerThread], rk[kInsPerThread];
+#pragma unroll
+    for (int r = 0; r < kInsPerThread; ++r) {
+        const u32 j = threadIdx.x + r * kInsThreads;
+        bool ok = true;
+        own[r] = 0xFFFFFFFFu;
+        if (j < cnt) {
+            v[r] = S::from_record(s_rec + j * pb, k, pl, ok);
+            if (ok) {
+                own[r] = owner_of<W>(v[r], world);
+                rk[r] = atomicAdd(&s_cnt[own[r]], 1u);
+            }
+        }
+    }
+    __syncthreads();
+    if (threadIdx.x < (u32)world)
+        s_base[threadIdx.x] = owner_base[threadIdx.x] +
+                              (s_cnt[threadIdx.x] ? atomicAdd(&owner_cursor[threadIdx.x], (u64)s_cnt[threadIdx.x]) : 0ull);
+    __syncthreads();
+#pragma unroll
+    for (int r = 0; r < kInsPerThread; ++r)
+        if (own[r] != 0xFFFFFFFFu) grouped[s_base[own[r]] + rk[r]] = v[r];
+}
+
+// ---- K2 on received slot values ------------------------------------------------------------
+template <int W>
+__global__ void __launch_bounds__(kInsThreads)
+insert_slots_direct_kernel(const typename Slot<W>::value_t* __restrict__ slots, u64 n,
+                           typename Slot<W>::value_t* table, u64 nbuckets, Counters* ctr) {
+    typedef Slot<W> S;
+    typedef typename S::value_t V;
+    __shared__ u32 s_inserted, s_dups, s_err;
+    if (threadIdx.x == 0) { s_inserted = 0; s_dups = 0; s_err = 0; }
+    __syncthreads();
+    const u64 base = (u64)blockIdx.x * kInsTile;
+    V v[kInsPerThread];
+    u64 b[kInsPerThread];
+    u64 q[kInsPerThread][4];
+    bool live[kInsPerThread];
+#pragma unroll
+    for (int r = 0; r < kInsPerThread; ++r) {
+        const u64 i = base + (u64)r * kInsThreads + threadIdx.x;
+        live[r] = i < n;
+        v[r] = live[r] ? slots[i] : S::zero();
+        live[r] = live[r] && !S::empty(v[r]);
+        b[r] = live[r] ? bucket_of(S::hash(v[r]), nbuckets) : 0;
+        if (live[r]) load256_cg(table + b[r] * S::kPerBucket, q[r]);
+    }
+    u32 inserted = 0, dups = 0, err = 0;
+#pragma unroll
+    for (int r = 0; r < kInsPerThread; ++r) {
+        if (!live[r]) continue;
+        const int rc = insert_one<W>(table, nbuckets, b[r], v[r], q[r]);
+        inserted += (rc == kInsInserted);
+        dups += (rc == kInsDuplicate);
+        if (rc == kInsFull) err |= kErrTableFull;
+    }
+    inserted = __reduce_add_sync(kFullMask, inserted);
+    dups = __reduce_add_sync(kFullMask, dups);
+    err = __reduce_or_sync(kFullMask, err);
+    if (lane_id() == 0) {
+        if (inserted) atomicAdd(&s_inserted, inserted);
+        if (dups) atomicAdd(&s_dups, dups);
+        if (err) atomicOr(&s_err, err);
+    }
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        if (s_inserted) atomicAdd(&ctr->n_inserted, (u64)s_inserted);
+        if (s_dups) atomicAdd(&ctr->n_duplicates, (u64)s_dups);
+        if (s_err) atomicOr(&ctr->errors, s_err);
+    }
+}
+
+// ---- K8: walk with peer lookups -----------------------------------------------------------------
+struct ShardWalkParams {
+    Peers peers;
+    const void* starts;
+    u64* link;                 // local segment arrays
+    unsigned char* seglen;
+    unsigned char* tmp;
+    Counters* ctr;
+    u32 n_starts, n_split;     // local
+    u32 split_shift, seg_chars, seg_cap;
+    int k;
+};
+
+template <int W>
+__device__ __forceinline__ bool lookup_sharded(const Peers& pe, typename Slot<W>::value_t keybits,
+                                               typename Slot<W>::value_t& found, u32& owner, u64& bucket, int& slot) {
+    typedef Slot<W> S;
+    owner = owner_of<W>(keybits, pe.world);
+    const typename S::value_t* __restrict__ table = static_cast<const typename S::value_t*>(pe.table[owner]);
+    const u64 nb = pe.nbuckets[owner];
+    u64 b = bucket_of(S::hash(keybits), nb);
+    for (u64 tries = 0; tries < nb; ++tries) {
+        u64 q[4];
+        load256_nc(table + b * S::kPerBucket, q);          // local HBM or a peer's HBM over NVLink
+#pragma unroll
+        for (int i = 0; i < S::kPerBucket; ++i) {
+            const typename S::value_t cur = S::from_bucket(q, i);
+            if (S::empty(cur)) return false;
+            if (S::same_key(cur, keybits)) { found = cur; bucket = b; slot = i; return true; }
+        }
+        b = (b + 1 == nb) ? 0 : b + 1;
+    }
+    return false;
+}
+
+template <int W>
+__global__ void __launch_bounds__(kWalkThreads)
+walk_sharded_kernel(const ShardWalkParams p) {
+    typedef Slot<W> S;
+    typedef typename S::value_t V;
+    const V* __restrict__ table = static_cast<const V*>(p.peers.table[p.peers.rank]);
+    const V* __restrict__ starts = static_cast<const V*>(p.starts);
+    const u32 total = p.n_split + p.n_starts;
+    const u32 lane = lane_id();
+    const u32 lt_mask = (1u << lane) - 1u;
+    const u64 split_mask = (1ull << p.split_shift) - 1ull;
+    const u32 my_rank_bits = (u32)p.peers.rank << kRankShift;
+
+    u32 w_next = 0, w_end = 0;
+    bool exhausted = false;
+    u32 o_next = 0, o_end = 0;
+    bool active = false;
+    V cur = S::zero(), chk = S::zero();
+    u32 seg = 0, n = 0, steps = 0, limit = 256;
+    u64 acc = 0;
+
+    auto close = [&](u32 next) {       // next: global id or kLinkTail
+        if (n & 7u) *reinterpret_cast<u64*>(p.tmp + (u64)seg * p.seg_chars + (n & ~7u)) = acc;
+        p.seglen[seg] = (unsigned char)n;
+        p.link[seg] = ((u64)next << 32) | (next == kLinkTail ? 0u : n);
+        active = false;
+    };
+
+    for (;;) {
+        __syncwarp();
+        const u32 idle = __ballot_sync(kFullMask, !active);
+        if (idle && !exhausted) {
+            if (w_next == w_end) {
+                u32 base = 0;
+                if (lane == 0) base = atomicAdd(&p.ctr->next_walker, kWalkBatch);
+                base = __shfl_sync(kFullMask, base, 0);
+                w_next = min(base, total);
+                w_end = min(base + kWalkBatch, total);
+                exhausted = (w_next == w_end);
+            }
+            const u32 avail = w_end - w_next;
+            const u32 rank = __popc(idle & lt_mask);
+            if (!active && rank < avail) {
+                const u32 w = w_next + rank;
+                seg = w; n = 0; acc = 0; steps = 0; limit = 256;
+                if (w >= p.n_split) {
+                    cur = starts[w - p.n_split];
+                    active = true;
+                } else {
+                    const u64 b = (u64)w << p.split_shift;
+                    cur = S::load_one_nc(table + b * S::kPerBucket);
+                    if (S::empty(cur)) p.link[seg] = (u64)kLinkUnused << 32;
+                    else active = true;
+                }
+                chk = cur;
+            }
+            w_next += min((u32)__popc(idle), avail);
+        }
+        if (__ballot_sync(kFullMask, active) == 0) {
+            if (exhausted) break;
+            continue;
+        }
+        const u32 full = __ballot_sync(kFullMask, active && n == p.seg_chars && S::fwd(cur) != kExtF);
+        if (full) {
+            const u32 want = __popc(full);
+            if (o_end - o_next < want) {
+                for (u32 id = o_next + lane; id < o_end; id += 32) p.link[id] = (u64)kLinkUnused << 32;
+                u32 base = 0;
+                if (lane == 0) base = atomicAdd(&p.ctr->next_seg, kSegBatch);
+                base = __shfl_sync(kFullMask, base, 0);
+                o_next = base; o_end = base + kSegBatch;
+            }
+            if (full & (1u << lane)) {
+                const u32 ns = o_next + __popc(full & lt_mask);
+                if (ns >= p.seg_cap) {
+                    atomicOr(&p.ctr->errors, kErrInternal);
+                    close(kLinkTail);
+                } else {
+                    close(my_rank_bits | ns);
+                    active = true; seg = ns; n = 0; acc = 0;
+                }
+            }
+            o_next += want;
+        }
+        if (active) {
+            const u32 f = S::fwd(cur);
+            if (f == kExtF) {
+                close(kLinkTail);
+            } else {
+                acc |= (u64)ext_char(f) << (8u * (n & 7u));
+                ++n;
+                if ((n & 7u) == 0) {
+                    *reinterpret_cast<u64*>(p.tmp + (u64)seg * p.seg_chars + n - 8) = acc;
+                    acc = 0;
+                }
+                V nxt; u64 b; int s; u32 owner;
+                if (!lookup_sharded<W>(p.peers, S::next_key(cur, p.k), nxt, owner, b, s)) {
+                    atomicOr(&p.ctr->errors, kErrNotFound);
+                    close(kLinkTail);
+                } else if (s == 0 && (b & split_mask) == 0) {
+                    close((owner << kRankShift) | (u32)(b >> p.split_shift));   // the owner's splitter walker takes over
+                } else {
+                    cur = nxt;
+                    if (S::same_key(cur, chk)) {
+                        atomicOr(&p.ctr->errors, kErrCycle);
+                        close(kLinkTail);
+                    } else if (++steps == limit) {
+                        chk = cur; steps = 0; limit <<= 1;
+                    }
+                }
+            }
+        }
+    }
+    for (u32 id = o_next + lane; id < o_end; id += 32)
+        if (id < p.seg_cap) p.link[id] = (u64)kLinkUnused << 32;
+}
+
+// ---- pointer jumping across GPUs -------------------------------------------------------------
+__device__ __forceinline__ u64* peer_link(const Peers& pe, u32 gid) { return pe.link[gid >> kRankShift] + (gid & kLocalMask); }
+
+// one round over the local segments; *changed = 1 if any local link moved
+__global__ void __launch_bounds__(256)
+rank_round_sharded_kernel(const Peers pe, u64* link, u32 seg_cap, Counters* ctr, u32* changed) {
+    const u32 nseg = min(ctr->next_seg, seg_cap);
+    bool moved = false;
+    for (u64 i = (u64)blockIdx.x * blockDim.x + threadIdx.x; i < nseg; i += (u64)gridDim.x * blockDim.x) {
+        const u64 li = __ldcg(link + i);
+        const u32 pi = (u32)(li >> 32);
+        if (pi >= kLinkClaimed) continue;
+        const u64 lp = __ldcg(peer_link(pe, pi));
+        const u32 pp = (u32)(lp >> 32);
+        if (pp == kLinkTail) continue;
+        if (pp >= kLinkClaimed) { atomicOr(&ctr->errors, kErrInternal); continue; }
+        __stcg(link + i, ((u64)pp << 32) | (u32)((u32)li + (u32)lp));
+        moved = true;
+    }
+    if (__any_sync(kFullMask, moved) && lane_id() == 0) *changed = 1;
+}
+
+// contig lengths for the local start nodes (local ids n_split + c)
+__global__ void __launch_bounds__(256)
+contig_lengths_sharded_kernel(const Peers pe, const u64* link, u32 n_split, u32 n_starts, int k,
+                              u32* contig_len, u32* contig_pre, Counters* ctr) {
+    u64 nodes = 0;
+    for (u64 c = (u64)blockIdx.x * blockDim.x + threadIdx.x; c < n_starts; c += (u64)gridDim.x * blockDim.x) {
+        const u64 lc = __ldcg(link + n_split + c);
+        const u32 pc = (u32)(lc >> 32);
+        u32 tail_gid = ((u32)pe.rank << kRankShift) | (u32)(n_split + c), pre = 0;
+        bool ok = true;
+        if (pc != kLinkTail) {
+            tail_gid = pc; pre = (u32)lc;
+            ok = pc < kLinkClaimed && (u32)(__ldcg(peer_link(pe, pc)) >> 32) == kLinkTail;
+        }
+        if (!ok) {
+            atomicOr(&ctr->errors, kErrCycle);
+            contig_pre[c] = 0; contig_len[c] = 0;
+            continue;
+        }
+        const u32 chars = pre + pe.seglen[tail_gid >> kRankShift][tail_gid & kLocalMask];
+        contig_pre[c] = pre;
+        contig_len[c] = (u32)k + chars + 1u;
+        nodes += (u64)chars + 1u;
+    }
+    nodes = warp_sum_u64(nodes);
+    if (lane_id() == 0 && nodes) atomicAdd(&ctr->n_nodes, nodes);
+}
+
+// each contig claims its tail (possibly on another GPU): link[tail] = (CLAIMED, rank<<28 | contig)
+__global__ void __launch_bounds__(256)
+claim_tails_sharded_kernel(const Peers pe, const u64* link, u32 n_split, u32 n_starts, const u32* contig_len, Counters* ctr) {
+    for (u64 c = (u64)blockIdx.x * blockDim.x + threadIdx.x; c < n_starts; c += (u64)gridDim.x * blockDim.x) {
+        if (contig_len[c] == 0) continue;
+        const u32 pc = (u32)(__ldcg(link + n_split + c) >> 32);
+        const u32 tail_gid = (pc == kLinkTail) ? (((u32)pe.rank << kRankShift) | (u32)(n_split + c)) : pc;
+        const u64 want = (u64)kLinkTail << 32;
+        const u64 old = atomicCAS(peer_link(pe, tail_gid), want,
+                                  ((u64)kLinkClaimed << 32) | (((u32)pe.rank << kRankShift) | (u32)c));
+        if (old != want) atomicOr(&ctr->errors, kErrConverge);
+    }
+}
+
+// copy the local segments' characters into the output buffer of the GPU that owns the contig
+__global__ void __launch_bounds__(256)
+emit_segments_sharded_kernel(const Peers pe, const u64* __restrict__ link, const unsigned char* __restrict__ seglen,
+                             const unsigned char* __restrict__ tmp, u32 seg_chars, u32 seg_cap, Counters* ctr, int k) {
+    const u64 seg = (u64)blockIdx.x * blockDim.x + threadIdx.x;
+    const u32 nseg = min(ctr->next_seg, seg_cap);
+    u32 len = 0;
+    char* dst = nullptr;
+    if (seg < nseg) {
+        const u64 li = link[seg];
+        const u32 pi = (u32)(li >> 32);
+        if (pi != kLinkUnused && pi != kLinkTail) {
+            bool ok = true, is_tail = (pi == kLinkClaimed);
+            u32 cg = 0;
+            if (is_tail) {
+                cg = (u32)li;
+            } else {
+                const u64 lt = *peer_link(pe, pi);
+                if ((u32)(lt >> 32) != kLinkClaimed) ok = false;
+                else cg = (u32)lt;
+            }
+            if (ok) {
+                const u32 r = cg >> kRankShift, c = cg & kLocalMask;
+                const u32 pre = pe.contig_pre[r][c];
+                u32 pos = pre;
+                if (!is_tail) {
+                    if ((u32)li > pre) { atomicOr(&ctr->errors, kErrConverge); ok = false; }
+                    else pos = pre - (u32)li;
+                }
+                if (ok) {
+                    const u64 off = pe.contig_off[r][c] + (u64)k + pos;
+                    len = seglen[seg];
+                    if (off + len > pe.out_cap[r]) { atomicOr(&ctr->errors, kErrInternal); len = 0; }
+                    dst = pe.out[r] + off;
+                }
+            }
+        }
+    }
+    u32 todo = __ballot_sync(kFullMask, len > 0);
+    const u64 seg0 = seg - lane_id();
+    while (todo) {
+        const int src_lane = __ffs(todo) - 1;
+        todo &= todo - 1;
+        const u32 n = __shfl_sync(kFullMask, len, src_lane);
+        char* d = reinterpret_cast<char*>(__shfl_sync(kFullMask, reinterpret_cast<u64>(dst), src_lane));
+        const unsigned char* src = tmp + (seg0 + src_lane) * (u64)seg_chars;
+        for (u32 j = lane_id(); j < n; j += 32) d[j] = (char)src[j];
+    }
+}
+
+}  // namespace kh

@@ -1,0 +1,455 @@
+"""Multi-GPU (hash-sharded) insert + traverse: host-side orchestration over the C ABI.
+
+Replaces what the reference does with UPC++: the table is sharded by
+``owner = hash(key) % ranks`` (hash_map.hpp:28-30); every rank groups its block of records by owner
+(K7), the groups cross ranks in ONE all-to-all (NCCL over NVLink through torch.distributed; the
+reference issues one blocking RPC per destination, hash_map.hpp:64-77), each rank inserts what it
+received (K2).  During the walk a successor lookup reads the owner's table directly through its
+NVLink peer mapping (K8) -- the one-sided analogue of the reference's per-lookup RPC round trip
+(hash_map.hpp:93-100) -- and the segment lists are stitched by pointer jumping across GPUs.
+Rank r emits the contigs whose start node lies in its block of input lines, in input order
+(kmer_hash.cpp:27-31, read_kmers.hpp:55-58), exactly like the reference's ``<prefix>_<r>.dat``.
+
+Two communicators:
+  * TorchComm  -- one process per GPU (torchrun), NCCL for the exchange and the barriers, CUDA IPC for
+                  the peer mappings.  This is the product path.
+  * LocalComm  -- all ranks in one process (even on ONE GPU): the same kernels and phases with the
+                  exchange done by device copies.  Used by the tests on single-GPU boxes.
+The pure-host pieces (owner function mirror, exchange plan, ``exchange_bytes``) run on CPU tensors
+with the gloo backend (tests/test_sharded_host.py).
+"""
+from __future__ import annotations
+
+import ctypes as C
+import math
+
+import numpy as np
+
+MAX_RANKS = 8
+_M64 = (1 << 64) - 1
+
+
+# ---------------------------------------------------------------------------- host mirrors ----
+def _fmix64(z: int) -> int:
+    z ^= z >> 33
+    z = (z * 0xFF51AFD7ED558CCD) & _M64
+    z ^= z >> 33
+    z = (z * 0xC4CEB9FE1A85EC53) & _M64
+    z ^= z >> 33
+    return z
+
+
+def ext_code(ch: int) -> int:
+    return {65: 0, 67: 1, 71: 2, 84: 3, 70: 4}[ch]
+
+
+def slot_from_pair(pair: bytes, k: int) -> int:
+    """kmer_pair bytes -> device slot value (csrc/slot.cuh): (key << 6) | (back << 3) | (fwd + 1)."""
+    pl = (k + 3) // 4
+    key = int.from_bytes(pair[:pl], "big") >> (8 * pl - 2 * k)
+    return (key << 6) | (ext_code(pair[pl]) << 3) | (ext_code(pair[pl + 1]) + 1)
+
+
+def owner_of_slot(slot: int, k: int, world: int) -> int:
+    """Mirror of owner_of<W>() in csrc/sharded.cuh (tests compare it with the GPU's grouping)."""
+    if 2 * k + 6 <= 64:
+        h = _fmix64((slot >> 6) ^ 0x9E3779B97F4A7C15)
+    else:
+        lo, hi = slot & _M64, slot >> 64
+        h = _fmix64(((lo >> 6) + 0xD6E8FEB86659FD93 + _fmix64(hi ^ 0xA0761D6478BD642F)) & _M64)
+    return (h * world) >> 64
+
+
+def slot_bytes(k: int) -> int:
+    return 8 if 2 * k + 6 <= 64 else 16
+
+
+def block_of_rank(n: int, world: int, rank: int) -> tuple[int, int]:
+    """read_kmers.hpp:55-58: rank r parses lines [ceil(n/P)*r, min(n, ceil(n/P)*(r+1)))."""
+    split = (n + world - 1) // world
+    lo = min(n, split * rank)
+    return lo, min(n, lo + split)
+
+
+def shard_capacity(n_total: int, world: int) -> int:
+    """k-mers a shard must be able to hold: its expected share plus 8 sigma of the binomial."""
+    share = n_total / world
+    return int(share + 8.0 * math.sqrt(share + 1.0)) + 1024
+
+
+def exchange_bytes(send, send_counts, elem_bytes, group=None):
+    """All-to-all of variable-size groups of `elem_bytes`-byte elements (torch tensors, any backend).
+
+    send        uint8 tensor: the groups for rank 0, 1, ... back to back
+    send_counts elements per destination
+    returns (recv uint8 tensor, recv_counts list)
+    """
+    import torch
+    import torch.distributed as dist
+
+    world = dist.get_world_size(group)
+    sc = torch.tensor(list(send_counts[:world]), dtype=torch.int64, device=send.device)
+    rc = torch.empty_like(sc)
+    dist.all_to_all_single(rc, sc, group=group)
+    recv_counts = [int(x) for x in rc.tolist()]
+    recv = torch.empty(sum(recv_counts) * elem_bytes, dtype=torch.uint8, device=send.device)
+    dist.all_to_all_single(recv, send[: sum(send_counts[:world]) * elem_bytes],
+                           output_split_sizes=[x * elem_bytes for x in recv_counts],
+                           input_split_sizes=[int(x) * elem_bytes for x in send_counts[:world]], group=group)
+    return recv, recv_counts
+
+
+# ---------------------------------------------------------------------------- shard object ----
+class Shard:
+    """One rank: a kh_table in sharded mode."""
+
+    def __init__(self, k: int, rank: int, world: int, n_local_max: int, n_total: int,
+                 load_factor: float = 0.5, device: int = 0):
+        import cs267_hw3_b200 as kh
+
+        self.kh, self.k, self.rank, self.world = kh, k, rank, world
+        self.tab = kh.KmerHashTable(k, shard_capacity(n_total, world), load_factor, device)
+        L = kh.lib()
+        self._declare(L)
+        self.tab._check(L.kh_shard_init(self.tab._h, rank, world, n_local_max, n_total))
+
+    @staticmethod
+    def _declare(L):
+        if getattr(L, "_shard_declared", False):
+            return
+        vp, u64, i32 = C.c_void_p, C.c_uint64, C.c_int
+        L.kh_shard_init.argtypes = [vp, i32, i32, u64, u64]
+        L.kh_shard_export.argtypes = [vp, vp, C.POINTER(u64)]
+        L.kh_shard_connect.argtypes = [vp, vp, C.POINTER(u64)]
+        L.kh_shard_connect_local.argtypes = [vp, C.POINTER(vp), i32]
+        L.kh_shard_owner_partition.argtypes = [vp, vp, u64, C.POINTER(vp), C.POINTER(u64)]
+        L.kh_insert_slots_device.argtypes = [vp, vp, u64]
+        L.kh_shard_phase.argtypes = [vp, i32, C.POINTER(i32)]
+        L.kh_shard_result.argtypes = [vp, C.POINTER(vp), C.POINTER(vp), C.POINTER(u64), C.POINTER(u64), C.POINTER(u64)]
+        L.kh_slot_bytes.argtypes = [i32]
+        L.kh_slot_bytes.restype = u64
+        L.kh_device_alloc.argtypes = [C.POINTER(vp), u64]
+        L.kh_device_free.argtypes = [vp]
+        L.kh_copy_to_host.argtypes = [vp, vp, vp, u64]
+        L.kh_copy_device.argtypes = [vp, vp, vp, u64]
+        L._shard_declared = True
+
+    # -- K7 --
+    def owner_partition(self, pairs_dev: int, n: int) -> tuple[int, list[int]]:
+        L = self.kh.lib()
+        out = C.c_void_p()
+        counts = (C.c_uint64 * MAX_RANKS)()
+        self.tab._check(L.kh_shard_owner_partition(self.tab._h, pairs_dev, n, C.byref(out), counts))
+        return out.value or 0, [int(x) for x in counts][: self.world]
+
+    def insert_slots(self, slots_dev: int, n: int) -> None:
+        self.tab._check(self.kh.lib().kh_insert_slots_device(self.tab._h, slots_dev, n))
+
+    def phase(self, which: int) -> int:
+        flag = C.c_int()
+        self.tab._check(self.kh.lib().kh_shard_phase(self.tab._h, which, C.byref(flag)))
+        return flag.value
+
+    def result(self):
+        cp, op = C.c_void_p(), C.c_void_p()
+        nc, nb, nn = C.c_uint64(), C.c_uint64(), C.c_uint64()
+        self.tab._check(self.kh.lib().kh_shard_result(self.tab._h, C.byref(cp), C.byref(op), C.byref(nc), C.byref(nb), C.byref(nn)))
+        return cp.value, op.value, nc.value, nb.value, nn.value
+
+    def result_host(self) -> tuple[np.ndarray, int, int]:
+        cp, _, nc, nb, nn = self.result()
+        buf = np.empty(nb, dtype=np.uint8)
+        self.tab._check(self.kh.lib().kh_copy_to_host(self.tab._h, buf.ctypes.data, cp, nb))
+        return buf, nc, nn
+
+    def export(self) -> tuple[bytes, tuple[int, int]]:
+        handles = (C.c_uint8 * (6 * 64))()
+        meta = (C.c_uint64 * 2)()
+        self.tab._check(self.kh.lib().kh_shard_export(self.tab._h, handles, meta))
+        return bytes(handles), (int(meta[0]), int(meta[1]))
+
+    def connect(self, all_handles: list[bytes], all_meta: list[tuple[int, int]]) -> None:
+        blob = b"".join(all_handles)
+        arr = (C.c_uint8 * len(blob)).from_buffer_copy(blob)
+        meta = (C.c_uint64 * (2 * len(all_meta)))(*[x for m in all_meta for x in m])
+        self.tab._check(self.kh.lib().kh_shard_connect(self.tab._h, arr, meta))
+
+    def connect_local(self, shards: list["Shard"]) -> None:
+        arr = (C.c_void_p * len(shards))(*[s.tab._h for s in shards])
+        self.tab._check(self.kh.lib().kh_shard_connect_local(self.tab._h, arr, len(shards)))
+
+    def close(self) -> None:
+        self.tab.close()
+
+
+ERR_BITS = {1: ("KH_ERR_NOT_FOUND", "Error: k-mer not found in Distributed HashMap."), 2: ("KH_ERR_TABLE_FULL", "hash table full"),
+            4: ("KH_ERR_CYCLE", "chain never terminates (cycle)"), 8: ("KH_ERR_BAD_INPUT", "malformed input"),
+            16: ("KH_ERR_CONVERGE", "chains are not linear"), 32: ("KH_ERR_CUDA", "internal segment bookkeeping overflow")}
+
+
+class ShardedError(RuntimeError):
+    def __init__(self, bits: int):
+        names = [v for b, v in ERR_BITS.items() if bits & b]
+        super().__init__("; ".join(f"{n}: {m}" for n, m in names))
+        self.bits = bits
+
+
+# ---------------------------------------------------------------------------- communicators ----
+class LocalComm:
+    """All ranks in this process; shards[i] is rank i."""
+
+    def __init__(self, shards: list[Shard]):
+        self.shards = shards
+        self._recv = [None] * len(shards)
+
+    def connect(self):
+        for s in self.shards:
+            s.connect_local(self.shards)
+
+    def barrier(self):
+        for s in self.shards:
+            s.tab.sync()
+
+    def any(self, flags: list[int]) -> bool:
+        return any(flags)
+
+    def bits_or(self, bits: list[int]) -> int:
+        out = 0
+        for b in bits:
+            out |= b
+        return out
+
+    def exchange(self, sends: list[tuple[int, list[int]]], elem: int) -> list[tuple[int, int]]:
+        """sends[src] = (device ptr of groups in owner order, counts per dest) -> [(recv ptr, n)] per dest."""
+        L = self.shards[0].kh.lib()
+        world = len(self.shards)
+        out = []
+        for d in range(world):
+            n_recv = sum(sends[s][1][d] for s in range(world))
+            if self._recv[d] is None or self._recv[d][1] < n_recv * elem:
+                if self._recv[d] is not None:
+                    L.kh_device_free(self._recv[d][0])
+                p = C.c_void_p()
+                assert L.kh_device_alloc(C.byref(p), max(n_recv * elem, 256) * 5 // 4) == 0
+                self._recv[d] = (p, max(n_recv * elem, 256) * 5 // 4)
+            base = self._recv[d][0].value
+            off = 0
+            for s in range(world):
+                cnt = sends[s][1][d]
+                src = sends[s][0] + sum(sends[s][1][:d]) * elem
+                self.shards[d].tab._check(L.kh_copy_device(self.shards[d].tab._h, base + off, src, cnt * elem))
+                off += cnt * elem
+            out.append((base, n_recv))
+        self.barrier()
+        return out
+
+    def close(self):
+        L = self.shards[0].kh.lib()
+        for r in self._recv:
+            if r is not None:
+                L.kh_device_free(r[0])
+        self._recv = []
+
+
+class _DevView:
+    """Expose a raw device pointer to torch through __cuda_array_interface__."""
+
+    def __init__(self, ptr: int, nbytes: int):
+        self.__cuda_array_interface__ = {"shape": (nbytes,), "typestr": "|u1", "data": (ptr, False), "version": 2}
+
+
+class TorchComm:
+    """One rank per process (torchrun); NCCL on the current CUDA stream."""
+
+    def __init__(self, shard: Shard):
+        import torch
+        import torch.distributed as dist
+
+        self.torch, self.dist = torch, dist
+        self.shards = [shard]
+        self.dev = torch.device("cuda", torch.cuda.current_device())
+        self._keep = None
+
+    def connect(self):
+        s = self.shards[0]
+        h, m = s.export()
+        gathered = [None] * s.world
+        self.dist.all_gather_object(gathered, (h, m))
+        s.connect([g[0] for g in gathered], [g[1] for g in gathered])
+        self.barrier()
+
+    def barrier(self):
+        t = self.torch.zeros(1, device=self.dev)
+        self.dist.all_reduce(t)
+        self.torch.cuda.current_stream().synchronize()
+
+    def any(self, flags: list[int]) -> bool:
+        t = self.torch.tensor([1.0 if any(flags) else 0.0], device=self.dev)
+        self.dist.all_reduce(t, op=self.dist.ReduceOp.MAX)
+        return bool(t.item() > 0)
+
+    def bits_or(self, bits: list[int]) -> int:
+        b = bits[0]
+        t = self.torch.tensor([float((b >> i) & 1) for i in range(8)], device=self.dev)
+        self.dist.all_reduce(t, op=self.dist.ReduceOp.MAX)
+        return sum(1 << i for i, v in enumerate(t.tolist()) if v > 0)
+
+    def exchange(self, sends, elem):
+        ptr, counts = sends[0]
+        n_send = sum(counts)
+        send = self.torch.as_tensor(_DevView(ptr, max(n_send * elem, 1)), device=self.dev) if ptr else \
+            self.torch.empty(0, dtype=self.torch.uint8, device=self.dev)
+        recv, rc = exchange_bytes(send, counts, elem)
+        self._keep = recv                      # alive until the insert kernel has consumed it
+        return [(recv.data_ptr(), sum(rc))]
+
+    def close(self):
+        self._keep = None
+
+
+# ---------------------------------------------------------------------------- the algorithm ----
+def sharded_insert(comm, blocks: list[tuple[int, int]]) -> None:
+    """blocks[i] = (device ptr of this rank's kmer_pair records, count) for comm.shards[i].
+
+    initialize_kmers (kmer_hash.cpp:21-33) across ranks: group by owner, ONE all-to-all, insert."""
+    shards = comm.shards
+    elem = slot_bytes(shards[0].k)
+    sends = [s.owner_partition(ptr, n) for s, (ptr, n) in zip(shards, blocks)]
+    recvs = comm.exchange(sends, elem)
+    for s, (ptr, n) in zip(shards, recvs):
+        s.insert_slots(ptr, n)
+    comm.barrier()                                        # hash_map.hpp:79: every insert is visible before any find
+
+
+def sharded_assemble(comm, max_rounds: int = 40) -> int:
+    """assemble_contigs (kmer_hash.cpp:38-55) across ranks.  Returns the number of pointer-jumping rounds.
+    Raises ShardedError if any rank flagged an error."""
+    shards = comm.shards
+    for s in shards:
+        s.phase(0)                                        # walk: lookups go to the owner's table over NVLink
+    comm.barrier()
+    rounds = 0
+    while rounds < max_rounds:
+        moved = [s.phase(1) for s in shards]
+        rounds += 1
+        comm.barrier()
+        if not comm.any(moved):
+            break
+    for ph in (2, 3, 4, 5):                               # lengths, tail claims, offsets, emit
+        for s in shards:
+            s.phase(ph)
+        comm.barrier()
+    bits = comm.bits_or([s.phase(6) for s in shards])
+    if bits:
+        raise ShardedError(bits)
+    return rounds
+
+
+# ---------------------------------------------------------------------------- bench (N > 1) ----
+def bench(args, k, n_total, c_total, longn, workload, rank, world, local_rank):
+    """Strong scaling of the N=1 workload: the same synthetic file, block-partitioned over the ranks
+    (read_kmers.hpp:55-58), table hash-sharded over the GPUs."""
+    import json
+    import time
+
+    import torch
+    import torch.distributed as dist
+
+    import cs267_hw3_b200 as kh
+    from tools import kmergen
+
+    t_gen = time.time()
+    data = kmergen.Dataset(k, n_total, c_total, seed=267, long_nodes=longn)     # every rank derives the same file
+    lo, hi = block_of_rank(n_total, world, rank)
+    n_local = hi - lo
+    pb = kh.pair_bytes(k)
+    host = kh.PinnedBuffer(max(n_local, 1) * pb)
+    data.pairs_into(host.ptr, lo, n_local)
+    exp_buf, exp_nc = data.expected_array(world, rank)
+    t_gen = time.time() - t_gen
+
+    stream = torch.cuda.current_stream()
+    n_local_max = (n_total + world - 1) // world
+    shard = Shard(k, rank, world, n_local_max, n_total, args.load_factor, device=local_rank)
+    shard.tab.set_stream(stream.cuda_stream)
+    comm = TorchComm(shard)
+    comm.connect()
+    dev = torch.empty(max(n_local, 1) * pb, dtype=torch.uint8, device="cuda")
+    dev.copy_(torch.from_numpy(host.array))
+    torch.cuda.synchronize()
+
+    def step():
+        shard.tab.clear()
+        comm.barrier()
+        e0, e1, e2 = (torch.cuda.Event(enable_timing=True) for _ in range(3))
+        e0.record(stream)
+        sharded_insert(comm, [(dev.data_ptr(), n_local)])
+        e1.record(stream)
+        rounds = sharded_assemble(comm)
+        e2.record(stream)
+        return e0, e1, e2, rounds
+
+    for _ in range(args.warmup):
+        step()
+    dist.barrier()
+    torch.cuda.synchronize()
+    from bench import ClockSampler
+    sampler = ClockSampler(local_rank)
+    sampler.start()
+    evs = []
+    wall0 = time.perf_counter()
+    for _ in range(args.steps):
+        evs.append(step())
+    dist.barrier()
+    torch.cuda.synchronize()
+    wall = time.perf_counter() - wall0
+    clocks = sampler.stop()
+    ms_total = float(np.mean([a.elapsed_time(c) for a, b, c, r in evs]))
+    ms_ins = float(np.mean([a.elapsed_time(b) for a, b, c, r in evs]))
+    t = torch.tensor([ms_total, ms_ins], device="cuda", dtype=torch.float64)
+    dist.all_reduce(t, op=dist.ReduceOp.MAX)                       # slowest rank defines the step
+    ms_total, ms_ins = t.tolist()
+
+    got, nc, nn = shard.result_host()
+    ok = bool(nc == exp_nc and got.size == exp_buf.size and np.array_equal(got, exp_buf))
+    tot = torch.tensor([float(nn), 1.0 if ok else 0.0, float(got.size)], device="cuda", dtype=torch.float64)
+    dist.all_reduce(tot, op=dist.ReduceOp.SUM)
+    nodes_all, ok_all, bytes_all = tot.tolist()
+    verified = bool(int(nodes_all) == n_total and int(ok_all) == world)
+    line = None
+    if rank == 0:
+        from bench import METRIC, UNIT, alg_bytes_per_kmer, measured_peak_gbs
+        peak, peak_src = measured_peak_gbs()
+        alg = alg_bytes_per_kmer(k)
+        path_gbs = n_total * alg["total"] / (ms_total * 1e-3) / 1e9
+        sb = slot_bytes(k)
+        line = {
+            "metric": METRIC, "value": n_total / (ms_total * 1e-3), "unit": UNIT, "n_gpus": world,
+            "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms_total, "higher_is_better": True,
+            "scaling": "strong", "vs_baseline": None, "dtype": "u64" if k <= 29 else "u128", "data": "synthetic",
+            "config": {"workload": workload, "k": k, "n_kmers": n_total, "n_contigs": c_total, "load_factor": args.load_factor,
+                       "seed": 267, "sharding": f"table hash-sharded over {world} GPUs; input lines block-partitioned "
+                       "(read_kmers.hpp:55-58); one NCCL all-to-all of slot values for the inserts; walk lookups read the "
+                       "owner's table over NVLink peer mappings; pointer jumping across GPUs",
+                       "timing": "CUDA events on the launching stream per step, max over ranks, mean of steps",
+                       "l2": "per-GPU table and records larger than L2; table re-zeroed between steps (outside the event pair)"},
+            "stages_ms": {"ms_insert_incl_all_to_all": ms_ins, "ms_traverse": ms_total - ms_ins},
+            "rank_rounds": evs[-1][3], "assembly_time_s": ms_total * 1e-3, "wall_s_timed_loop": wall, "gen_s": t_gen,
+            "verified": verified,
+            "roofline": {"bound": "hbm", "kernel": "walk_sharded_kernel + insert_slots_direct_kernel (whole path)",
+                         "achieved": path_gbs, "peak": peak * world, "unit": "GB/s", "frac": path_gbs / (peak * world),
+                         "traffic": None, "peak_source": peak_src + f" x {world} GPUs", "alg_bytes_per_kmer": alg,
+                         "nvlink_bytes_per_step": int(n_total * (world - 1) / world * (sb + 32)),
+                         "nvlink_note": "(P-1)/P of the slot values cross in the all-to-all and (P-1)/P of the successor "
+                                        "lookups read a 32-byte bucket from a peer"},
+            "e2e": {"value": None, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0,
+                    "note": "host-buffer leg is measured at N=1 only"},
+            "gpu_launches": (12 + evs[-1][3]) * args.steps,
+            "clocks": clocks,
+        }
+    comm.close()
+    shard.close()
+    host.free()
+    dist.barrier()
+    dist.destroy_process_group()
+    return line

@@ -137,6 +137,39 @@ int kh_host_free(void* ptr);
  * random 32-byte sector reads over a `footprint_bytes` buffer; returns sectors per second. */
 int kh_measure_random_sector_rate(int device, uint64_t footprint_bytes, uint64_t n_probes, double* sectors_per_s);
 
+/* ---------------------------------------------------------------------------------------------
+ * Sharded (multi-GPU) path -- replaces the UPC++ side of DistributedHashMap: owner-rank selection
+ * (hash_map.hpp:28-30), batched remote inserts (hash_map.hpp:38-46, 64-77) and remote finds
+ * (hash_map.hpp:93-100).  One handle per GPU / per rank.  The caller moves the per-owner batches
+ * between ranks (NCCL all-to-all through torch.distributed in cs267_hw3_b200/sharded.py) and
+ * separates the phases with barriers; lookups during the walk read the owner's table directly
+ * over NVLink peer mappings (CUDA IPC between processes, or kh_shard_connect_local in one process).
+ * ------------------------------------------------------------------------------------------- */
+uint64_t kh_slot_bytes(int k);            /* bytes of one exchanged slot value: 8 (K<=29) or 16 */
+/* Fix all capacities for this rank: at most n_local_max records parsed here, n_total over all ranks. */
+int kh_shard_init(kh_table* t, int rank, int world, uint64_t n_local_max, uint64_t n_total);
+/* 6 CUDA IPC handles (64 bytes each) + 2 uint64 of metadata for this rank; gather them from all ranks */
+int kh_shard_export(kh_table* t, void* handles_out, uint64_t* meta_out);
+int kh_shard_connect(kh_table* t, const void* all_handles, const uint64_t* all_meta);
+int kh_shard_connect_local(kh_table* t, kh_table* const* peers, int world);
+/* K7: group this rank's records by owning rank (slot values, owner order) and register its start
+ * nodes in input order (kmer_hash.cpp:27-31).  counts_out has 8 entries. */
+int kh_shard_owner_partition(kh_table* t, const void* pairs_dev, uint64_t n, const void** slots_dev_out, uint64_t* counts_out);
+/* K2 on slot values received from the other ranks */
+int kh_insert_slots_device(kh_table* t, const void* slots_dev, uint64_t n);
+/* phases, each followed by a barrier across ranks: 0 walk, 1 one pointer-jumping round (flag_out =
+ * "something moved"; repeat until no rank moved), 2 contig lengths, 3 claim tails, 4 offsets,
+ * 5 emit, 6 collect (flag_out = device error bits) */
+int kh_shard_phase(kh_table* t, int phase, int* flag_out);
+int kh_shard_result(kh_table* t, const char** contigs_dev, const uint64_t** offsets_dev,
+                    uint64_t* n_contigs, uint64_t* contig_bytes, uint64_t* n_nodes);
+
+/* small device-memory helpers for hosts without their own CUDA binding */
+int kh_device_alloc(void** ptr, uint64_t bytes);
+int kh_device_free(void* ptr);
+int kh_copy_to_host(kh_table* t, void* dst_host, const void* src_dev, uint64_t bytes);
+int kh_copy_device(kh_table* t, void* dst_dev, const void* src_dev, uint64_t bytes);
+
 #ifdef __cplusplus
 }
 #endif
