@@ -332,7 +332,7 @@ def main():
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
     ap.add_argument("--workload", default=None, choices=sorted(WORKLOADS))
-    ap.add_argument("--n", type=int, default=0, help="override the number of k-mers (contigs scale along)")
+    ap.add_argument("--kmers", dest="n", type=int, default=0, help="override the number of k-mers (contigs scale along)")
     ap.add_argument("--load-factor", type=float, default=0.5)
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-e2e", action="store_true", help="skip the host-buffer leg (profiling runs)")

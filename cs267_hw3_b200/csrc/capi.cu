@@ -33,6 +33,8 @@ enum { EV_INS0, EV_INS1, EV_AS0, EV_WALK, EV_RANK, EV_AS1, EV_PACK0, EV_PACK1, E
 
 struct kh_table {
     int k = 0, W = 1, device = 0, pl = 0, pb = 0, slot_bytes = 8, per_bucket = 4;
+    int mlen = 0;                     // minimizer length of the in-table placement (0 = plain key hash; KH_LOCALITY=1 turns it on)
+    int olen = 0;                     // minimizer length of the owner-GPU function (0 = plain key hash; KH_OWNER_LOCALITY=0)
     double lf = 0.5;
     u64 n_expected = 0, nbuckets = 0;
     cudaStream_t stream = nullptr, own_stream = nullptr, copy_stream = nullptr;
@@ -182,9 +184,10 @@ int insert_device_impl(kh_table* t, const unsigned char* recs, u64 n, bool recor
         while ((32ull << part_shift) < t->part_bytes) ++part_shift;
         while (((t->nbuckets - 1) >> part_shift) + 1 > (u64)kMaxParts) ++part_shift;
         nparts = (u32)(((t->nbuckets - 1) >> part_shift) + 1);
-        // a partition's expected share of n plus 6 sigma plus slack, rounded to whole insert tiles
+        // a partition's expected share of n plus slack (supermers move as a unit, so the spread is a few times
+        // the binomial sigma), rounded to whole insert tiles; overflow falls back to a direct insert
         const double share = (double)n * (double)std::min<u64>(t->nbuckets, 1ull << part_shift) / (double)t->nbuckets;
-        part_cap = (u64)(share + 6.0 * std::sqrt(share + 1.0) + 64.0);
+        part_cap = (u64)(share + 24.0 * std::sqrt(share + 1.0) + 64.0);
         part_cap = (part_cap + kInsTile - 1) / kInsTile * kInsTile;
         bpp = (u32)(part_cap / kInsTile);
         KH_TRY(ensure(t, t->part_cursor, kMaxParts * sizeof(u32)));
@@ -198,7 +201,7 @@ int insert_device_impl(kh_table* t, const unsigned char* recs, u64 n, bool recor
     if (record_start) KH_CUDA(t, cudaEventRecord(t->ev[EV_INS0], t->stream));
     if (!part) {
         insert_kernel<W><<<(unsigned)ntiles, kInsThreads, (size_t)kInsTile * t->pb, t->stream>>>(
-            recs, n, t->k, static_cast<V*>(t->table), t->nbuckets, static_cast<u32*>(t->mask.p),
+            recs, n, t->k, t->mlen, static_cast<V*>(t->table), t->nbuckets, static_cast<u32*>(t->mask.p),
             static_cast<u32*>(t->tile_counts.p), t->d_ctr);
     } else {
         KH_CUDA(t, cudaMemsetAsync(t->part_cursor.p, 0, kMaxParts * sizeof(u32), t->stream));
@@ -210,18 +213,18 @@ int insert_device_impl(kh_table* t, const unsigned char* recs, u64 n, bool recor
         }
         const u64 pblocks = (n + kPartTile - 1) / kPartTile;
         partition_kernel<W><<<(unsigned)pblocks, kPartThreads, partition_smem(W, nparts, t->pb), t->stream>>>(
-            recs, n, t->k, t->nbuckets, part_shift, nparts, part_cap, static_cast<u32*>(t->part_cursor.p),
+            recs, n, t->k, t->mlen, t->nbuckets, part_shift, nparts, part_cap, static_cast<u32*>(t->part_cursor.p),
             static_cast<V*>(t->grouped.p), static_cast<V*>(t->table), static_cast<u32*>(t->mask.p),
             static_cast<u32*>(t->tile_counts.p), t->d_ctr);
         const unsigned iblocks = nparts * bpp;
         if (t->ins_mode == 0)
             insert_slots_kernel<W, 0><<<iblocks, kInsThreads, 0, t->stream>>>(
                 static_cast<const V*>(t->grouped.p), static_cast<const u32*>(t->part_cursor.p), part_cap, bpp, nparts,
-                part_shift, ahead, static_cast<V*>(t->table), t->nbuckets, t->d_ctr);
+                part_shift, ahead, t->k, t->mlen, static_cast<V*>(t->table), t->nbuckets, t->d_ctr);
         else
             insert_slots_kernel<W, 1><<<iblocks, kInsThreads, 0, t->stream>>>(
                 static_cast<const V*>(t->grouped.p), static_cast<const u32*>(t->part_cursor.p), part_cap, bpp, nparts,
-                part_shift, ahead, static_cast<V*>(t->table), t->nbuckets, t->d_ctr);
+                part_shift, ahead, t->k, t->mlen, static_cast<V*>(t->table), t->nbuckets, t->d_ctr);
     }
     KH_CUDA(t, cudaGetLastError());
     KH_TRY(device_scan(t, static_cast<u32*>(t->tile_counts.p), ntiles, static_cast<u64*>(t->tile_offs.p),
@@ -300,7 +303,7 @@ int assemble_impl(kh_table* t) {
     wp.link = static_cast<u64*>(t->link.p); wp.seglen = static_cast<unsigned char*>(t->seglen.p);
     wp.tmp = static_cast<unsigned char*>(t->tmp.p); wp.ctr = t->d_ctr;
     wp.n_starts = (u32)n_starts; wp.n_split = (u32)n_split; wp.split_shift = t->split_shift;
-    wp.seg_chars = t->seg_chars; wp.seg_cap = (u32)seg_cap; wp.k = t->k;
+    wp.seg_chars = t->seg_chars; wp.seg_cap = (u32)seg_cap; wp.k = t->k; wp.m = t->mlen;
     walk_kernel<W><<<walk_blocks, kWalkThreads, 0, t->stream>>>(wp);
     KH_CUDA(t, cudaGetLastError());
     KH_CUDA(t, cudaEventRecord(t->ev[EV_WALK], t->stream));
@@ -441,7 +444,7 @@ int shard_owner_partition_impl(kh_table* t, const unsigned char* recs, u64 n, co
     KH_CUDA(t, cudaEventRecord(t->ev[EV_INS0], t->stream));
     KH_CUDA(t, cudaMemsetAsync(octr, 0, 3 * kMaxRanks * sizeof(u64), t->stream));
     owner_count_kernel<W><<<(unsigned)ntiles, kInsThreads, (size_t)kInsTile * t->pb, t->stream>>>(
-        recs, n, t->k, world, static_cast<u32*>(t->mask.p), static_cast<u32*>(t->tile_counts.p), octr, t->d_ctr);
+        recs, n, t->k, t->olen, world, static_cast<u32*>(t->mask.p), static_cast<u32*>(t->tile_counts.p), octr, t->d_ctr);
     KH_CUDA(t, cudaGetLastError());
     KH_TRY(device_scan(t, static_cast<u32*>(t->tile_counts.p), ntiles, static_cast<u64*>(t->tile_offs.p), &t->d_ctr->scan_total));
     u64 host_counts[kMaxRanks];
@@ -453,7 +456,7 @@ int shard_owner_partition_impl(kh_table* t, const unsigned char* recs, u64 n, co
     for (int w = 0; w < kMaxRanks; ++w) { base[w] = run; run += host_counts[w]; counts_out[w] = host_counts[w]; }
     KH_CUDA(t, cudaMemcpyAsync(octr + kMaxRanks, base, sizeof(base), cudaMemcpyHostToDevice, t->stream));
     owner_scatter_kernel<W><<<(unsigned)ntiles, kInsThreads, (size_t)kInsTile * t->pb, t->stream>>>(
-        recs, n, t->k, world, octr + kMaxRanks, octr + 2 * kMaxRanks, static_cast<V*>(t->grouped.p));
+        recs, n, t->k, t->olen, world, octr + kMaxRanks, octr + 2 * kMaxRanks, static_cast<V*>(t->grouped.p));
     const u64 fresh = t->h_ctr->scan_total;
     if (t->n_starts + fresh > t->shard_n_local_max) return fail(t, KH_ERR_ARG, "more start nodes than reserved");
     if (fresh) {
@@ -472,7 +475,7 @@ int insert_slots_impl(kh_table* t, const void* slots, u64 n) {
     typedef typename Slot<W>::value_t V;
     if (n == 0) return KH_OK;
     insert_slots_direct_kernel<W><<<(unsigned)((n + kInsTile - 1) / kInsTile), kInsThreads, 0, t->stream>>>(
-        static_cast<const V*>(slots), n, static_cast<V*>(t->table), t->nbuckets, t->d_ctr);
+        static_cast<const V*>(slots), n, t->k, t->mlen, static_cast<V*>(t->table), t->nbuckets, t->d_ctr);
     KH_CUDA(t, cudaGetLastError());
     KH_CUDA(t, cudaEventRecord(t->ev[EV_INS1], t->stream));
     t->have_ins = true;
@@ -496,7 +499,7 @@ int shard_phase_impl(kh_table* t, int phase, int* flag_out) {
         wp.link = static_cast<u64*>(t->link.p); wp.seglen = static_cast<unsigned char*>(t->seglen.p);
         wp.tmp = static_cast<unsigned char*>(t->tmp.p); wp.ctr = t->d_ctr;
         wp.n_starts = n_starts; wp.n_split = n_split; wp.split_shift = t->split_shift;
-        wp.seg_chars = t->seg_chars; wp.seg_cap = (u32)t->shard_seg_cap; wp.k = t->k;
+        wp.seg_chars = t->seg_chars; wp.seg_cap = (u32)t->shard_seg_cap; wp.k = t->k; wp.m = t->mlen; wp.mo = t->olen;
         const u64 walkers = (u64)n_starts + n_split;
         const unsigned blocks = (unsigned)std::max<u64>(1, std::min<u64>(t->shard_walk_blocks, (walkers + kWalkThreads - 1) / kWalkThreads));
         walk_sharded_kernel<W><<<blocks, kWalkThreads, 0, t->stream>>>(wp);
@@ -613,7 +616,8 @@ int kh_create(int k, uint64_t n_expected, double load_factor, int device, kh_tab
     if (gran > 0) { cudaDeviceSetLimit(cudaLimitMaxL2FetchGranularity, (size_t)gran); cudaGetLastError(); }
 
     const long double slots = (long double)std::max<uint64_t>(n_expected, 1) / (long double)load_factor;
-    t->nbuckets = std::max<u64>(8, (u64)(slots / t->per_bucket) + 1);
+    t->nbuckets = std::max<u64>(16, (u64)(slots / t->per_bucket) + 1);
+    t->nbuckets = (t->nbuckets + 15) / 16 * 16;       // whole placement regions (slot.cuh RegionOf)
     t->table_bytes = (size_t)t->nbuckets * 32;
     int rc = KH_OK;
     auto ck = [&](cudaError_t e) { if (e != cudaSuccess && rc == KH_OK) { rc = e == cudaErrorMemoryAllocation ? KH_ERR_NOMEM : KH_ERR_CUDA; t->err = cudaGetErrorString(e); } };
@@ -634,6 +638,8 @@ int kh_create(int k, uint64_t n_expected, double load_factor, int device, kh_tab
     memset(t->h_ctr, 0, sizeof(Counters));
     int v = env_int("KH_SPLIT_BUCKETS", 0);
     if (v > 0 && set_option(t, "split_buckets", v) != KH_OK) fprintf(stderr, "libkh_b200: ignoring KH_SPLIT_BUCKETS=%d\n", v);
+    t->mlen = env_int("KH_LOCALITY", 0) ? minimizer_len(k) : 0;
+    t->olen = env_int("KH_OWNER_LOCALITY", 1) ? minimizer_len(k) : 0;
     t->partition_mode = env_int("KH_PARTITION", -1);
     t->ins_mode = env_int("KH_INS_MODE", 1);
     t->warm_ahead = env_int("KH_WARM_AHEAD", 1);
@@ -692,7 +698,9 @@ int kh_set_stream(kh_table* t, void* cuda_stream) {
     if (!t) return KH_ERR_ARG;
     KH_CUDA(t, cudaSetDevice(t->device));
     KH_CUDA(t, cudaStreamSynchronize(t->stream));
-    t->stream = cuda_stream ? static_cast<cudaStream_t>(cuda_stream) : t->own_stream;
+    // NULL is CUDA's legacy default stream (what torch.cuda.current_stream() is unless changed); it orders
+    // with NCCL work that torch enqueues relative to that stream
+    t->stream = cuda_stream ? static_cast<cudaStream_t>(cuda_stream) : cudaStreamLegacy;
     return KH_OK;
 }
 
@@ -804,10 +812,10 @@ int kh_find_device(kh_table* t, const void* pkmers_dev, uint64_t n, void* pairs_
     KH_CUDA(t, cudaSetDevice(t->device));
     const unsigned blocks = (unsigned)((n + 255) / 256);
     if (t->W == 1)
-        find_kernel<1><<<blocks, 256, 0, t->stream>>>(static_cast<const u64*>(t->table), t->nbuckets, t->k,
+        find_kernel<1><<<blocks, 256, 0, t->stream>>>(static_cast<const u64*>(t->table), t->nbuckets, t->k, t->mlen,
             static_cast<const unsigned char*>(pkmers_dev), n, static_cast<unsigned char*>(pairs_dev_out), found_dev_out);
     else
-        find_kernel<2><<<blocks, 256, 0, t->stream>>>(static_cast<const u128*>(t->table), t->nbuckets, t->k,
+        find_kernel<2><<<blocks, 256, 0, t->stream>>>(static_cast<const u128*>(t->table), t->nbuckets, t->k, t->mlen,
             static_cast<const unsigned char*>(pkmers_dev), n, static_cast<unsigned char*>(pairs_dev_out), found_dev_out);
     KH_CUDA(t, cudaGetLastError());
     return KH_OK;

@@ -130,7 +130,7 @@ __device__ __forceinline__ int insert_one(typename Slot<W>::value_t* table, u64 
 
 template <int W>
 __global__ void __launch_bounds__(kInsThreads)
-insert_kernel(const unsigned char* __restrict__ recs, u64 n, int k,
+insert_kernel(const unsigned char* __restrict__ recs, u64 n, int k, int m,
               typename Slot<W>::value_t* table, u64 nbuckets,
               u32* __restrict__ start_mask, u32* __restrict__ tile_starts, Counters* ctr) {
     typedef Slot<W> S;
@@ -157,12 +157,12 @@ insert_kernel(const unsigned char* __restrict__ recs, u64 n, int k,
         v[r] = S::zero();
         if (live[r]) v[r] = S::from_record(s_rec + j * pb, k, pl, ok);
         if (!ok) { err |= kErrBadInput; live[r] = false; }
-        b[r] = live[r] ? bucket_of(S::hash(v[r]), nbuckets) : 0;
+        b[r] = live[r] ? place_bucket<W>(v[r], k, m, nbuckets) : 0;
         if (live[r]) load256_cg(table + b[r] * S::kPerBucket, q[r]);      // 4 independent sector reads in flight
         // kmer_hash.cpp:27-31: remember which records start a contig, by position in the input
-        const u32 m = __ballot_sync(kFullMask, live[r] && S::back(v[r]) == kExtF);
+        const u32 bal = __ballot_sync(kFullMask, live[r] && S::back(v[r]) == kExtF);
         const u64 word = (rec0 + (u64)r * kInsThreads + (threadIdx.x & ~31u)) >> 5;
-        if (lane_id() == 0 && (word << 5) < n) { start_mask[word] = m; starts += __popc(m); }
+        if (lane_id() == 0 && (word << 5) < n) { start_mask[word] = bal; starts += __popc(bal); }
     }
     u32 inserted = 0, dups = 0;
 #pragma unroll
@@ -243,7 +243,7 @@ constexpr int kPartTile = kPartThreads * kPartPerThread;     // 2048 records per
 // scatter_starts_kernel consumes (tiles of kInsTile records, identical to insert_kernel's).
 template <int W>
 __global__ void __launch_bounds__(kPartThreads)
-partition_kernel(const unsigned char* __restrict__ recs, u64 n, int k, u64 nbuckets, u32 part_shift, u32 nparts,
+partition_kernel(const unsigned char* __restrict__ recs, u64 n, int k, int m, u64 nbuckets, u32 part_shift, u32 nparts,
                  u64 part_cap, u32* __restrict__ cursor, typename Slot<W>::value_t* __restrict__ grouped,
                  typename Slot<W>::value_t* table, u32* __restrict__ start_mask, u32* __restrict__ tile_starts,
                  Counters* ctr) {
@@ -281,15 +281,15 @@ partition_kernel(const unsigned char* __restrict__ recs, u64 n, int k, u64 nbuck
         if (live) v[r] = S::from_record(s_rec + j * pb, k, pl, ok);
         if (!ok) { err |= kErrBadInput; live = false; }
         if (live) {
-            pid[r] = (u32)(bucket_of(S::hash(v[r]), nbuckets) >> part_shift);
+            pid[r] = (u32)(place_bucket<W>(v[r], k, m, nbuckets) >> part_shift);
             rk[r] = atomicAdd(&s_hist[pid[r]], 1u);
         }
         // kmer_hash.cpp:27-31: which records start a contig, by position in the input
-        const u32 m = __ballot_sync(kFullMask, live && S::back(v[r]) == kExtF);
+        const u32 bal = __ballot_sync(kFullMask, live && S::back(v[r]) == kExtF);
         const u64 first = rec0 + (u64)r * kPartThreads + (threadIdx.x & ~31u);
         if (lane_id() == 0 && first < n) {
-            start_mask[first >> 5] = m;
-            if (m) atomicAdd(&s_starts[(r * kPartThreads + threadIdx.x) / kInsTile], (u32)__popc(m));
+            start_mask[first >> 5] = bal;
+            if (bal) atomicAdd(&s_starts[(r * kPartThreads + threadIdx.x) / kInsTile], (u32)__popc(bal));
         }
     }
     err = __reduce_or_sync(kFullMask, err);
@@ -334,7 +334,7 @@ partition_kernel(const unsigned char* __restrict__ recs, u64 n, int k, u64 nbuck
             grouped[(u64)p * part_cap + at] = s_sorted[pos];
         } else {                                           // partition buffer full: insert right here
             const V val = s_sorted[pos];
-            const u64 b = bucket_of(S::hash(val), nbuckets);
+            const u64 b = place_bucket<W>(val, k, m, nbuckets);
             u64 q[4];
             load256_cg(table + b * S::kPerBucket, q);
             const int rc = insert_one<W>(table, nbuckets, b, val, q);
@@ -368,7 +368,7 @@ warm_kernel(const char* __restrict__ base, u64 nlines) {
 template <int W, int MODE>
 __global__ void __launch_bounds__(kInsThreads)
 insert_slots_kernel(const typename Slot<W>::value_t* __restrict__ grouped, const u32* __restrict__ cursor,
-                    u64 part_cap, u32 blocks_per_part, u32 nparts, u32 part_shift, u32 warm_ahead,
+                    u64 part_cap, u32 blocks_per_part, u32 nparts, u32 part_shift, u32 warm_ahead, int k, int m,
                     typename Slot<W>::value_t* table, u64 nbuckets, Counters* ctr) {
     typedef Slot<W> S;
     typedef typename S::value_t V;
@@ -405,7 +405,7 @@ insert_slots_kernel(const typename Slot<W>::value_t* __restrict__ grouped, const
             const u64 i = base + (u64)r * kInsThreads + threadIdx.x;
             live[r] = i < n;
             v[r] = live[r] ? slots[i] : S::zero();
-            b[r] = live[r] ? bucket_of(S::hash(v[r]), nbuckets) : 0;
+            b[r] = live[r] ? place_bucket<W>(v[r], k, m, nbuckets) : 0;
             if (live[r]) load256_cg(table + b[r] * S::kPerBucket, q[r]);
         }
 #pragma unroll
@@ -423,7 +423,7 @@ insert_slots_kernel(const typename Slot<W>::value_t* __restrict__ grouped, const
             const u64 i = base + (u64)r * kInsThreads + threadIdx.x;
             live[r] = i < n;
             v[r] = live[r] ? slots[i] : S::zero();
-            b[r] = live[r] ? bucket_of(S::hash(v[r]), nbuckets) : 0;
+            b[r] = live[r] ? place_bucket<W>(v[r], k, m, nbuckets) : 0;
             old[r] = S::zero();
             if (live[r]) old[r] = S::cas(table + b[r] * S::kPerBucket, S::zero(), v[r]);
         }
@@ -555,11 +555,11 @@ scatter_starts_kernel(const unsigned char* __restrict__ recs, u64 n, int k,
 // K4  lookup
 // =========================================================================================
 template <int W>
-__device__ __forceinline__ bool lookup(const typename Slot<W>::value_t* __restrict__ table, u64 nbuckets,
+__device__ __forceinline__ bool lookup(const typename Slot<W>::value_t* __restrict__ table, u64 nbuckets, int k, int m,
                                        typename Slot<W>::value_t keybits, typename Slot<W>::value_t& found,
                                        u64& bucket, int& slot) {
     typedef Slot<W> S;
-    u64 b = bucket_of(S::hash(keybits), nbuckets);
+    u64 b = place_bucket<W>(keybits, k, m, nbuckets);
     for (u64 tries = 0; tries < nbuckets; ++tries) {
         u64 q[4];
         load256_nc(table + b * S::kPerBucket, q);
@@ -576,7 +576,7 @@ __device__ __forceinline__ bool lookup(const typename Slot<W>::value_t* __restri
 
 template <int W>
 __global__ void __launch_bounds__(256)
-find_kernel(const typename Slot<W>::value_t* __restrict__ table, u64 nbuckets, int k,
+find_kernel(const typename Slot<W>::value_t* __restrict__ table, u64 nbuckets, int k, int m,
             const unsigned char* __restrict__ pkmers, u64 n,
             unsigned char* __restrict__ pairs_out, unsigned char* __restrict__ found_out) {
     typedef Slot<W> S;
@@ -587,7 +587,7 @@ find_kernel(const typename Slot<W>::value_t* __restrict__ table, u64 nbuckets, i
     for (int j = 0; j < pl; ++j) key[j] = pkmers[i * pl + j];
     typename S::value_t hit;
     u64 b; int s;
-    const bool ok = lookup<W>(table, nbuckets, S::from_packed(key, k, pl), hit, b, s);
+    const bool ok = lookup<W>(table, nbuckets, k, m, S::from_packed(key, k, pl), hit, b, s);
     unsigned char rec[18];
     for (int j = 0; j < pb; ++j) rec[j] = 0;
     if (ok) S::to_record(hit, k, pl, rec);
@@ -621,6 +621,7 @@ struct WalkParams {
     u32 seg_chars;        // multiple of 8
     u32 seg_cap;          // capacity of link/seglen/tmp in segments
     int k;
+    int m;                // minimizer length of the placement (0 = plain key hash)
 };
 
 constexpr u32 kWalkBatch = 128;     // walker ids a warp takes per global atomic
@@ -729,7 +730,7 @@ walk_kernel(const WalkParams p) {
                     acc = 0;
                 }
                 V nxt; u64 b; int s;
-                if (!lookup<W>(table, p.nbuckets, S::next_key(cur, p.k), nxt, b, s)) {
+                if (!lookup<W>(table, p.nbuckets, p.k, p.m, S::next_key(cur, p.k), nxt, b, s)) {
                     atomicOr(&p.ctr->errors, kErrNotFound);         // kmer_hash.cpp:47-49
                     close(kLinkTail);
                 } else if (s == 0 && (b & split_mask) == 0) {

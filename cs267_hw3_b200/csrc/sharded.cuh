@@ -39,15 +39,15 @@ struct Peers {
 };
 
 template <int W>
-__device__ __forceinline__ u32 owner_of(typename Slot<W>::value_t v, int world) {
-    return (u32)__umul64hi(Slot<W>::owner_hash(v), (u64)world);
+__device__ __forceinline__ u32 owner_of(typename Slot<W>::value_t v, int world, int k, int m) {
+    return (u32)__umul64hi(owner_hash_of<W>(v, k, m), (u64)world);
 }
 
 // ---- K7: group records by owner ---------------------------------------------------------
 // pass 1: per-owner counts + start bitmask / per-tile start counts (same tiles as insert_kernel)
 template <int W>
 __global__ void __launch_bounds__(kInsThreads)
-owner_count_kernel(const unsigned char* __restrict__ recs, u64 n, int k, int world,
+owner_count_kernel(const unsigned char* __restrict__ recs, u64 n, int k, int mo, int world,
                    u32* __restrict__ start_mask, u32* __restrict__ tile_starts, u64* __restrict__ owner_counts,
                    Counters* ctr) {
     typedef Slot<W> S;
@@ -69,15 +69,15 @@ owner_count_kernel(const unsigned char* __restrict__ recs, u64 n, int k, int wor
         V v = S::zero();
         if (live) v = S::from_record(s_rec + j * pb, k, pl, ok);
         if (!ok) { err |= kErrBadInput; live = false; }
-        const u32 o = live ? owner_of<W>(v, world) : 0u;
+        const u32 o = live ? owner_of<W>(v, world, k, mo) : 0u;
         // warp-aggregate per owner (world <= 8)
         for (int w = 0; w < world; ++w) {
-            const u32 m = __ballot_sync(kFullMask, live && o == (u32)w);
-            if (lane_id() == 0 && m) atomicAdd(&s_cnt[w], (u32)__popc(m));
+            const u32 bo = __ballot_sync(kFullMask, live && o == (u32)w);
+            if (lane_id() == 0 && bo) atomicAdd(&s_cnt[w], (u32)__popc(bo));
         }
-        const u32 m = __ballot_sync(kFullMask, live && S::back(v) == kExtF);
+        const u32 bal = __ballot_sync(kFullMask, live && S::back(v) == kExtF);
         const u64 word = (rec0 + (u64)r * kInsThreads + (threadIdx.x & ~31u)) >> 5;
-        if (lane_id() == 0 && (word << 5) < n) { start_mask[word] = m; starts += __popc(m); }
+        if (lane_id() == 0 && (word << 5) < n) { start_mask[word] = bal; starts += __popc(bal); }
     }
     err = __reduce_or_sync(kFullMask, err);
     if (lane_id() == 0) {
@@ -95,7 +95,7 @@ owner_count_kernel(const unsigned char* __restrict__ recs, u64 n, int k, int wor
 // pass 2: scatter slot values to their owner's group (owner_base = exclusive prefix of the counts)
 template <int W>
 __global__ void __launch_bounds__(kInsThreads)
-owner_scatter_kernel(const unsigned char* __restrict__ recs, u64 n, int k, int world,
+owner_scatter_kernel(const unsigned char* __restrict__ recs, u64 n, int k, int mo, int world,
                      const u64* __restrict__ owner_base, u64* __restrict__ owner_cursor,
                      typename Slot<W>::value_t* __restrict__ grouped) {
     typedef Slot<W> S;
@@ -119,7 +119,7 @@ owner_scatter_kernel(const unsigned char* __restrict__ recs, u64 n, int k, int w
         if (j < cnt) {
             v[r] = S::from_record(s_rec + j * pb, k, pl, ok);
             if (ok) {
-                own[r] = owner_of<W>(v[r], world);
+                own[r] = owner_of<W>(v[r], world, k, mo);
                 rk[r] = atomicAdd(&s_cnt[own[r]], 1u);
             }
         }
@@ -137,7 +137,7 @@ owner_scatter_kernel(const unsigned char* __restrict__ recs, u64 n, int k, int w
 // ---- K2 on received slot values ------------------------------------------------------------
 template <int W>
 __global__ void __launch_bounds__(kInsThreads)
-insert_slots_direct_kernel(const typename Slot<W>::value_t* __restrict__ slots, u64 n,
+insert_slots_direct_kernel(const typename Slot<W>::value_t* __restrict__ slots, u64 n, int k, int m,
                            typename Slot<W>::value_t* table, u64 nbuckets, Counters* ctr) {
     typedef Slot<W> S;
     typedef typename S::value_t V;
@@ -155,7 +155,7 @@ insert_slots_direct_kernel(const typename Slot<W>::value_t* __restrict__ slots, 
         live[r] = i < n;
         v[r] = live[r] ? slots[i] : S::zero();
         live[r] = live[r] && !S::empty(v[r]);
-        b[r] = live[r] ? bucket_of(S::hash(v[r]), nbuckets) : 0;
+        b[r] = live[r] ? place_bucket<W>(v[r], k, m, nbuckets) : 0;
         if (live[r]) load256_cg(table + b[r] * S::kPerBucket, q[r]);
     }
     u32 inserted = 0, dups = 0, err = 0;
@@ -193,20 +193,23 @@ struct ShardWalkParams {
     Counters* ctr;
     u32 n_starts, n_split;     // local
     u32 split_shift, seg_chars, seg_cap;
-    int k;
+    int k, m, mo;          // m: minimizer length of the in-shard placement (0 = key hash); mo: of the owner function
 };
 
 template <int W>
-__device__ __forceinline__ bool lookup_sharded(const Peers& pe, typename Slot<W>::value_t keybits,
+__device__ __forceinline__ bool lookup_sharded(const Peers& pe, int k, int m, int mo, typename Slot<W>::value_t keybits,
                                                typename Slot<W>::value_t& found, u32& owner, u64& bucket, int& slot) {
     typedef Slot<W> S;
-    owner = owner_of<W>(keybits, pe.world);
+    // the owner is a hash of the minimizer: the successor of a k-mer usually shares it, so most steps stay on-GPU
+    const u64 oh = mo ? fmix64(minimizer_value<W>(keybits, k, mo) + 0x632BE59BD9B4E019ull) : S::owner_hash(keybits);
+    owner = (u32)__umul64hi(oh, (u64)pe.world);
     const typename S::value_t* __restrict__ table = static_cast<const typename S::value_t*>(pe.table[owner]);
     const u64 nb = pe.nbuckets[owner];
-    u64 b = bucket_of(S::hash(keybits), nb);
+    u64 b = (m == 0) ? bucket_of(S::hash(keybits), nb)
+                     : place_bucket_from<W>(m == mo ? oh : fmix64(minimizer_value<W>(keybits, k, m) + 0x632BE59BD9B4E019ull), keybits, nb);
     for (u64 tries = 0; tries < nb; ++tries) {
         u64 q[4];
-        load256_nc(table + b * S::kPerBucket, q);          // local HBM or a peer's HBM over NVLink
+        load256_ro(table + b * S::kPerBucket, q);          // local HBM or a peer's HBM over NVLink
 #pragma unroll
         for (int i = 0; i < S::kPerBucket; ++i) {
             const typename S::value_t cur = S::from_bucket(q, i);
@@ -314,7 +317,7 @@ walk_sharded_kernel(const ShardWalkParams p) {
                     acc = 0;
                 }
                 V nxt; u64 b; int s; u32 owner;
-                if (!lookup_sharded<W>(p.peers, S::next_key(cur, p.k), nxt, owner, b, s)) {
+                if (!lookup_sharded<W>(p.peers, p.k, p.m, p.mo, S::next_key(cur, p.k), nxt, owner, b, s)) {
                     atomicOr(&p.ctr->errors, kErrNotFound);
                     close(kLinkTail);
                 } else if (s == 0 && (b & split_mask) == 0) {

@@ -69,6 +69,10 @@ __device__ __forceinline__ void load256_nc(const void* p, u64 (&q)[4]) {   // re
     asm volatile("ld.global.nc.L1::no_allocate.v4.u64 {%0,%1,%2,%3}, [%4];"
                  : "=l"(q[0]), "=l"(q[1]), "=l"(q[2]), "=l"(q[3]) : "l"(p));
 }
+__device__ __forceinline__ void load256_ro(const void* p, u64 (&q)[4]) {   // read-only table, keep the line in L1/L2
+    asm volatile("ld.global.nc.v4.u64 {%0,%1,%2,%3}, [%4];"
+                 : "=l"(q[0]), "=l"(q[1]), "=l"(q[2]), "=l"(q[3]) : "l"(p));
+}
 __device__ __forceinline__ void load256_cg(const void* p, u64 (&q)[4]) {   // coherent at L2 (table being built)
     asm volatile("ld.global.cg.v4.u64 {%0,%1,%2,%3}, [%4];"
                  : "=l"(q[0]), "=l"(q[1]), "=l"(q[2]), "=l"(q[3]) : "l"(p) : "memory");
@@ -220,6 +224,50 @@ template <> struct Slot<2> {
     }
 };
 
+
+// ---- placement: where a k-mer lives -------------------------------------------------------------
+// With a plain key hash, the successor of a k-mer (its last K-1 bases + one new base) lands in an
+// unrelated bucket, so every step of a contig walk is a random DRAM access (and, sharded, usually a
+// remote one).  Hashing the k-mer's MINIMIZER instead -- the m-mer with the smallest order value
+// among its K-m+1 m-mers, leftmost on ties -- gives consecutive k-mers of a contig the same home for
+// as long as they share the minimizer (a "supermer": (K-m+2)/2 k-mers on average on random
+// sequence), so they fill adjacent slots of one bucket run on one GPU.  Nothing else about the table
+// changes: the home is still a pure function of the key, probing is linear from the home bucket.
+// m = 0 selects the plain key hash.
+__host__ __device__ __forceinline__ int minimizer_len(int k) {
+    return k <= 14 ? k : (k <= 18 ? 11 : (k <= 29 ? 13 : (k <= 40 ? 21 : 31)));
+}
+__host__ __device__ __forceinline__ u32 mmer_order(u64 x) {      // order value of an m-mer (<= 42 bits)
+    return (u32)((x * 0x9E3779B97F4A7C15ull) >> 32);
+}
+template <int W> __host__ __device__ __forceinline__ u64 minimizer_value(typename Slot<W>::value_t v, int k, int m);
+template <> __host__ __device__ __forceinline__ u64 minimizer_value<1>(u64 v, int k, int m) {
+    const u64 key = v >> 6, mask = (m >= 32) ? ~0ull : ((1ull << (2 * m)) - 1ull);
+    u32 best = 0xFFFFFFFFu;
+    u64 bx = 0;
+    for (int s = 2 * (k - m); s >= 0; s -= 2) {                  // leftmost m-mer first
+        const u64 x = (key >> s) & mask;
+        const u32 g = mmer_order(x);
+        if (g < best) { best = g; bx = x; }
+    }
+    return bx;
+}
+template <> __host__ __device__ __forceinline__ u64 minimizer_value<2>(u128 v, int k, int m) {
+    const u64 lo = (v.lo >> 6) | (v.hi << 58), hi = v.hi >> 6, mask = (m >= 32) ? ~0ull : ((1ull << (2 * m)) - 1ull);
+    u32 best = 0xFFFFFFFFu;
+    u64 bx = 0;
+    for (int s = 2 * (k - m); s >= 0; s -= 2) {
+        const u64 x = (s >= 64 ? (hi >> (s - 64)) : (s == 0 ? lo : ((lo >> s) | (hi << (64 - s))))) & mask;
+        const u32 g = mmer_order(x);
+        if (g < best) { best = g; bx = x; }
+    }
+    return bx;
+}
+// hash that selects the owning GPU, and hash that selects the home bucket (independent of each other)
+template <int W> __host__ __device__ __forceinline__ u64 owner_hash_of(typename Slot<W>::value_t v, int k, int m) {
+    return m ? fmix64(minimizer_value<W>(v, k, m) + 0x632BE59BD9B4E019ull) : Slot<W>::owner_hash(v);
+}
+
 // hash -> bucket without requiring a power-of-two table (load-factor sweeps need exact sizes)
 __host__ __device__ __forceinline__ u64 bucket_of(u64 h, u64 nbuckets) {
 #ifdef __CUDA_ARCH__
@@ -227,6 +275,24 @@ __host__ __device__ __forceinline__ u64 bucket_of(u64 h, u64 nbuckets) {
 #else
     return (u64)(((unsigned __int128)h * nbuckets) >> 64);
 #endif
+}
+
+// Home bucket of a k-mer.  With locality (m != 0) the REGION -- kRegionBuckets consecutive buckets: one
+// 128-byte line of 16 slots for 64-bit slots, four lines of 32 slots for 128-bit slots -- is chosen by
+// the minimizer, and the bucket inside the region by the key itself: the members of a supermer spread
+// over the region instead of queueing behind one home bucket (probe chains stay ~1 bucket), yet they
+// share cache lines and DRAM rows.  Regions that overflow spill into the following buckets as usual.
+template <int W> struct RegionOf { static constexpr u64 kBuckets = (W == 1) ? 4 : 16; };
+template <int W>
+__host__ __device__ __forceinline__ u64 place_bucket_from(u64 minimizer_hash, typename Slot<W>::value_t v, u64 nbuckets) {
+    constexpr u64 G = RegionOf<W>::kBuckets;
+    const u64 region = bucket_of(fmix64(minimizer_hash ^ 0x9E3779B97F4A7C15ull), nbuckets / G);   // nbuckets % G == 0
+    return region * G + (Slot<W>::hash(v) & (G - 1));
+}
+template <int W>
+__host__ __device__ __forceinline__ u64 place_bucket(typename Slot<W>::value_t v, int k, int m, u64 nbuckets) {
+    if (m == 0) return bucket_of(Slot<W>::hash(v), nbuckets);
+    return place_bucket_from<W>(fmix64(minimizer_value<W>(v, k, m) + 0x632BE59BD9B4E019ull), v, nbuckets);
 }
 
 // Error bits accumulated on the device (Counters::errors)

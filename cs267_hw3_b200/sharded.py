@@ -50,9 +50,30 @@ def slot_from_pair(pair: bytes, k: int) -> int:
     return (key << 6) | (ext_code(pair[pl]) << 3) | (ext_code(pair[pl + 1]) + 1)
 
 
-def owner_of_slot(slot: int, k: int, world: int) -> int:
-    """Mirror of owner_of<W>() in csrc/sharded.cuh (tests compare it with the GPU's grouping)."""
-    if 2 * k + 6 <= 64:
+def minimizer_len(k: int) -> int:
+    return k if k <= 14 else (11 if k <= 18 else (13 if k <= 29 else (21 if k <= 40 else 31)))
+
+
+def minimizer_value(slot: int, k: int, m: int) -> int:
+    """The m-mer of the k-mer with the smallest order value, leftmost on ties (csrc/slot.cuh)."""
+    key, mask = slot >> 6, (1 << (2 * m)) - 1
+    best, bx = 1 << 32, 0
+    for s in range(2 * (k - m), -1, -2):
+        x = (key >> s) & mask
+        g = ((x * 0x9E3779B97F4A7C15) & _M64) >> 32
+        if g < best:
+            best, bx = g, x
+    return bx
+
+
+def owner_of_slot(slot: int, k: int, world: int, locality: bool = True) -> int:
+    """Mirror of owner_of<W>() in csrc/sharded.cuh (tests compare it with the GPU's grouping).
+
+    locality=True: the owner is a hash of the k-mer's minimizer, so the successor of a k-mer usually has the
+    same owner; False: plain hash of the key (KH_LOCALITY=0)."""
+    if locality:
+        h = _fmix64((minimizer_value(slot, k, minimizer_len(k)) + 0x632BE59BD9B4E019) & _M64)
+    elif 2 * k + 6 <= 64:
         h = _fmix64((slot >> 6) ^ 0x9E3779B97F4A7C15)
     else:
         lo, hi = slot & _M64, slot >> 64
@@ -72,9 +93,10 @@ def block_of_rank(n: int, world: int, rank: int) -> tuple[int, int]:
 
 
 def shard_capacity(n_total: int, world: int) -> int:
-    """k-mers a shard must be able to hold: its expected share plus 8 sigma of the binomial."""
+    """k-mers a shard must be able to hold: its expected share plus slack.  With minimizer-keyed ownership whole
+    supermers (runs of ~4-16 k-mers) move together, so the spread is a few times the binomial one."""
     share = n_total / world
-    return int(share + 8.0 * math.sqrt(share + 1.0)) + 1024
+    return int(share * 1.005 + 40.0 * math.sqrt(share + 1.0)) + 1024
 
 
 def exchange_bytes(send, send_counts, elem_bytes, group=None):

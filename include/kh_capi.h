@@ -86,7 +86,8 @@ int kh_create(int k, uint64_t n_expected, double load_factor, int device, kh_tab
 int kh_destroy(kh_table* t);
 /* Empty the table and forget the start nodes (a fresh DistributedHashMap). Stream-ordered. */
 int kh_clear(kh_table* t);
-/* Run on an existing CUDA stream (cudaStream_t) instead of the handle's own. */
+/* Run on an existing CUDA stream (cudaStream_t) instead of the handle's own; NULL = the legacy
+ * default stream.  Work the caller orders against this handle (NCCL, copies) must use the same stream. */
 int kh_set_stream(kh_table* t, void* cuda_stream);
 int kh_sync(kh_table* t);
 /* Tuning knobs (also read from the environment at create: KH_SPLIT_BUCKETS, KH_SEG_CHARS):

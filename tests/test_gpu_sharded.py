@@ -70,7 +70,7 @@ def test_sharded_matches_per_rank_reference_output(k, world):
     # the shards really are shards: nobody holds everything (world > 1) and the split is even
     if world > 1:
         share = 60000 / world
-        assert all(abs(x["n_inserted"] - share) < 6 * share ** 0.5 + 10 for x in st)
+        assert all(abs(x["n_inserted"] - share) < 30 * share ** 0.5 + 10 for x in st)   # supermers move as a unit
 
 
 def test_sharded_long_contig_and_dense_splitters():

@@ -54,7 +54,7 @@ def test_exchange_plan_world2_gloo(tmp_path, k):
     res = [torch.load(out + f".{r}") for r in range(world)]
     assert all(r["ok"] for r in res)
     assert sum(r["n_recv"] for r in res) == n                          # a partition of the k-mers
-    assert all(abs(r["n_recv"] - n / world) < 6 * (n / world) ** 0.5 for r in res)
+    assert all(abs(r["n_recv"] - n / world) < 30 * (n / world) ** 0.5 for r in res)   # supermers move as a unit
     # start nodes stay with the rank that parsed them (kmer_hash.cpp:27-31)
     assert [r["n_starts"] for r in res] == [r["expected_contigs"] for r in res]
     assert sum(r["n_starts"] for r in res) == c
