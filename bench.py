@@ -195,6 +195,7 @@ def run_b200_arm(args, k: int, workload: str) -> dict | None:
         raise RuntimeError("bench.py: no CUDA device; the B200 arm has no CPU fallback")
     torch.cuda.set_device(local_rank)
     if world > 1:
+        os.environ["NCCL_DEBUG"] = "WARN"      # the VERSION banner would land on stdout next to the JSON line
         dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
     if world != args.gpus:
         raise RuntimeError(f"--gpus {args.gpus} but WORLD_SIZE={world}: launch with torch.distributed.run")

@@ -72,6 +72,10 @@ struct kh_table {
     DevBuf owner_ctr;                 // u64[3*kMaxRanks]: counts | base | cursor
     DevBuf changed_flag;              // u32
     unsigned shard_walk_blocks = 0;
+    int shard_migrate = 1;            // KH_SHARD_WALK=peer selects the peer-lookup walk instead of the migrating walk
+    MigLayout lay = {};
+    DevBuf seg_of_slot, boundary_list, outbox, outbox_grouped;
+    u64 shard_n_starts_max = 0;
 };
 
 namespace {
@@ -389,34 +393,64 @@ int shard_require(kh_table* t) {
     return KH_OK;
 }
 
+template <int W> int shard_phase_impl(kh_table* t, int phase, int* flag_out);
+
 template <int W>
-int shard_init_impl(kh_table* t, int rank, int world, u64 n_local_max, u64 n_total) {
+int shard_init_impl(kh_table* t, int rank, int world, u64 n_local_max, u64 n_total, u64 n_starts_max) {
     typedef typename Slot<W>::value_t V;
     if (world < 1 || world > kMaxRanks || rank < 0 || rank >= world) return fail(t, KH_ERR_ARG, "1 <= world <= 8 and 0 <= rank < world");
-    t->shard_n_local_max = n_local_max; t->shard_n_total = n_total;
+    n_starts_max = std::min<u64>(std::max<u64>(n_starts_max, 1), n_local_max + 1);
+    t->shard_n_local_max = n_local_max; t->shard_n_total = n_total; t->shard_n_starts_max = n_starts_max;
+    t->shard_migrate = 1;
+    if (const char* e = getenv("KH_SHARD_WALK")) t->shard_migrate = (std::string(e) == "peer") ? 0 : 1;
     t->shard_n_split = (u32)(((t->nbuckets - 1) >> t->split_shift) + 1);
-    int bps = 0;
+    int bps = 0, bps2 = 0;
     KH_CUDA(t, cudaOccupancyMaxActiveBlocksPerMultiprocessor(&bps, walk_sharded_kernel<W>, kWalkThreads, 0));
-    if (bps < 1) return fail(t, KH_ERR_CUDA, "walk_sharded_kernel does not fit on an SM");
+    KH_CUDA(t, cudaOccupancyMaxActiveBlocksPerMultiprocessor(&bps2, walk_mig_kernel<W>, kWalkThreads, 0));
+    bps = std::min(bps, bps2);
+    if (bps < 1) return fail(t, KH_ERR_CUDA, "walk kernel does not fit on an SM");
     t->shard_walk_blocks = (unsigned)(t->sm_count * bps);
     const u64 nwarps = (u64)t->shard_walk_blocks * (kWalkThreads / 32);
-    const u64 seg_cap = (u64)t->shard_n_split + n_local_max + 2 * (n_total / t->seg_chars + 1) + (u64)kSegBatch * nwarps + 64;
-    if (seg_cap >= (u64)kLocalMask - 16) return fail(t, KH_ERR_ARG, "too many walk segments per GPU for 28-bit local ids");
+    const u64 n_exp = std::max<u64>(t->n_expected, 1);          // k-mers this shard is sized for
+    u64 seg_cap = 0, tmp_rows = 0;
+    if (t->shard_migrate) {
+        // boundary starts: nodes whose predecessor lives elsewhere -- a fraction ~2/(w+1) * (P-1)/P of the shard
+        // with a minimizer window of w m-mers (everything when the owner is a plain key hash) -- plus the start
+        // nodes (backward ext 'F') that hash here.  Twice the expectation, capped by the shard itself.
+        const int w = t->olen ? t->k - t->olen + 1 : 1;
+        const double frac = world == 1 ? 0.0 : (w <= 1 ? 1.0 : std::min(1.0, 4.0 / (w + 1)));
+        const u64 bcap = std::min<u64>(n_exp, (u64)(frac * (double)n_exp)) + 2 * n_starts_max + 1024;
+        const u64 ocap = 2 * (n_exp / t->seg_chars + 1) + (u64)kSegBatch * nwarps + 64;
+        const u64 walk_cap = (u64)t->shard_n_split + bcap + ocap;
+        seg_cap = walk_cap + n_starts_max;
+        if (seg_cap >= (u64)kLocalMask - 16) return fail(t, KH_ERR_ARG, "too many walk segments per GPU for 28-bit local ids");
+        t->lay.n_split = t->shard_n_split; t->lay.bcap = (u32)bcap; t->lay.walk_cap = (u32)walk_cap;
+        t->lay.hcap = (u32)n_starts_max; t->lay.outbox_cap = (u32)seg_cap;
+        tmp_rows = walk_cap;
+        KH_TRY(ensure(t, t->seg_of_slot, t->nbuckets * t->per_bucket * sizeof(u32)));
+        KH_TRY(ensure(t, t->boundary_list, (bcap + 1) * sizeof(V)));
+        KH_TRY(ensure(t, t->outbox, (seg_cap + 1) * sizeof(OutEntry<W>)));
+        KH_TRY(ensure(t, t->outbox_grouped, (seg_cap + 1) * sizeof(OutEntry<W>)));
+    } else {
+        seg_cap = (u64)t->shard_n_split + n_starts_max + 2 * (n_total / t->seg_chars + 1) + (u64)kSegBatch * nwarps + 64;
+        if (seg_cap >= (u64)kLocalMask - 16) return fail(t, KH_ERR_ARG, "too many walk segments per GPU for 28-bit local ids");
+        tmp_rows = seg_cap;
+    }
     t->shard_seg_cap = seg_cap;
-    t->shard_out_cap = n_total + n_local_max * (u64)(t->k + 1) + 64;
+    t->shard_out_cap = n_total + n_starts_max * (u64)(t->k + 1) + 64;
     const u64 ntiles = (n_local_max + kInsTile - 1) / kInsTile + 1;
     KH_TRY(ensure(t, t->link, seg_cap * sizeof(u64)));
     KH_TRY(ensure(t, t->seglen, seg_cap));
-    KH_TRY(ensure(t, t->tmp, seg_cap * (u64)t->seg_chars + 16));
-    KH_TRY(ensure(t, t->contig_len, (n_local_max + 1) * sizeof(u32)));
-    KH_TRY(ensure(t, t->contig_pre, (n_local_max + 1) * sizeof(u32)));
-    KH_TRY(ensure(t, t->contig_off, (n_local_max + 1) * sizeof(u64)));
+    KH_TRY(ensure(t, t->tmp, tmp_rows * (u64)t->seg_chars + 16));
+    KH_TRY(ensure(t, t->contig_len, (n_starts_max + 1) * sizeof(u32)));
+    KH_TRY(ensure(t, t->contig_pre, (n_starts_max + 1) * sizeof(u32)));
+    KH_TRY(ensure(t, t->contig_off, (n_starts_max + 1) * sizeof(u64)));
     KH_TRY(ensure(t, t->out, t->shard_out_cap));
-    KH_TRY(ensure(t, t->starts, (n_local_max + 1) * sizeof(V)));
+    KH_TRY(ensure(t, t->starts, (n_starts_max + 1) * sizeof(V)));
     KH_TRY(ensure(t, t->mask, ntiles * (kInsTile / 32) * sizeof(u32)));
     KH_TRY(ensure(t, t->tile_counts, ntiles * sizeof(u32)));
     KH_TRY(ensure(t, t->tile_offs, ntiles * sizeof(u64)));
-    KH_TRY(ensure(t, t->scan_blocks, ((std::max(ntiles, n_local_max + 1) + kScanTile - 1) / kScanTile + 2) * sizeof(u64)));
+    KH_TRY(ensure(t, t->scan_blocks, ((std::max(ntiles, n_starts_max + 1) + kScanTile - 1) / kScanTile + 2) * sizeof(u64)));
     KH_TRY(ensure(t, t->grouped, (n_local_max + 1) * sizeof(V)));
     KH_TRY(ensure(t, t->owner_ctr, 3 * kMaxRanks * sizeof(u64)));
     KH_TRY(ensure(t, t->changed_flag, 16));
@@ -458,7 +492,7 @@ int shard_owner_partition_impl(kh_table* t, const unsigned char* recs, u64 n, co
     owner_scatter_kernel<W><<<(unsigned)ntiles, kInsThreads, (size_t)kInsTile * t->pb, t->stream>>>(
         recs, n, t->k, t->olen, world, octr + kMaxRanks, octr + 2 * kMaxRanks, static_cast<V*>(t->grouped.p));
     const u64 fresh = t->h_ctr->scan_total;
-    if (t->n_starts + fresh > t->shard_n_local_max) return fail(t, KH_ERR_ARG, "more start nodes than reserved");
+    if (t->n_starts + fresh > t->shard_n_starts_max) return fail(t, KH_ERR_ARG, "more start nodes than kh_shard_init reserved (n_starts_max)");
     if (fresh) {
         scatter_starts_kernel<W><<<(unsigned)((ntiles * 32 + 255) / 256), 256, 0, t->stream>>>(
             recs, n, t->k, static_cast<u32*>(t->mask.p), static_cast<u64*>(t->tile_offs.p), ntiles,
@@ -474,11 +508,74 @@ template <int W>
 int insert_slots_impl(kh_table* t, const void* slots, u64 n) {
     typedef typename Slot<W>::value_t V;
     if (n == 0) return KH_OK;
-    insert_slots_direct_kernel<W><<<(unsigned)((n + kInsTile - 1) / kInsTile), kInsThreads, 0, t->stream>>>(
-        static_cast<const V*>(slots), n, t->k, t->mlen, static_cast<V*>(t->table), t->nbuckets, t->d_ctr);
+    const unsigned blocks = (unsigned)((n + kInsTile - 1) / kInsTile);
+    if (t->shard_on && t->shard_migrate)
+        insert_slots_shard_kernel<W><<<blocks, kInsThreads, 0, t->stream>>>(
+            static_cast<const V*>(slots), n, t->k, t->mlen, t->olen, t->peers.rank, t->peers.world, static_cast<V*>(t->table),
+            t->nbuckets, static_cast<u32*>(t->seg_of_slot.p), static_cast<V*>(t->boundary_list.p), t->lay.bcap, t->d_ctr);
+    else
+        insert_slots_direct_kernel<W><<<blocks, kInsThreads, 0, t->stream>>>(
+            static_cast<const V*>(slots), n, t->k, t->mlen, static_cast<V*>(t->table), t->nbuckets, t->d_ctr);
     KH_CUDA(t, cudaGetLastError());
     KH_CUDA(t, cudaEventRecord(t->ev[EV_INS1], t->stream));
     t->have_ins = true;
+    return KH_OK;
+}
+
+// walk phase: returns the pending cross-GPU links grouped by destination (migrating mode)
+template <int W>
+int shard_walk_impl(kh_table* t, const void** entries_out, u64* counts_out) {
+    typedef typename Slot<W>::value_t V;
+    for (int w = 0; w < kMaxRanks; ++w) counts_out[w] = 0;
+    *entries_out = t->outbox_grouped.p;
+    const u32 n_starts = (u32)t->n_starts;
+    KH_CUDA(t, cudaEventRecord(t->ev[EV_AS0], t->stream));
+    KH_CUDA(t, cudaMemsetAsync(static_cast<u32*>(t->contig_len.p) + n_starts, 0, sizeof(u32), t->stream));
+    t->stats.rank_rounds = 0;
+    if (!t->shard_migrate) {
+        int dummy;
+        return shard_phase_impl<W>(t, 0, &dummy);
+    }
+    const MigLayout lay = t->lay;
+    init_mig_kernel<<<1, 1, 0, t->stream>>>(t->d_ctr, lay.n_split + lay.bcap);
+    if (n_starts)
+        head_stub_kernel<W><<<(n_starts + 255) / 256, 256, 0, t->stream>>>(
+            static_cast<const V*>(t->starts.p), n_starts, t->k, t->olen, t->peers.rank, t->peers.world, lay,
+            static_cast<u64*>(t->link.p), static_cast<unsigned char*>(t->seglen.p), static_cast<OutEntry<W>*>(t->outbox.p), t->d_ctr);
+    MigWalkParams wp;
+    wp.table = t->table; wp.nbuckets = t->nbuckets; wp.boundary_list = t->boundary_list.p;
+    wp.link = static_cast<u64*>(t->link.p); wp.seglen = static_cast<unsigned char*>(t->seglen.p);
+    wp.tmp = static_cast<unsigned char*>(t->tmp.p); wp.outbox = t->outbox.p; wp.ctr = t->d_ctr; wp.lay = lay;
+    wp.split_shift = t->split_shift; wp.seg_chars = t->seg_chars; wp.k = t->k; wp.m = t->mlen; wp.mo = t->olen;
+    wp.rank = t->peers.rank; wp.world = t->peers.world;
+    walk_mig_kernel<W><<<t->shard_walk_blocks, kWalkThreads, 0, t->stream>>>(wp);
+    KH_CUDA(t, cudaGetLastError());
+    KH_CUDA(t, cudaEventRecord(t->ev[EV_WALK], t->stream));
+    u64* octr = static_cast<u64*>(t->owner_ctr.p);
+    KH_CUDA(t, cudaMemsetAsync(octr, 0, 3 * kMaxRanks * sizeof(u64), t->stream));
+    const unsigned gb = (unsigned)t->sm_count * 4;
+    outbox_count_kernel<W><<<gb, 256, 0, t->stream>>>(static_cast<const OutEntry<W>*>(t->outbox.p), t->d_ctr, lay.outbox_cap, octr);
+    u64 host_counts[kMaxRanks];
+    KH_CUDA(t, cudaMemcpyAsync(host_counts, octr, sizeof(host_counts), cudaMemcpyDeviceToHost, t->stream));
+    KH_CUDA(t, cudaStreamSynchronize(t->stream));
+    u64 base[kMaxRanks], run = 0;
+    for (int w = 0; w < kMaxRanks; ++w) { base[w] = run; run += host_counts[w]; counts_out[w] = host_counts[w]; }
+    KH_CUDA(t, cudaMemcpyAsync(octr + kMaxRanks, base, sizeof(base), cudaMemcpyHostToDevice, t->stream));
+    outbox_scatter_kernel<W><<<gb, 256, 0, t->stream>>>(static_cast<const OutEntry<W>*>(t->outbox.p), t->d_ctr, lay.outbox_cap,
+                                                       octr + kMaxRanks, octr + 2 * kMaxRanks, static_cast<OutEntry<W>*>(t->outbox_grouped.p));
+    KH_CUDA(t, cudaGetLastError());
+    KH_CUDA(t, cudaStreamSynchronize(t->stream));    // base[] is on this frame
+    return KH_OK;
+}
+
+template <int W>
+int shard_resolve_impl(kh_table* t, const void* inbox, u64 n) {
+    typedef typename Slot<W>::value_t V;
+    if (!t->shard_migrate || n == 0) return KH_OK;
+    resolve_links_kernel<W><<<(unsigned)((n + 255) / 256), 256, 0, t->stream>>>(
+        t->peers, static_cast<const OutEntry<W>*>(inbox), n, static_cast<const V*>(t->table), t->nbuckets, t->k, t->mlen,
+        static_cast<const u32*>(t->seg_of_slot.p), static_cast<const V*>(t->boundary_list.p), t->lay, t->d_ctr);
+    KH_CUDA(t, cudaGetLastError());
     return KH_OK;
 }
 
@@ -488,6 +585,7 @@ int shard_phase_impl(kh_table* t, int phase, int* flag_out) {
     const Peers& pe = t->peers;
     const u32 n_starts = (u32)t->n_starts, n_split = t->shard_n_split;
     const unsigned gb = (unsigned)t->sm_count * 8;
+    const u32 head_base = t->shard_migrate ? t->lay.walk_cap : n_split;     // local id of contig 0's head segment
     if (flag_out) *flag_out = 0;
     switch (phase) {
     case 0: {   // walk
@@ -507,25 +605,31 @@ int shard_phase_impl(kh_table* t, int phase, int* flag_out) {
         KH_CUDA(t, cudaEventRecord(t->ev[EV_WALK], t->stream));
         return KH_OK;
     }
-    case 1: {   // one pointer-jumping round
+    case 1: {   // a batch of pointer-jumping rounds; stale peer reads are valid, so no barrier between them
         u32* flag = static_cast<u32*>(t->changed_flag.p);
-        KH_CUDA(t, cudaMemsetAsync(flag, 0, sizeof(u32), t->stream));
-        rank_round_sharded_kernel<<<gb, 256, 0, t->stream>>>(pe, static_cast<u64*>(t->link.p), (u32)t->shard_seg_cap, t->d_ctr, flag);
+        const int batch = 4;
+        for (int r = 0; r < batch; ++r) {
+            KH_CUDA(t, cudaMemsetAsync(flag, 0, sizeof(u32), t->stream));
+            if (t->shard_migrate)
+                rank_round_mig_kernel<<<gb, 256, 0, t->stream>>>(pe, static_cast<u64*>(t->link.p), t->lay, n_starts, t->d_ctr, flag);
+            else
+                rank_round_sharded_kernel<<<gb, 256, 0, t->stream>>>(pe, static_cast<u64*>(t->link.p), (u32)t->shard_seg_cap, t->d_ctr, flag);
+        }
         KH_CUDA(t, cudaGetLastError());
         u32 h = 0;
         KH_CUDA(t, cudaMemcpyAsync(&h, flag, sizeof(u32), cudaMemcpyDeviceToHost, t->stream));
         KH_CUDA(t, cudaStreamSynchronize(t->stream));
-        if (flag_out) *flag_out = (int)h;
-        t->stats.rank_rounds += 1;
+        if (flag_out) *flag_out = (int)h;          // did the LAST round of the batch still move something?
+        t->stats.rank_rounds += batch;
         return KH_OK;
     }
     case 2:     // contig lengths
-        contig_lengths_sharded_kernel<<<gb, 256, 0, t->stream>>>(pe, static_cast<u64*>(t->link.p), n_split, n_starts, t->k,
+        contig_lengths_sharded_kernel<<<gb, 256, 0, t->stream>>>(pe, static_cast<u64*>(t->link.p), head_base, n_starts, t->k,
             static_cast<u32*>(t->contig_len.p), static_cast<u32*>(t->contig_pre.p), t->d_ctr);
         KH_CUDA(t, cudaGetLastError());
         return KH_OK;
     case 3:     // claim tails
-        claim_tails_sharded_kernel<<<gb, 256, 0, t->stream>>>(pe, static_cast<u64*>(t->link.p), n_split, n_starts,
+        claim_tails_sharded_kernel<<<gb, 256, 0, t->stream>>>(pe, static_cast<u64*>(t->link.p), head_base, n_starts,
             static_cast<u32*>(t->contig_len.p), t->d_ctr);
         KH_CUDA(t, cudaGetLastError());
         return KH_OK;
@@ -534,9 +638,14 @@ int shard_phase_impl(kh_table* t, int phase, int* flag_out) {
         KH_CUDA(t, cudaEventRecord(t->ev[EV_RANK], t->stream));
         return KH_OK;
     case 5: {   // emit
-        emit_segments_sharded_kernel<<<(unsigned)((t->shard_seg_cap + 255) / 256), 256, 0, t->stream>>>(
-            pe, static_cast<u64*>(t->link.p), static_cast<unsigned char*>(t->seglen.p), static_cast<unsigned char*>(t->tmp.p),
-            t->seg_chars, (u32)t->shard_seg_cap, t->d_ctr, t->k);
+        if (t->shard_migrate)
+            emit_segments_mig_kernel<<<(unsigned)(((u64)t->lay.walk_cap + 255) / 256), 256, 0, t->stream>>>(
+                pe, static_cast<u64*>(t->link.p), static_cast<unsigned char*>(t->seglen.p), static_cast<unsigned char*>(t->tmp.p),
+                t->seg_chars, t->lay, t->d_ctr, t->k);
+        else
+            emit_segments_sharded_kernel<<<(unsigned)((t->shard_seg_cap + 255) / 256), 256, 0, t->stream>>>(
+                pe, static_cast<u64*>(t->link.p), static_cast<unsigned char*>(t->seglen.p), static_cast<unsigned char*>(t->tmp.p),
+                t->seg_chars, (u32)t->shard_seg_cap, t->d_ctr, t->k);
         if (n_starts) {
             const u64 head_threads = (u64)n_starts * (u64)(t->k + 1);
             emit_heads_kernel<W><<<(unsigned)((head_threads + 255) / 256), 256, 0, t->stream>>>(
@@ -662,6 +771,7 @@ int kh_destroy(kh_table* t) {
     for (DevBuf* b : bufs) if (b->p) cudaFree(b->p);
     for (auto& row : t->ipc_opened) for (void* q : row) if (q) cudaIpcCloseMemHandle(q);
     if (t->owner_ctr.p) cudaFree(t->owner_ctr.p);
+    for (DevBuf* b : {&t->seg_of_slot, &t->boundary_list, &t->outbox, &t->outbox_grouped}) if (b->p) cudaFree(b->p);
     if (t->changed_flag.p) cudaFree(t->changed_flag.p);
     if (t->table) cudaFree(t->table);
     if (t->d_ctr) cudaFree(t->d_ctr);
@@ -940,11 +1050,27 @@ int kh_measure_random_sector_rate(int device, uint64_t footprint_bytes, uint64_t
 
 
 // ---------------------------------------------------------------- sharded (multi-GPU) ------
-int kh_shard_init(kh_table* t, int rank, int world, uint64_t n_local_max, uint64_t n_total) {
+int kh_shard_init(kh_table* t, int rank, int world, uint64_t n_local_max, uint64_t n_total, uint64_t n_starts_max) {
     if (!t) return KH_ERR_ARG;
     KH_CUDA(t, cudaSetDevice(t->device));
-    return t->W == 1 ? shard_init_impl<1>(t, rank, world, n_local_max, n_total)
-                     : shard_init_impl<2>(t, rank, world, n_local_max, n_total);
+    return t->W == 1 ? shard_init_impl<1>(t, rank, world, n_local_max, n_total, n_starts_max)
+                     : shard_init_impl<2>(t, rank, world, n_local_max, n_total, n_starts_max);
+}
+
+int kh_shard_walk(kh_table* t, const void** links_dev_out, uint64_t* counts_out, uint64_t* link_bytes_out) {
+    if (!t || !links_dev_out || !counts_out) return KH_ERR_ARG;
+    KH_TRY(shard_require(t));
+    KH_CUDA(t, cudaSetDevice(t->device));
+    if (link_bytes_out) *link_bytes_out = t->W == 1 ? sizeof(OutEntry<1>) : sizeof(OutEntry<2>);
+    return t->W == 1 ? shard_walk_impl<1>(t, links_dev_out, reinterpret_cast<u64*>(counts_out))
+                     : shard_walk_impl<2>(t, links_dev_out, reinterpret_cast<u64*>(counts_out));
+}
+
+int kh_shard_resolve(kh_table* t, const void* links_dev, uint64_t n) {
+    if (!t || (n && !links_dev)) return KH_ERR_ARG;
+    KH_TRY(shard_require(t));
+    KH_CUDA(t, cudaSetDevice(t->device));
+    return t->W == 1 ? shard_resolve_impl<1>(t, links_dev, n) : shard_resolve_impl<2>(t, links_dev, n);
 }
 
 int kh_shard_export(kh_table* t, void* handles_out, uint64_t* meta_out) {

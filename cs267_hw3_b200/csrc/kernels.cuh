@@ -110,7 +110,7 @@ enum { kInsInserted = 0, kInsDuplicate = 1, kInsFull = 2 };
 // empty slot.  First writer wins on a duplicate key.
 template <int W>
 __device__ __forceinline__ int insert_one(typename Slot<W>::value_t* table, u64 nbuckets, u64 b,
-                                          typename Slot<W>::value_t v, u64 (&q)[4]) {
+                                          typename Slot<W>::value_t v, u64 (&q)[4], u64* pos_out = nullptr) {
     typedef Slot<W> S;
     for (u64 tries = 0; tries < nbuckets; ++tries) {
 #pragma unroll
@@ -118,7 +118,10 @@ __device__ __forceinline__ int insert_one(typename Slot<W>::value_t* table, u64 
             typename S::value_t cur = S::from_bucket(q, i);
             if (S::empty(cur)) {
                 cur = S::cas(table + b * S::kPerBucket + i, S::zero(), v);
-                if (S::empty(cur)) return kInsInserted;
+                if (S::empty(cur)) {
+                    if (pos_out) *pos_out = b * S::kPerBucket + i;
+                    return kInsInserted;
+                }
             }
             if (S::same_key(cur, v)) return kInsDuplicate;
         }

@@ -452,4 +452,463 @@ emit_segments_sharded_kernel(const Peers pe, const u64* __restrict__ link, const
     }
 }
 
+
+// =========================================================================================
+// Migrating walk: every GPU walks only the nodes it owns
+// =========================================================================================
+// With peer lookups (walk_sharded_kernel above) a walker stays on the GPU where it started, so after its
+// first supermer (P-1)/P of its lookups cross NVLink no matter how owners are chosen; measured on
+// B200s the walk gets SLOWER with every GPU added (3.4 ms at 2 GPUs, 7.9 ms at 4, ~18 ms at 8 for the
+// chr14 k=19 shape).  Here the walk follows the data instead:
+//   * a node whose predecessor lives on another GPU (or that has backward ext 'F') is a "boundary
+//     start": its owner registers it as a walker at insert time (the predecessor key follows from
+//     the backward extension, kmer_pair::last_kmer, kmer_t.hpp:55-57);
+//   * a walker follows successors only while they are local; when the successor belongs to another
+//     GPU it closes its segment with a PENDING link and drops (successor key, own segment id) into an
+//     outbox;
+//   * one all-to-all delivers the outboxes; the owner looks each key up locally, finds the boundary
+//     walker that started there and writes its segment id into the sender's link with one peer store.
+// With the minimizer-keyed owner function segments break only where the minimizer changes AND the new
+// owner differs, so the number of cross-GPU links is ~N/((K-m+2)/2) * (P-1)/P, each 16-32 bytes.
+// The start nodes parsed by a rank become zero-length "head stubs" that link to their first k-mer's
+// walker the same way, so contigs stay with the rank that parsed their start line.
+//
+// Local segment ids:  [0, n_split) splitters | [n_split, n_split+bcap) boundary starts (n_boundary used)
+//                     | [n_split+bcap, walk_cap) overflow | [walk_cap, walk_cap+n_starts) head stubs
+struct MigLayout {
+    u32 n_split, bcap, walk_cap, hcap;
+    u32 outbox_cap;
+};
+
+template <int W> struct OutEntry;
+template <> struct alignas(16) OutEntry<1> { u64 key; u32 src; u32 dest; };
+template <> struct alignas(16) OutEntry<2> { u128 key; u32 src; u32 dest; u64 pad; };
+
+// ---- K2 on received slot values, registering boundary starts ---------------------------------------
+template <int W>
+__global__ void __launch_bounds__(kInsThreads)
+insert_slots_shard_kernel(const typename Slot<W>::value_t* __restrict__ slots, u64 n, int k, int m, int mo,
+                          int rank, int world, typename Slot<W>::value_t* table, u64 nbuckets,
+                          u32* __restrict__ seg_of_slot, typename Slot<W>::value_t* __restrict__ boundary_list,
+                          u32 bcap, Counters* ctr) {
+    typedef Slot<W> S;
+    typedef typename S::value_t V;
+    __shared__ u32 s_inserted, s_dups, s_err;
+    if (threadIdx.x == 0) { s_inserted = 0; s_dups = 0; s_err = 0; }
+    __syncthreads();
+    const u64 base = (u64)blockIdx.x * kInsTile;
+    V v[kInsPerThread];
+    u64 b[kInsPerThread], pos[kInsPerThread];
+    u64 q[kInsPerThread][4];
+    bool live[kInsPerThread], fresh[kInsPerThread];
+#pragma unroll
+    for (int r = 0; r < kInsPerThread; ++r) {
+        const u64 i = base + (u64)r * kInsThreads + threadIdx.x;
+        live[r] = i < n;
+        v[r] = live[r] ? slots[i] : S::zero();
+        live[r] = live[r] && !S::empty(v[r]);
+        b[r] = live[r] ? place_bucket<W>(v[r], k, m, nbuckets) : 0;
+        if (live[r]) load256_cg(table + b[r] * S::kPerBucket, q[r]);
+    }
+    u32 inserted = 0, dups = 0, err = 0;
+#pragma unroll
+    for (int r = 0; r < kInsPerThread; ++r) {
+        fresh[r] = false; pos[r] = 0;
+        if (!live[r]) continue;
+        const int rc = insert_one<W>(table, nbuckets, b[r], v[r], q[r], &pos[r]);
+        fresh[r] = (rc == kInsInserted);
+        inserted += fresh[r];
+        dups += (rc == kInsDuplicate);
+        if (rc == kInsFull) err |= kErrTableFull;
+    }
+    // boundary starts: backward ext 'F', or the predecessor (backward ext + first K-1 bases) lives elsewhere
+#pragma unroll
+    for (int r = 0; r < kInsPerThread; ++r) {
+        bool bnd = false;
+        if (fresh[r]) {
+            bnd = S::back(v[r]) == kExtF;
+            if (!bnd && world > 1) bnd = owner_of<W>(S::prev_key(v[r], k), world, k, mo) != (u32)rank;
+        }
+        const u32 bal = __ballot_sync(kFullMask, bnd);
+        if (bal) {
+            u32 first = 0;
+            if (lane_id() == 0) first = atomicAdd(&ctr->n_boundary, (u32)__popc(bal));
+            first = __shfl_sync(kFullMask, first, 0);
+            if (bnd) {
+                const u32 id = first + __popc(bal & ((1u << lane_id()) - 1u));
+                if (id < bcap) { boundary_list[id] = v[r]; seg_of_slot[pos[r]] = id; }
+                else err |= kErrInternal;
+            }
+        }
+    }
+    inserted = __reduce_add_sync(kFullMask, inserted);
+    dups = __reduce_add_sync(kFullMask, dups);
+    err = __reduce_or_sync(kFullMask, err);
+    if (lane_id() == 0) {
+        if (inserted) atomicAdd(&s_inserted, inserted);
+        if (dups) atomicAdd(&s_dups, dups);
+        if (err) atomicOr(&s_err, err);
+    }
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        if (s_inserted) atomicAdd(&ctr->n_inserted, (u64)s_inserted);
+        if (s_dups) atomicAdd(&ctr->n_duplicates, (u64)s_dups);
+        if (s_err) atomicOr(&ctr->errors, s_err);
+    }
+}
+
+__global__ void init_mig_kernel(Counters* c, u32 first_overflow_seg) {
+    c->next_walker = 0;
+    c->next_seg = first_overflow_seg;
+    c->rank_rounds = 0;
+    c->n_nodes = 0;
+    c->contig_bytes = 0;
+    c->n_outbox = 0;
+    for (int i = 0; i < 40; ++i) c->flags[i] = 0;
+}
+
+// ---- head stubs: one zero-length segment per start node parsed here --------------------------------
+// Contig c of this rank is segment walk_cap + c; it emits nothing itself and links to the walker of its
+// first k-mer on that k-mer's owner (every node with backward ext 'F' is a boundary start there).
+template <int W>
+__global__ void __launch_bounds__(256)
+head_stub_kernel(const typename Slot<W>::value_t* __restrict__ starts, u32 n_starts, int k, int mo, int rank, int world,
+                 MigLayout lay, u64* __restrict__ link, unsigned char* __restrict__ seglen,
+                 OutEntry<W>* __restrict__ outbox, Counters* ctr) {
+    typedef Slot<W> S;
+    const u32 c = blockIdx.x * blockDim.x + threadIdx.x;
+    const bool on = c < n_starts;
+    const u32 bal = __ballot_sync(kFullMask, on);
+    if (!bal) return;
+    u32 first = 0;
+    if (lane_id() == 0) first = atomicAdd(&ctr->n_outbox, (u32)__popc(bal));
+    first = __shfl_sync(kFullMask, first, 0);
+    if (!on) return;
+    const u32 lid = lay.walk_cap + c;
+    const typename S::value_t key = S::key_only(starts[c]);
+    seglen[lid] = 0;
+    link[lid] = (u64)kLinkPending << 32;
+    const u32 at = first + __popc(bal & ((1u << lane_id()) - 1u));
+    if (at < lay.outbox_cap) {
+        OutEntry<W> e;
+        e.key = key; e.src = ((u32)rank << kRankShift) | lid; e.dest = owner_of<W>(key, world, k, mo);
+        outbox[at] = e;
+    } else {
+        atomicOr(&ctr->errors, kErrInternal);
+    }
+}
+
+// ---- the local walk --------------------------------------------------------------------------------
+struct MigWalkParams {
+    const void* table;
+    u64 nbuckets;
+    const void* boundary_list;
+    u64* link;
+    unsigned char* seglen;
+    unsigned char* tmp;
+    void* outbox;
+    Counters* ctr;
+    MigLayout lay;
+    u32 split_shift, seg_chars;
+    int k, m, mo, rank, world;
+};
+
+template <int W>
+__global__ void __launch_bounds__(kWalkThreads)
+walk_mig_kernel(const MigWalkParams p) {
+    typedef Slot<W> S;
+    typedef typename S::value_t V;
+    const V* __restrict__ table = static_cast<const V*>(p.table);
+    const V* __restrict__ bstart = static_cast<const V*>(p.boundary_list);
+    OutEntry<W>* __restrict__ outbox = static_cast<OutEntry<W>*>(p.outbox);
+    const u32 n_boundary = min(p.ctr->n_boundary, p.lay.bcap);
+    const u32 total = p.lay.n_split + n_boundary;
+    const u32 lane = lane_id();
+    const u32 lt_mask = (1u << lane) - 1u;
+    const u64 split_mask = (1ull << p.split_shift) - 1ull;
+    const u32 my_bits = (u32)p.rank << kRankShift;
+
+    u32 w_next = 0, w_end = 0;
+    bool exhausted = false;
+    u32 o_next = 0, o_end = 0;
+    bool active = false;
+    V cur = S::zero(), chk = S::zero();
+    u32 seg = 0, n = 0, steps = 0, limit = 256;
+    u64 acc = 0;
+
+    auto close = [&](u32 next) {       // next: global id, kLinkTail or kLinkPending
+        if (n & 7u) *reinterpret_cast<u64*>(p.tmp + (u64)seg * p.seg_chars + (n & ~7u)) = acc;
+        p.seglen[seg] = (unsigned char)n;
+        p.link[seg] = ((u64)next << 32) | (next == kLinkTail ? 0u : n);
+        active = false;
+    };
+
+    for (;;) {
+        __syncwarp();
+        const u32 idle = __ballot_sync(kFullMask, !active);
+        if (idle && !exhausted) {
+            if (w_next == w_end) {
+                u32 base = 0;
+                if (lane == 0) base = atomicAdd(&p.ctr->next_walker, kWalkBatch);
+                base = __shfl_sync(kFullMask, base, 0);
+                w_next = min(base, total);
+                w_end = min(base + kWalkBatch, total);
+                exhausted = (w_next == w_end);
+            }
+            const u32 avail = w_end - w_next;
+            const u32 rank_in = __popc(idle & lt_mask);
+            if (!active && rank_in < avail) {
+                const u32 w = w_next + rank_in;
+                seg = w; n = 0; acc = 0; steps = 0; limit = 256;          // boundary id b has local id n_split + b = w
+                if (w >= p.lay.n_split) {
+                    cur = bstart[w - p.lay.n_split];
+                    active = true;
+                } else {
+                    const u64 b = (u64)w << p.split_shift;
+                    cur = S::load_one_nc(table + b * S::kPerBucket);
+                    if (S::empty(cur)) p.link[seg] = (u64)kLinkUnused << 32;
+                    else active = true;
+                }
+                chk = cur;
+            }
+            w_next += min((u32)__popc(idle), avail);
+        }
+        if (__ballot_sync(kFullMask, active) == 0) {
+            if (exhausted) break;
+            continue;
+        }
+        const u32 full = __ballot_sync(kFullMask, active && n == p.seg_chars && S::fwd(cur) != kExtF);
+        if (full) {
+            const u32 want = __popc(full);
+            if (o_end - o_next < want) {
+                for (u32 id = o_next + lane; id < o_end; id += 32) p.link[id] = (u64)kLinkUnused << 32;
+                u32 base = 0;
+                if (lane == 0) base = atomicAdd(&p.ctr->next_seg, kSegBatch);
+                base = __shfl_sync(kFullMask, base, 0);
+                o_next = base; o_end = base + kSegBatch;
+            }
+            if (full & (1u << lane)) {
+                const u32 ns = o_next + __popc(full & lt_mask);
+                if (ns >= p.lay.walk_cap) {
+                    atomicOr(&p.ctr->errors, kErrInternal);
+                    close(kLinkTail);
+                } else {
+                    close(my_bits | ns);
+                    active = true; seg = ns; n = 0; acc = 0;
+                }
+            }
+            o_next += want;
+        }
+        // ---- one step; a lane whose successor lives elsewhere parks (key, dest) for the outbox ----
+        bool send = false;
+        V send_key = S::zero();
+        u32 send_dest = 0, send_src = 0;
+        if (active) {
+            const u32 f = S::fwd(cur);
+            if (f == kExtF) {
+                close(kLinkTail);
+            } else {
+                acc |= (u64)ext_char(f) << (8u * (n & 7u));
+                ++n;
+                if ((n & 7u) == 0) {
+                    *reinterpret_cast<u64*>(p.tmp + (u64)seg * p.seg_chars + n - 8) = acc;
+                    acc = 0;
+                }
+                const V nk = S::next_key(cur, p.k);
+                const u64 oh = owner_hash_of<W>(nk, p.k, p.mo);
+                const u32 owner = (u32)__umul64hi(oh, (u64)p.world);
+                if (owner != (u32)p.rank) {
+                    send = true; send_key = nk; send_dest = owner; send_src = my_bits | seg;
+                    close(kLinkPending);
+                } else {
+                    const u64 home = (p.m == 0) ? bucket_of(S::hash(nk), p.nbuckets)
+                                                : place_bucket_from<W>(p.m == p.mo ? oh : fmix64(minimizer_value<W>(nk, p.k, p.m) + 0x632BE59BD9B4E019ull), nk, p.nbuckets);
+                    V nxt = S::zero();
+                    u64 b = home; int s = -1;
+                    for (u64 tries = 0; tries < p.nbuckets && s < 0; ++tries) {
+                        u64 q[4];
+                        load256_ro(table + b * S::kPerBucket, q);
+                        bool hole = false;
+#pragma unroll
+                        for (int i = 0; i < S::kPerBucket; ++i) {
+                            const V c2 = S::from_bucket(q, i);
+                            if (s < 0 && !hole) {
+                                if (S::empty(c2)) hole = true;
+                                else if (S::same_key(c2, nk)) { nxt = c2; s = i; }
+                            }
+                        }
+                        if (hole) break;
+                        if (s < 0) b = (b + 1 == p.nbuckets) ? 0 : b + 1;
+                    }
+                    if (s < 0) {
+                        atomicOr(&p.ctr->errors, kErrNotFound);
+                        close(kLinkTail);
+                    } else if (s == 0 && (b & split_mask) == 0) {
+                        close(my_bits | (u32)(b >> p.split_shift));
+                    } else {
+                        cur = nxt;
+                        if (S::same_key(cur, chk)) {
+                            atomicOr(&p.ctr->errors, kErrCycle);
+                            close(kLinkTail);
+                        } else if (++steps == limit) {
+                            chk = cur; steps = 0; limit <<= 1;
+                        }
+                    }
+                }
+            }
+        }
+        const u32 sends = __ballot_sync(kFullMask, send);
+        if (sends) {
+            u32 first = 0;
+            if (lane == 0) first = atomicAdd(&p.ctr->n_outbox, (u32)__popc(sends));
+            first = __shfl_sync(kFullMask, first, 0);
+            if (send) {
+                const u32 at = first + __popc(sends & lt_mask);
+                if (at < p.lay.outbox_cap) {
+                    OutEntry<W> e;
+                    e.key = send_key; e.src = send_src; e.dest = send_dest;
+                    outbox[at] = e;
+                } else {
+                    atomicOr(&p.ctr->errors, kErrInternal);
+                }
+            }
+        }
+    }
+    for (u32 id = o_next + lane; id < o_end; id += 32)
+        if (id < p.lay.walk_cap) p.link[id] = (u64)kLinkUnused << 32;
+}
+
+// ---- outbox -> groups per destination (count, then scatter) ----------------------------------------
+template <int W>
+__global__ void __launch_bounds__(256)
+outbox_count_kernel(const OutEntry<W>* __restrict__ outbox, const Counters* __restrict__ ctr, u32 cap, u64* __restrict__ counts) {
+    __shared__ u32 s_cnt[kMaxRanks];
+    if (threadIdx.x < kMaxRanks) s_cnt[threadIdx.x] = 0;
+    __syncthreads();
+    const u32 n = min(ctr->n_outbox, cap);
+    for (u32 i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x)
+        atomicAdd(&s_cnt[outbox[i].dest & (kMaxRanks - 1)], 1u);
+    __syncthreads();
+    if (threadIdx.x < kMaxRanks && s_cnt[threadIdx.x]) atomicAdd(&counts[threadIdx.x], (u64)s_cnt[threadIdx.x]);
+}
+template <int W>
+__global__ void __launch_bounds__(256)
+outbox_scatter_kernel(const OutEntry<W>* __restrict__ outbox, const Counters* __restrict__ ctr, u32 cap,
+                      const u64* __restrict__ base, u64* __restrict__ cursor, OutEntry<W>* __restrict__ grouped) {
+    const u32 n = min(ctr->n_outbox, cap);
+    for (u32 i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) {
+        const OutEntry<W> e = outbox[i];
+        const u32 d = e.dest & (kMaxRanks - 1);
+        grouped[base[d] + atomicAdd(&cursor[d], 1ull)] = e;
+    }
+}
+
+// ---- resolve the links that arrived: local lookup, then one peer store into the sender's link --------
+template <int W>
+__global__ void __launch_bounds__(256)
+resolve_links_kernel(const Peers pe, const OutEntry<W>* __restrict__ inbox, u64 n,
+                     const typename Slot<W>::value_t* __restrict__ table, u64 nbuckets, int k, int m,
+                     const u32* __restrict__ seg_of_slot, const typename Slot<W>::value_t* __restrict__ boundary_list,
+                     MigLayout lay, Counters* ctr) {
+    typedef Slot<W> S;
+    const u64 i = (u64)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    const OutEntry<W> e = inbox[i];
+    typename S::value_t hit;
+    u64 b; int s;
+    if (!lookup<W>(table, nbuckets, k, m, e.key, hit, b, s)) {
+        atomicOr(&ctr->errors, kErrNotFound);              // kmer_hash.cpp:47-49
+        return;
+    }
+    const u32 id = seg_of_slot[b * S::kPerBucket + s];
+    const u32 n_boundary = min(ctr->n_boundary, lay.bcap);
+    if (id >= n_boundary || !S::same_key(boundary_list[id], e.key)) {
+        // the successor was not registered as a walker start: its backward extension does not name its predecessor
+        atomicOr(&ctr->errors, kErrBadInput);
+        return;
+    }
+    const u32 next_gid = ((u32)pe.rank << kRankShift) | (lay.n_split + id);
+    reinterpret_cast<u32*>(peer_link(pe, e.src))[1] = next_gid;       // high word of the sender's link
+}
+
+// valid local ids: splitters, used boundary starts, allocated overflow segments, head stubs
+__device__ __forceinline__ bool mig_live_id(u32 lid, const MigLayout& lay, u32 n_boundary, u32 next_seg, u32 n_starts) {
+    if (lid < lay.n_split + n_boundary) return true;
+    if (lid < lay.n_split + lay.bcap) return false;
+    if (lid < lay.walk_cap) return lid < next_seg;
+    return lid < lay.walk_cap + n_starts;
+}
+
+__global__ void __launch_bounds__(256)
+rank_round_mig_kernel(const Peers pe, u64* link, MigLayout lay, u32 n_starts, Counters* ctr, u32* changed) {
+    const u32 n_boundary = min(ctr->n_boundary, lay.bcap), next_seg = min(ctr->next_seg, lay.walk_cap);
+    const u32 end = lay.walk_cap + n_starts;
+    bool moved = false;
+    for (u64 i = (u64)blockIdx.x * blockDim.x + threadIdx.x; i < end; i += (u64)gridDim.x * blockDim.x) {
+        if (!mig_live_id((u32)i, lay, n_boundary, next_seg, n_starts)) continue;
+        const u64 li = __ldcg(link + i);
+        const u32 pi = (u32)(li >> 32);
+        if (pi >= kLinkFirstMarker) {
+            if (pi == kLinkPending) atomicOr(&ctr->errors, kErrInternal);     // a link nobody resolved
+            continue;
+        }
+        const u64 lp = __ldcg(peer_link(pe, pi));
+        const u32 pp = (u32)(lp >> 32);
+        if (pp == kLinkTail) continue;
+        if (pp >= kLinkFirstMarker) { atomicOr(&ctr->errors, kErrInternal); continue; }
+        __stcg(link + i, ((u64)pp << 32) | (u32)((u32)li + (u32)lp));
+        moved = true;
+    }
+    if (__any_sync(kFullMask, moved) && lane_id() == 0) *changed = 1;
+}
+
+__global__ void __launch_bounds__(256)
+emit_segments_mig_kernel(const Peers pe, const u64* __restrict__ link, const unsigned char* __restrict__ seglen,
+                         const unsigned char* __restrict__ tmp, u32 seg_chars, MigLayout lay, Counters* ctr, int k) {
+    const u64 seg = (u64)blockIdx.x * blockDim.x + threadIdx.x;
+    const u32 n_boundary = min(ctr->n_boundary, lay.bcap), next_seg = min(ctr->next_seg, lay.walk_cap);
+    u32 len = 0;
+    char* dst = nullptr;
+    if (seg < lay.walk_cap && mig_live_id((u32)seg, lay, n_boundary, next_seg, 0)) {
+        const u64 li = link[seg];
+        const u32 pi = (u32)(li >> 32);
+        if (pi != kLinkUnused && pi != kLinkTail && pi != kLinkPending) {
+            bool ok = true, is_tail = (pi == kLinkClaimed);
+            u32 cg = 0;
+            if (is_tail) {
+                cg = (u32)li;
+            } else {
+                const u64 lt = *peer_link(pe, pi);
+                if ((u32)(lt >> 32) != kLinkClaimed) ok = false;
+                else cg = (u32)lt;
+            }
+            if (ok) {
+                const u32 r = cg >> kRankShift, c = cg & kLocalMask;
+                const u32 pre = pe.contig_pre[r][c];
+                u32 pos = pre;
+                if (!is_tail) {
+                    if ((u32)li > pre) { atomicOr(&ctr->errors, kErrConverge); ok = false; }
+                    else pos = pre - (u32)li;
+                }
+                if (ok) {
+                    const u64 off = pe.contig_off[r][c] + (u64)k + pos;
+                    len = seglen[seg];
+                    if (off + len > pe.out_cap[r]) { atomicOr(&ctr->errors, kErrInternal); len = 0; }
+                    dst = pe.out[r] + off;
+                }
+            }
+        }
+    }
+    u32 todo = __ballot_sync(kFullMask, len > 0);
+    const u64 seg0 = seg - lane_id();
+    while (todo) {
+        const int src_lane = __ffs(todo) - 1;
+        todo &= todo - 1;
+        const u32 n = __shfl_sync(kFullMask, len, src_lane);
+        char* d = reinterpret_cast<char*>(__shfl_sync(kFullMask, reinterpret_cast<u64>(dst), src_lane));
+        const unsigned char* src = tmp + (seg0 + src_lane) * (u64)seg_chars;
+        for (u32 j = lane_id(); j < n; j += 32) d[j] = (char)src[j];
+    }
+}
+
 }  // namespace kh

@@ -108,6 +108,7 @@ template <> struct Slot<1> {
     static __host__ __device__ __forceinline__ u32 back(value_t v) { return (u32)(v >> 3) & 7u; }
     static __host__ __device__ __forceinline__ bool same_key(value_t a, value_t b) { return ((a ^ b) >> 6) == 0ull; }
     static __host__ __device__ __forceinline__ bool equal(value_t a, value_t b) { return a == b; }
+    static __host__ __device__ __forceinline__ value_t key_only(value_t v) { return v & ~63ull; }
     static __host__ __device__ __forceinline__ u64 hash(value_t v) { return fmix64(v >> 6); }
     static __host__ __device__ __forceinline__ u64 owner_hash(value_t v) { return fmix64((v >> 6) ^ 0x9E3779B97F4A7C15ull); }
     static __device__ __forceinline__ value_t from_bucket(const u64 (&q)[4], int i) { return q[i]; }
@@ -142,6 +143,10 @@ template <> struct Slot<1> {
     static __host__ __device__ __forceinline__ u32 base_at(value_t v, int k, int i) {
         return (u32)(v >> (6 + 2 * (k - 1 - i))) & 3u;
     }
+    // key bits of backward_ext + kmer[:-1]  (kmer_pair::last_kmer, kmer_t.hpp:55-57); back must be a base
+    static __host__ __device__ __forceinline__ value_t prev_key(value_t v, int k) {
+        return ((((v >> 6) >> 2) | ((u64)back(v) << (2 * (k - 1)))) << 6);
+    }
     static __device__ __forceinline__ value_t cas(value_t* addr, value_t expect, value_t val) {
         return atomicCAS(addr, expect, val);
     }
@@ -161,6 +166,7 @@ template <> struct Slot<2> {
         return (((a.lo ^ b.lo) >> 6) | (a.hi ^ b.hi)) == 0ull;
     }
     static __host__ __device__ __forceinline__ bool equal(value_t a, value_t b) { return a.lo == b.lo && a.hi == b.hi; }
+    static __host__ __device__ __forceinline__ value_t key_only(value_t v) { return u128{v.lo & ~63ull, v.hi}; }
     static __host__ __device__ __forceinline__ u64 hash(value_t v) {
         return fmix64((v.lo >> 6) ^ fmix64(v.hi + 0x9E3779B97F4A7C15ull));
     }
@@ -214,6 +220,12 @@ template <> struct Slot<2> {
     static __host__ __device__ __forceinline__ u32 base_at(value_t v, int k, int i) {
         const int sh = 6 + 2 * (k - 1 - i);
         return (u32)(sh >= 64 ? (v.hi >> (sh - 64)) : (v.lo >> sh)) & 3u;
+    }
+    static __host__ __device__ __forceinline__ value_t prev_key(value_t v, int k) {
+        u128 key = shr(shr(v, 6), 2);                       // drop ext bits, drop the last base
+        const int sh = 2 * (k - 1);                          // 58..120 for K in 30..61
+        if (sh >= 64) key.hi |= (u64)back(v) << (sh - 64); else key.lo |= (u64)back(v) << sh;
+        return shl(key, 6);
     }
     static __device__ __forceinline__ value_t cas(value_t* addr, value_t expect, value_t val) {
         return cas128(addr, expect, val);
@@ -304,6 +316,8 @@ enum : u32 {
 constexpr u32 kLinkTail = 0xFFFFFFFFu;      // segment ends a contig (forward ext 'F')
 constexpr u32 kLinkUnused = 0xFFFFFFFEu;    // id never walked
 constexpr u32 kLinkClaimed = 0xFFFFFFFDu;   // tail claimed by a contig; low word = contig id
+constexpr u32 kLinkPending = 0xFFFFFFFCu;   // sharded walk: successor lives on another GPU, link not resolved yet
+constexpr u32 kLinkFirstMarker = kLinkPending;
 
 struct Counters {
     u32 next_walker;
@@ -315,6 +329,8 @@ struct Counters {
     u64 scan_total;       // result of the last device scan (start nodes of the last insert call)
     u64 n_nodes;
     u64 contig_bytes;
+    u32 n_boundary;       // sharded: nodes of this shard whose predecessor lives on another GPU (walker starts)
+    u32 n_outbox;         // sharded: pending links produced by the local walk
     u32 flags[40];
 };
 

@@ -126,21 +126,30 @@ class Shard:
     """One rank: a kh_table in sharded mode."""
 
     def __init__(self, k: int, rank: int, world: int, n_local_max: int, n_total: int,
-                 load_factor: float = 0.5, device: int = 0):
+                 load_factor: float = 0.5, device: int = 0, n_starts_max: int | None = None):
         import cs267_hw3_b200 as kh
 
         self.kh, self.k, self.rank, self.world = kh, k, rank, world
+        self.n_local_max, self.n_total = n_local_max, n_total
+        self.n_starts_max = n_local_max if n_starts_max is None else n_starts_max
         self.tab = kh.KmerHashTable(k, shard_capacity(n_total, world), load_factor, device)
         L = kh.lib()
         self._declare(L)
-        self.tab._check(L.kh_shard_init(self.tab._h, rank, world, n_local_max, n_total))
+        self.reinit()
+
+    def reinit(self) -> None:
+        """(Re)compute the fixed capacities, e.g. after changing split_buckets / seg_chars."""
+        self.tab._check(self.kh.lib().kh_shard_init(self.tab._h, self.rank, self.world, self.n_local_max, self.n_total,
+                                                    self.n_starts_max))
 
     @staticmethod
     def _declare(L):
         if getattr(L, "_shard_declared", False):
             return
         vp, u64, i32 = C.c_void_p, C.c_uint64, C.c_int
-        L.kh_shard_init.argtypes = [vp, i32, i32, u64, u64]
+        L.kh_shard_init.argtypes = [vp, i32, i32, u64, u64, u64]
+        L.kh_shard_walk.argtypes = [vp, C.POINTER(vp), C.POINTER(u64), C.POINTER(u64)]
+        L.kh_shard_resolve.argtypes = [vp, vp, u64]
         L.kh_shard_export.argtypes = [vp, vp, C.POINTER(u64)]
         L.kh_shard_connect.argtypes = [vp, vp, C.POINTER(u64)]
         L.kh_shard_connect_local.argtypes = [vp, C.POINTER(vp), i32]
@@ -166,6 +175,16 @@ class Shard:
 
     def insert_slots(self, slots_dev: int, n: int) -> None:
         self.tab._check(self.kh.lib().kh_insert_slots_device(self.tab._h, slots_dev, n))
+
+    def walk(self) -> tuple[int, list[int], int]:
+        """K8: local walk; returns (device ptr of pending links grouped by destination, counts, bytes per link)."""
+        out, nb = C.c_void_p(), C.c_uint64()
+        counts = (C.c_uint64 * MAX_RANKS)()
+        self.tab._check(self.kh.lib().kh_shard_walk(self.tab._h, C.byref(out), counts, C.byref(nb)))
+        return out.value or 0, [int(x) for x in counts][: self.world], int(nb.value)
+
+    def resolve(self, links_dev: int, n: int) -> None:
+        self.tab._check(self.kh.lib().kh_shard_resolve(self.tab._h, links_dev, n))
 
     def phase(self, which: int) -> int:
         flag = C.c_int()
@@ -343,25 +362,44 @@ def sharded_insert(comm, blocks: list[tuple[int, int]]) -> None:
     comm.barrier()                                        # hash_map.hpp:79: every insert is visible before any find
 
 
-def sharded_assemble(comm, max_rounds: int = 40) -> int:
+def sharded_assemble(comm, max_rounds: int = 40, timings: dict | None = None) -> int:
     """assemble_contigs (kmer_hash.cpp:38-55) across ranks.  Returns the number of pointer-jumping rounds.
-    Raises ShardedError if any rank flagged an error."""
+    Raises ShardedError if any rank flagged an error.  `timings` (optional) receives host wall-clock
+    milliseconds per phase (each phase ends with a barrier that drains the stream)."""
+    import time
+
     shards = comm.shards
-    for s in shards:
-        s.phase(0)                                        # walk: lookups go to the owner's table over NVLink
+    t0 = time.perf_counter()
+
+    def lap(name):
+        nonlocal t0
+        if timings is not None:
+            t1 = time.perf_counter()
+            timings[name] = timings.get(name, 0.0) + (t1 - t0) * 1e3
+            t0 = t1
+
+    walked = [s.walk() for s in shards]                   # every GPU walks the k-mers it owns
+    lap("walk")
+    recvs = comm.exchange([(w[0], w[1]) for w in walked], walked[0][2])     # links that leave the GPU: one all-to-all
+    for s, (ptr, n) in zip(shards, recvs):
+        s.resolve(ptr, n)                                 # local lookup + one peer store into the sender's link
     comm.barrier()
+    lap("links")
     rounds = 0
     while rounds < max_rounds:
-        moved = [s.phase(1) for s in shards]
-        rounds += 1
+        moved = [s.phase(1) for s in shards]              # a batch of rounds, no barrier needed inside it
+        rounds += 4
         comm.barrier()
         if not comm.any(moved):
             break
-    for ph in (2, 3, 4, 5):                               # lengths, tail claims, offsets, emit
+    lap("rank_rounds")
+    for ph, name in ((2, "lengths"), (3, "claims"), (4, "offsets"), (5, "emit")):
         for s in shards:
             s.phase(ph)
         comm.barrier()
+        lap(name)
     bits = comm.bits_or([s.phase(6) for s in shards])
+    lap("collect")
     if bits:
         raise ShardedError(bits)
     return rounds
@@ -400,6 +438,8 @@ def bench(args, k, n_total, c_total, longn, workload, rank, world, local_rank):
     dev.copy_(torch.from_numpy(host.array))
     torch.cuda.synchronize()
 
+    phase_ms: dict = {}
+
     def step():
         shard.tab.clear()
         comm.barrier()
@@ -407,12 +447,13 @@ def bench(args, k, n_total, c_total, longn, workload, rank, world, local_rank):
         e0.record(stream)
         sharded_insert(comm, [(dev.data_ptr(), n_local)])
         e1.record(stream)
-        rounds = sharded_assemble(comm)
+        rounds = sharded_assemble(comm, timings=phase_ms)
         e2.record(stream)
         return e0, e1, e2, rounds
 
     for _ in range(args.warmup):
         step()
+    phase_ms.clear()
     dist.barrier()
     torch.cuda.synchronize()
     from bench import ClockSampler
@@ -455,7 +496,8 @@ def bench(args, k, n_total, c_total, longn, workload, rank, world, local_rank):
                        "owner's table over NVLink peer mappings; pointer jumping across GPUs",
                        "timing": "CUDA events on the launching stream per step, max over ranks, mean of steps",
                        "l2": "per-GPU table and records larger than L2; table re-zeroed between steps (outside the event pair)"},
-            "stages_ms": {"ms_insert_incl_all_to_all": ms_ins, "ms_traverse": ms_total - ms_ins},
+            "stages_ms": {"ms_insert_incl_all_to_all": ms_ins, "ms_traverse": ms_total - ms_ins,
+                          "traverse_phases_host_ms_rank0": {k2: v / args.steps for k2, v in phase_ms.items()}},
             "rank_rounds": evs[-1][3], "assembly_time_s": ms_total * 1e-3, "wall_s_timed_loop": wall, "gen_s": t_gen,
             "verified": verified,
             "roofline": {"bound": "hbm", "kernel": "walk_sharded_kernel + insert_slots_direct_kernel (whole path)",

@@ -147,8 +147,9 @@ int kh_measure_random_sector_rate(int device, uint64_t footprint_bytes, uint64_t
  * over NVLink peer mappings (CUDA IPC between processes, or kh_shard_connect_local in one process).
  * ------------------------------------------------------------------------------------------- */
 uint64_t kh_slot_bytes(int k);            /* bytes of one exchanged slot value: 8 (K<=29) or 16 */
-/* Fix all capacities for this rank: at most n_local_max records parsed here, n_total over all ranks. */
-int kh_shard_init(kh_table* t, int rank, int world, uint64_t n_local_max, uint64_t n_total);
+/* Fix all capacities for this rank: at most n_local_max records (n_starts_max of them start nodes) parsed
+ * here, n_total records over all ranks. */
+int kh_shard_init(kh_table* t, int rank, int world, uint64_t n_local_max, uint64_t n_total, uint64_t n_starts_max);
 /* 6 CUDA IPC handles (64 bytes each) + 2 uint64 of metadata for this rank; gather them from all ranks */
 int kh_shard_export(kh_table* t, void* handles_out, uint64_t* meta_out);
 int kh_shard_connect(kh_table* t, const void* all_handles, const uint64_t* all_meta);
@@ -158,9 +159,16 @@ int kh_shard_connect_local(kh_table* t, kh_table* const* peers, int world);
 int kh_shard_owner_partition(kh_table* t, const void* pairs_dev, uint64_t n, const void** slots_dev_out, uint64_t* counts_out);
 /* K2 on slot values received from the other ranks */
 int kh_insert_slots_device(kh_table* t, const void* slots_dev, uint64_t n);
-/* phases, each followed by a barrier across ranks: 0 walk, 1 one pointer-jumping round (flag_out =
- * "something moved"; repeat until no rank moved), 2 contig lengths, 3 claim tails, 4 offsets,
- * 5 emit, 6 collect (flag_out = device error bits) */
+/* K8, the walk: every GPU follows successors only through k-mers it owns; where a chain leaves the GPU the
+ * segment ends with a pending link.  Returns those links grouped by destination rank (counts_out has 8
+ * entries, *link_bytes_out is the size of one link record); the caller moves them with one all-to-all
+ * and hands what it received to kh_shard_resolve, which looks the k-mers up locally and patches the
+ * senders' links through the peer mapping.  Barrier after each. */
+int kh_shard_walk(kh_table* t, const void** links_dev_out, uint64_t* counts_out, uint64_t* link_bytes_out);
+int kh_shard_resolve(kh_table* t, const void* links_dev, uint64_t n);
+/* remaining phases, each followed by a barrier across ranks: 1 a batch of pointer-jumping rounds
+ * (flag_out = "the last one still moved something"; repeat until no rank reports movement),
+ * 2 contig lengths, 3 claim tails, 4 offsets, 5 emit, 6 collect (flag_out = device error bits) */
 int kh_shard_phase(kh_table* t, int phase, int* flag_out);
 int kh_shard_result(kh_table* t, const char** contigs_dev, const uint64_t** offsets_dev,
                     uint64_t* n_contigs, uint64_t* contig_bytes, uint64_t* n_nodes);

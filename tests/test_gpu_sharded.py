@@ -24,8 +24,8 @@ def _run(k, n, c, world, seed=1, longn=0, lf=0.5, options=None):
         for name, val in (options or {}).items():
             s.tab.set_option(name, val)
     if options:       # capacities depend on the options: re-init
-        for r, s in enumerate(shards):
-            s.tab._check(kh.lib().kh_shard_init(s.tab._h, r, world, n_local_max, n))
+        for s in shards:
+            s.reinit()
     comm = sh.LocalComm(shards)
     comm.connect()
     L = kh.lib()
