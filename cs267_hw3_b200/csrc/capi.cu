@@ -425,11 +425,11 @@ int shard_init_impl(kh_table* t, int rank, int world, u64 n_local_max, u64 n_tot
         seg_cap = walk_cap + n_starts_max;
         if (seg_cap >= (u64)kLocalMask - 16) return fail(t, KH_ERR_ARG, "too many walk segments per GPU for 28-bit local ids");
         t->lay.n_split = t->shard_n_split; t->lay.bcap = (u32)bcap; t->lay.walk_cap = (u32)walk_cap;
-        t->lay.hcap = (u32)n_starts_max; t->lay.outbox_cap = (u32)seg_cap;
+        t->lay.hcap = (u32)n_starts_max; t->lay.outbox_cap = (u32)std::min<u64>(0xFFFFFF00ull, 2 * seg_cap + (u64)kOutBatch * (nwarps + 1));
         tmp_rows = walk_cap;
         KH_TRY(ensure(t, t->seg_of_slot, t->nbuckets * t->per_bucket * sizeof(u32)));
         KH_TRY(ensure(t, t->boundary_list, (bcap + 1) * sizeof(V)));
-        KH_TRY(ensure(t, t->outbox, (seg_cap + 1) * sizeof(OutEntry<W>)));
+        KH_TRY(ensure(t, t->outbox, ((u64)t->lay.outbox_cap + 1) * sizeof(OutEntry<W>)));
         KH_TRY(ensure(t, t->outbox_grouped, (seg_cap + 1) * sizeof(OutEntry<W>)));
     } else {
         seg_cap = (u64)t->shard_n_split + n_starts_max + 2 * (n_total / t->seg_chars + 1) + (u64)kSegBatch * nwarps + 64;
@@ -748,7 +748,8 @@ int kh_create(int k, uint64_t n_expected, double load_factor, int device, kh_tab
     int v = env_int("KH_SPLIT_BUCKETS", 0);
     if (v > 0 && set_option(t, "split_buckets", v) != KH_OK) fprintf(stderr, "libkh_b200: ignoring KH_SPLIT_BUCKETS=%d\n", v);
     t->mlen = env_int("KH_LOCALITY", 0) ? minimizer_len(k) : 0;
-    t->olen = env_int("KH_OWNER_LOCALITY", 1) ? minimizer_len(k) : 0;
+    t->olen = env_int("KH_OWNER_LOCALITY", 1) ? owner_minimizer_len(k) : 0;
+    if (env_int("KH_OWNER_MLEN", 0) > 0) t->olen = std::min(k, env_int("KH_OWNER_MLEN", 0));
     t->partition_mode = env_int("KH_PARTITION", -1);
     t->ins_mode = env_int("KH_INS_MODE", 1);
     t->warm_ahead = env_int("KH_WARM_AHEAD", 1);

@@ -480,6 +480,8 @@ struct MigLayout {
     u32 outbox_cap;
 };
 
+constexpr u32 kOutBatch = 256;          // outbox entries a warp reserves per global atomic
+constexpr u32 kOutVoid = 0xFFu;          // dest of a reserved-but-unused outbox entry
 template <int W> struct OutEntry;
 template <> struct alignas(16) OutEntry<1> { u64 key; u32 src; u32 dest; };
 template <> struct alignas(16) OutEntry<2> { u128 key; u32 src; u32 dest; u64 pad; };
@@ -631,10 +633,12 @@ walk_mig_kernel(const MigWalkParams p) {
     u32 w_next = 0, w_end = 0;
     bool exhausted = false;
     u32 o_next = 0, o_end = 0;
+    u32 x_next = 0, x_end = 0;          // this warp's block of outbox entries (one global atomic per kOutBatch links)
     bool active = false;
     V cur = S::zero(), chk = S::zero();
     u32 seg = 0, n = 0, steps = 0, limit = 256;
     u64 acc = 0;
+    MinState ms{0, 0, 0};               // owner minimizer of `cur`, carried along the chain
 
     auto close = [&](u32 next) {       // next: global id, kLinkTail or kLinkPending
         if (n & 7u) *reinterpret_cast<u64*>(p.tmp + (u64)seg * p.seg_chars + (n & ~7u)) = acc;
@@ -670,6 +674,7 @@ walk_mig_kernel(const MigWalkParams p) {
                     else active = true;
                 }
                 chk = cur;
+                if (active && p.mo) ms = min_scan<W>(cur, p.k, p.mo);
             }
             w_next += min((u32)__popc(idle), avail);
         }
@@ -715,7 +720,9 @@ walk_mig_kernel(const MigWalkParams p) {
                     acc = 0;
                 }
                 const V nk = S::next_key(cur, p.k);
-                const u64 oh = owner_hash_of<W>(nk, p.k, p.mo);
+                u64 oh;
+                if (p.mo) { ms = min_step<W>(ms, nk, p.k, p.mo); oh = owner_hash_from_minimizer(ms.val); }
+                else oh = S::owner_hash(nk);
                 const u32 owner = (u32)__umul64hi(oh, (u64)p.world);
                 if (owner != (u32)p.rank) {
                     send = true; send_key = nk; send_dest = owner; send_src = my_bits | seg;
@@ -759,11 +766,18 @@ walk_mig_kernel(const MigWalkParams p) {
         }
         const u32 sends = __ballot_sync(kFullMask, send);
         if (sends) {
-            u32 first = 0;
-            if (lane == 0) first = atomicAdd(&p.ctr->n_outbox, (u32)__popc(sends));
-            first = __shfl_sync(kFullMask, first, 0);
+            const u32 want = __popc(sends);
+            if (x_end - x_next < want) {
+                // unused tail of the old block: mark the entries void (dest = kOutVoid) so grouping skips them
+                for (u32 at = x_next + lane; at < x_end; at += 32)
+                    if (at < p.lay.outbox_cap) outbox[at].dest = kOutVoid;
+                u32 base = 0;
+                if (lane == 0) base = atomicAdd(&p.ctr->n_outbox, kOutBatch);
+                base = __shfl_sync(kFullMask, base, 0);
+                x_next = base; x_end = base + kOutBatch;
+            }
             if (send) {
-                const u32 at = first + __popc(sends & lt_mask);
+                const u32 at = x_next + __popc(sends & lt_mask);
                 if (at < p.lay.outbox_cap) {
                     OutEntry<W> e;
                     e.key = send_key; e.src = send_src; e.dest = send_dest;
@@ -772,10 +786,13 @@ walk_mig_kernel(const MigWalkParams p) {
                     atomicOr(&p.ctr->errors, kErrInternal);
                 }
             }
+            x_next += want;
         }
     }
     for (u32 id = o_next + lane; id < o_end; id += 32)
         if (id < p.lay.walk_cap) p.link[id] = (u64)kLinkUnused << 32;
+    for (u32 at = x_next + lane; at < x_end; at += 32)
+        if (at < p.lay.outbox_cap) outbox[at].dest = kOutVoid;
 }
 
 // ---- outbox -> groups per destination (count, then scatter) ----------------------------------------
@@ -787,7 +804,10 @@ outbox_count_kernel(const OutEntry<W>* __restrict__ outbox, const Counters* __re
     __syncthreads();
     const u32 n = min(ctr->n_outbox, cap);
     for (u32 i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x)
-        atomicAdd(&s_cnt[outbox[i].dest & (kMaxRanks - 1)], 1u);
+    {
+        const u32 d = outbox[i].dest;
+        if (d < (u32)kMaxRanks) atomicAdd(&s_cnt[d], 1u);
+    }
     __syncthreads();
     if (threadIdx.x < kMaxRanks && s_cnt[threadIdx.x]) atomicAdd(&counts[threadIdx.x], (u64)s_cnt[threadIdx.x]);
 }
@@ -798,8 +818,8 @@ outbox_scatter_kernel(const OutEntry<W>* __restrict__ outbox, const Counters* __
     const u32 n = min(ctr->n_outbox, cap);
     for (u32 i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) {
         const OutEntry<W> e = outbox[i];
-        const u32 d = e.dest & (kMaxRanks - 1);
-        grouped[base[d] + atomicAdd(&cursor[d], 1ull)] = e;
+        const u32 d = e.dest;
+        if (d < (u32)kMaxRanks) grouped[base[d] + atomicAdd(&cursor[d], 1ull)] = e;
     }
 }
 

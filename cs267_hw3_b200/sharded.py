@@ -54,6 +54,10 @@ def minimizer_len(k: int) -> int:
     return k if k <= 14 else (11 if k <= 18 else (13 if k <= 29 else (21 if k <= 40 else 31)))
 
 
+def owner_minimizer_len(k: int) -> int:
+    return k if k <= 14 else 7
+
+
 def minimizer_value(slot: int, k: int, m: int) -> int:
     """The m-mer of the k-mer with the smallest order value, leftmost on ties (csrc/slot.cuh)."""
     key, mask = slot >> 6, (1 << (2 * m)) - 1
@@ -72,7 +76,7 @@ def owner_of_slot(slot: int, k: int, world: int, locality: bool = True) -> int:
     locality=True: the owner is a hash of the k-mer's minimizer, so the successor of a k-mer usually has the
     same owner; False: plain hash of the key (KH_LOCALITY=0)."""
     if locality:
-        h = _fmix64((minimizer_value(slot, k, minimizer_len(k)) + 0x632BE59BD9B4E019) & _M64)
+        h = _fmix64((minimizer_value(slot, k, owner_minimizer_len(k)) + 0x632BE59BD9B4E019) & _M64)
     elif 2 * k + 6 <= 64:
         h = _fmix64((slot >> 6) ^ 0x9E3779B97F4A7C15)
     else:
