@@ -43,7 +43,7 @@ struct kh_table {
     DevBuf starts;
     u64 n_starts = 0;
     DevBuf mask, tile_counts, tile_offs, scan_blocks;
-    DevBuf part_hist, part_base, part_cursor, grouped;
+    DevBuf part_cursor, grouped;
     int partition_mode = -1;          // -1 auto, 0 never, 1 always (KH_PARTITION)
     u64 part_bytes = 16ull << 20;     // table bytes per partition (KH_PART_MB)
     bool part_attr_set = false;
@@ -55,7 +55,7 @@ struct kh_table {
     DevBuf stage[2], text_stage, scratch_a, scratch_b, scratch_c;
     void* h_out = nullptr; size_t h_out_cap = 0;
     void* h_off = nullptr; size_t h_off_cap = 0;
-    u32 split_shift = 3, seg_chars = 64;
+    u32 split_shift = 5, seg_chars = 64;     // every 32nd bucket's first slot is a splitter (tools/probes/sweep_walk.sh)
     cudaEvent_t ev[EV_COUNT] = {};
     cudaEvent_t ev_copied[2] = {}, ev_consumed[2] = {};
     bool have_ins = false, have_as = false, have_pack = false, have_clr = false;
@@ -767,7 +767,7 @@ int kh_destroy(kh_table* t) {
     cudaSetDevice(t->device);
     if (t->own_stream) cudaStreamSynchronize(t->own_stream);
     DevBuf* bufs[] = {&t->starts, &t->mask, &t->tile_counts, &t->tile_offs, &t->scan_blocks, &t->link, &t->seglen,
-                      &t->tmp, &t->part_hist, &t->part_base, &t->part_cursor, &t->grouped, &t->contig_len, &t->contig_pre, &t->contig_off, &t->out, &t->stage[0], &t->stage[1],
+                      &t->tmp, &t->part_cursor, &t->grouped, &t->contig_len, &t->contig_pre, &t->contig_off, &t->out, &t->stage[0], &t->stage[1],
                       &t->text_stage, &t->scratch_a, &t->scratch_b, &t->scratch_c};
     for (DevBuf* b : bufs) if (b->p) cudaFree(b->p);
     for (auto& row : t->ipc_opened) for (void* q : row) if (q) cudaIpcCloseMemHandle(q);

@@ -1,15 +1,18 @@
-// kernels.cuh -- the sm_100a kernels of the k-mer hash / contig traversal path.
+// kernels.cuh -- the sm_100a kernels of the single-GPU k-mer hash / contig traversal path.
 //
-//   K1 pack_lines_kernel     text lines -> kmer_pair records          (read_kmers.hpp:72-76, packing.hpp:50-92)
-//   K2 insert_kernel         records -> open-addressing table, + start-node bitmask
-//                                                                      (hash_map.hpp:55-72, kmer_hash.cpp:27-31)
-//   K3 scatter_starts_kernel bitmask -> start list in file order       (kmer_hash.cpp:27-31)
-//   K4 find_kernel           batch lookup                              (hash_map.hpp:83-92)
-//   K5 walk_kernel           one lane per walk segment                 (kmer_hash.cpp:38-55, kmer_t.hpp:51-53)
-//      rank_kernel           pointer jumping over the segment list
-//   K6 emit_*_kernel         contig text                               (read_kmers.hpp:81-92)
+//   K1 pack_lines_kernel      text lines -> kmer_pair records            (read_kmers.hpp:72-76, packing.hpp:50-92)
+//   K2 insert_kernel          records -> open-addressing table + start bitmask, direct (tables that fit L2)
+//                                                                         (hash_map.hpp:55-72, kmer_hash.cpp:27-31)
+//   K2p partition_kernel      records grouped by ~16 MB table region (+ start bitmask)
+//       insert_slots_kernel   grouped slot values -> table, CAS-first, region warm-up      (tables larger than L2)
+//   K3 scan_* / scatter_starts_kernel   start bitmask -> start list in file order           (kmer_hash.cpp:27-31)
+//   K4 find_kernel            batch lookup                                (hash_map.hpp:83-92)
+//   K5 walk_kernel            one lane per walk segment                   (kmer_hash.cpp:38-55, kmer_t.hpp:51-53)
+//      rank_kernel            pointer jumping over the segment list (cooperative launch)
+//   K6 emit_segments_kernel / emit_heads_kernel   contig text             (read_kmers.hpp:81-92)
 //
-// All of it is HBM-bound integer work: no tensor cores, no floating point.
+// All of it is HBM-bound integer work: no tensor cores, no floating point.  The multi-GPU kernels are in
+// sharded.cuh.
 #pragma once
 #include <cooperative_groups.h>
 
@@ -244,8 +247,11 @@ constexpr int kPartTile = kPartThreads * kPartPerThread;     // 2048 records per
 // reserved with one atomicAdd per (block, partition); a record that does not fit -- never in practice
 // -- is inserted directly).  Also produces the start bitmask / per-tile start counts that
 // scatter_starts_kernel consumes (tiles of kInsTile records, identical to insert_kernel's).
+#ifndef KH_PART_MIN_BLOCKS
+#define KH_PART_MIN_BLOCKS 4
+#endif
 template <int W>
-__global__ void __launch_bounds__(kPartThreads)
+__global__ void __launch_bounds__(kPartThreads, KH_PART_MIN_BLOCKS)
 partition_kernel(const unsigned char* __restrict__ recs, u64 n, int k, int m, u64 nbuckets, u32 part_shift, u32 nparts,
                  u64 part_cap, u32* __restrict__ cursor, typename Slot<W>::value_t* __restrict__ grouped,
                  typename Slot<W>::value_t* table, u32* __restrict__ start_mask, u32* __restrict__ tile_starts,
@@ -365,11 +371,14 @@ warm_kernel(const char* __restrict__ base, u64 nlines) {
         asm volatile("prefetch.global.L2 [%0];" ::"l"(base + (l << 7)));
 }
 
+#ifndef KH_INS_SLOTS_MIN_BLOCKS
+#define KH_INS_SLOTS_MIN_BLOCKS 6          // latency-bound kernel: trade registers for resident warps
+#endif
 // pass 3: insert pre-converted slot values (grouped by partition, so the table traffic is L2-resident).
 // MODE 0: read the bucket, then CAS the first empty slot.  MODE 1: CAS slot 0 of the home bucket blind
 // (4 independent atomics in flight per thread) and fall back to read + CAS only when it is taken.
 template <int W, int MODE>
-__global__ void __launch_bounds__(kInsThreads)
+__global__ void __launch_bounds__(kInsThreads, KH_INS_SLOTS_MIN_BLOCKS)
 insert_slots_kernel(const typename Slot<W>::value_t* __restrict__ grouped, const u32* __restrict__ cursor,
                     u64 part_cap, u32 blocks_per_part, u32 nparts, u32 part_shift, u32 warm_ahead, int k, int m,
                     typename Slot<W>::value_t* table, u64 nbuckets, Counters* ctr) {
