@@ -36,6 +36,7 @@ WORKLOADS = {
     # name: (k, n_kmers, n_contigs, long_nodes)
     "chr14_k19": (19, 89_710_742, 860_329, 0),        # BASELINE.json configs[1]
     "chr14_k51": (51, 89_710_742, 860_329, 0),        # configs[2]
+    "chr14_k31": (31, 89_710_742, 860_329, 0),        # per-GPU share of the whole-genome shape (configs[4], K=31)
     "chr14_k51_long": (51, 89_710_742, 8_603, 1_000_000),
     "test_k19": (19, 4_514_197, 5_736, 0),            # test.txt shape
     "small_k19": (19, 977_112, 1_000, 0),             # configs[0] (CPU reference case)
@@ -360,6 +361,8 @@ def main():
     ap.add_argument("--load-factor", type=float, default=0.5)
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-e2e", action="store_true", help="skip the host-buffer leg (profiling runs)")
+    ap.add_argument("--scaling", default="strong", choices=["strong", "weak"],
+                    help="N>1 only: strong = the N=1 file split over the GPUs (default); weak = one such file per GPU (K>=31)")
     args = ap.parse_args()
     args.warmup = max(args.warmup, 3) if args.impl == "b200" else args.warmup
     workload = args.workload or "chr14_k19"      # the same file at every N (strong scaling over the sharded table)

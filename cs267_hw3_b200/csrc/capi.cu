@@ -263,7 +263,7 @@ int pack_device(kh_table* t, const void* text_dev, u64 n_lines, void* pairs_dev)
     if (n_lines == 0) return KH_OK;
     const u64 nblk = (n_lines + kPackLines - 1) / kPackLines;
     if (nblk > 0x7FFFFFFFull) return fail(t, KH_ERR_ARG, "too many lines in one pack call");
-    const size_t smem = (((size_t)kPackLines * (t->k + 4) + 15) & ~(size_t)15) + (size_t)kPackLines * t->pb;
+    const size_t smem = (((size_t)kPackLines * (t->k + 4) + 8 + 15) & ~(size_t)15) + (size_t)kPackLines * t->pb;
     pack_lines_kernel<<<(unsigned)nblk, kPackLines, smem, t->stream>>>(
         static_cast<const unsigned char*>(text_dev), n_lines, t->k, static_cast<unsigned char*>(pairs_dev), t->d_ctr);
     KH_CUDA(t, cudaGetLastError());

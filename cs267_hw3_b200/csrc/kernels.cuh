@@ -59,37 +59,46 @@ __device__ __forceinline__ void stage_out(unsigned char* g_dst, const unsigned c
 // =========================================================================================
 constexpr int kPackLines = 256;   // lines per block; 256*(K+4) is a multiple of 16 for every K
 
+// Four letters (little-endian in one 32-bit word, first letter in the low byte) -> one packed byte
+// (first letter in bits 7..6), branch-free:  code = ((c >> 1) & 3) ^ ((c >> 2) & 1)  maps A,C,G,T to
+// 0,1,2,3; the multiply gathers the four 2-bit codes.  `ok` is cleared unless all four are ACGT.
+__device__ __forceinline__ u32 pack4(u32 w, bool& ok) {
+    const u32 valid = __vcmpeq4(w, 0x41414141u) | __vcmpeq4(w, 0x43434343u) | __vcmpeq4(w, 0x47474747u) |
+                      __vcmpeq4(w, 0x54545454u);
+    ok = ok && (valid == 0xFFFFFFFFu);
+    const u32 codes = ((w >> 1) & 0x03030303u) ^ ((w >> 2) & 0x01010101u);
+    return (codes * 0x40100401u) >> 24;
+}
+// 32-bit word at an arbitrary byte offset of a 4-byte aligned shared array
+__device__ __forceinline__ u32 lds_unaligned32(const unsigned char* base, u32 off) {
+    const u32* w = reinterpret_cast<const u32*>(base) + (off >> 2);
+    return __funnelshift_r(w[0], w[1], (off & 3u) * 8u);
+}
+
 __global__ void __launch_bounds__(kPackLines)
 pack_lines_kernel(const unsigned char* __restrict__ text, u64 n_lines, int k,
                   unsigned char* __restrict__ pairs, Counters* ctr) {
     extern __shared__ __align__(16) unsigned char smem[];
     const int ll = k + 4, pl = (k + 3) >> 2, pb = pl + 2;
-    unsigned char* s_in = smem;
-    unsigned char* s_out = smem + (((u32)kPackLines * ll + 15u) & ~15u);
+    unsigned char* s_in = smem;                                   // + 8 bytes of slack for the word reads
+    unsigned char* s_out = smem + (((u32)kPackLines * ll + 8u + 15u) & ~15u);
     const u64 line0 = (u64)blockIdx.x * kPackLines;
     const u32 cnt = (u32)min((u64)kPackLines, n_lines - line0);
     stage_in(s_in, text + line0 * ll, cnt * ll);
     __syncthreads();
     if (threadIdx.x < cnt) {
-        const unsigned char* line = s_in + threadIdx.x * ll;
+        const u32 off = threadIdx.x * ll;
         unsigned char* rec = s_out + threadIdx.x * pb;
         bool ok = true;
-        for (int q = 0; q < pl; ++q) {
-            u32 v = 0;
-#pragma unroll
-            for (int j = 0; j < 4; ++j) {
-                const int idx = 4 * q + j;
-                u32 code = 0;                       // packing.hpp:85-91: the tail is padded with 'A'
-                if (idx < k) {
-                    const unsigned char c = line[idx];
-                    ok = ok && is_base(c);
-                    code = base_code_fast(c);
-                }
-                v = (v << 2) | code;
-            }
-            rec[q] = (unsigned char)v;
+        const int full = k >> 2;                                  // whole groups of four bases
+        for (int q = 0; q < full; ++q) rec[q] = (unsigned char)pack4(lds_unaligned32(s_in, off + 4 * q), ok);
+        if (k & 3) {                                              // packing.hpp:85-91: the tail is padded with 'A'
+            u32 w = lds_unaligned32(s_in, off + 4 * full);
+            const u32 keep = (1u << (8 * (k & 3))) - 1u;
+            w = (w & keep) | (0x41414141u & ~keep);
+            rec[full] = (unsigned char)pack4(w, ok);
         }
-        const unsigned char b = line[k + 1], f = line[k + 2];   // byte k is a separator nobody reads
+        const unsigned char b = s_in[off + k + 1], f = s_in[off + k + 2];   // byte k is a separator nobody reads
         ok = ok && ext_code(b) != kExtBad && ext_code(f) != kExtBad;
         rec[pl] = b;
         rec[pl + 1] = f;

@@ -423,18 +423,31 @@ def bench(args, k, n_total, c_total, longn, workload, rank, world, local_rank):
     from tools import kmergen
 
     t_gen = time.time()
-    data = kmergen.Dataset(k, n_total, c_total, seed=267, long_nodes=longn)     # every rank derives the same file
-    lo, hi = block_of_rank(n_total, world, rank)
-    n_local = hi - lo
+    weak = getattr(args, "scaling", "strong") == "weak"
+    if weak:
+        # per-GPU work fixed: every rank brings its own file of n_total k-mers (its block of a world-times larger
+        # input).  Independent files are only collision-free for long k-mers, so this mode needs K >= 31.
+        if k < 31:
+            raise ValueError("--scaling weak needs K >= 31 (independent per-rank files must not share k-mers)")
+        data = kmergen.Dataset(k, n_total, c_total, seed=267 + 1000 * rank, long_nodes=longn)
+        n_local, lo = n_total, 0
+        n_per_rank, c_per_rank = n_total, c_total
+        n_total, c_total = n_total * world, c_total * world
+        exp_buf, exp_nc = data.expected_array(1, 0)
+    else:
+        data = kmergen.Dataset(k, n_total, c_total, seed=267, long_nodes=longn)     # every rank derives the same file
+        lo, hi = block_of_rank(n_total, world, rank)
+        n_local = hi - lo
+        exp_buf, exp_nc = data.expected_array(world, rank)
     pb = kh.pair_bytes(k)
     host = kh.PinnedBuffer(max(n_local, 1) * pb)
     data.pairs_into(host.ptr, lo, n_local)
-    exp_buf, exp_nc = data.expected_array(world, rank)
     t_gen = time.time() - t_gen
 
     stream = torch.cuda.current_stream()
-    n_local_max = (n_total + world - 1) // world
-    shard = Shard(k, rank, world, n_local_max, n_total, args.load_factor, device=local_rank)
+    n_local_max = n_local if weak else (n_total + world - 1) // world
+    shard = Shard(k, rank, world, n_local_max, n_total, args.load_factor, device=local_rank,
+                  n_starts_max=int(exp_nc * 1.25) + 4096)
     shard.tab.set_stream(stream.cuda_stream)
     comm = TorchComm(shard)
     comm.connect()
@@ -493,11 +506,13 @@ def bench(args, k, n_total, c_total, longn, workload, rank, world, local_rank):
         line = {
             "metric": METRIC, "value": n_total / (ms_total * 1e-3), "unit": UNIT, "n_gpus": world,
             "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms_total, "higher_is_better": True,
-            "scaling": "strong", "vs_baseline": None, "dtype": "u64" if k <= 29 else "u128", "data": "synthetic",
+            "scaling": "weak" if weak else "strong", "vs_baseline": None, "dtype": "u64" if k <= 29 else "u128", "data": "synthetic",
             "config": {"workload": workload, "k": k, "n_kmers": n_total, "n_contigs": c_total, "load_factor": args.load_factor,
-                       "seed": 267, "sharding": f"table hash-sharded over {world} GPUs; input lines block-partitioned "
-                       "(read_kmers.hpp:55-58); one NCCL all-to-all of slot values for the inserts; walk lookups read the "
-                       "owner's table over NVLink peer mappings; pointer jumping across GPUs",
+                       "seed": 267, "per_gpu_kmers": n_local,
+                       "sharding": f"table sharded over {world} GPUs by minimizer hash; input lines block-partitioned "
+                       "(read_kmers.hpp:55-58); one NCCL all-to-all of slot values for the inserts; every GPU walks the "
+                       "k-mers it owns, chain hand-overs travel in one all-to-all and are patched in through NVLink peer "
+                       "mappings; pointer jumping and contig text across GPUs over peer mappings",
                        "timing": "CUDA events on the launching stream per step, max over ranks, mean of steps",
                        "l2": "per-GPU table and records larger than L2; table re-zeroed between steps (outside the event pair)"},
             "stages_ms": {"ms_insert_incl_all_to_all": ms_ins, "ms_traverse": ms_total - ms_ins,
