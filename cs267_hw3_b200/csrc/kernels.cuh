@@ -264,7 +264,7 @@ __global__ void __launch_bounds__(kPartThreads, KH_PART_MIN_BLOCKS)
 partition_kernel(const unsigned char* __restrict__ recs, u64 n, int k, int m, u64 nbuckets, u32 part_shift, u32 nparts,
                  u64 part_cap, u32* __restrict__ cursor, typename Slot<W>::value_t* __restrict__ grouped,
                  typename Slot<W>::value_t* table, u32* __restrict__ start_mask, u32* __restrict__ tile_starts,
-                 Counters* ctr) {
+                 typename Slot<W>::value_t* __restrict__ overflow, u32 overflow_cap, Counters* ctr) {
     typedef Slot<W> S;
     typedef typename S::value_t V;
     extern __shared__ __align__(16) unsigned char s_raw[];
@@ -350,6 +350,10 @@ partition_kernel(const unsigned char* __restrict__ recs, u64 n, int k, int m, u6
         const u64 at = (u64)s_gbase[p] + (pos - s_off[p]);
         if (at < part_cap) {
             grouped[(u64)p * part_cap + at] = s_sorted[pos];
+        } else if (overflow) {                             // chunked build: the fix-up pass inserts it after the chunks are final
+            const u32 o = atomicAdd(&ctr->n_outbox, 1u);
+            if (o < overflow_cap) overflow[o] = s_sorted[pos];
+            else atomicOr(&s_err, kErrInternal);
         } else {                                           // partition buffer full: insert right here
             const V val = s_sorted[pos];
             const u64 b = place_bucket<W>(val, k, m, nbuckets);
@@ -370,6 +374,211 @@ partition_kernel(const unsigned char* __restrict__ recs, u64 n, int k, int m, u6
         if (s_err) atomicOr(&ctr->errors, s_err);
         if (s_direct_ins) atomicAdd(&ctr->n_inserted, (u64)s_direct_ins);
         if (s_direct_dup) atomicAdd(&ctr->n_duplicates, (u64)s_direct_dup);
+    }
+}
+
+// =========================================================================================
+// K2c  chunked build: no global atomics at all
+// =========================================================================================
+// The grouped records of one partition (partition_kernel) are split once more by 64 KB table chunk
+// (subpartition_kernel); then one block per chunk builds the chunk in SHARED memory with ATOMS.CAS and
+// writes it to HBM in one coalesced sweep (build_chunks_kernel).  DRAM sees only streaming traffic
+// (7 + 8 + 8 + 8 + 8 + 16 bytes per k-mer), no random row activations.  Probing stays the table's
+// ordinary linear probing: a record whose probe sequence would leave its chunk (its home is at the very
+// end of the chunk and those buckets are full) goes to a small overflow list that is inserted afterwards
+// with the ordinary global insert -- by then every chunk is final, so "first empty slot from home" holds.
+constexpr u32 kChunkShift = 11;                       // 2048 buckets = 64 KB per chunk
+constexpr u32 kChunkBuckets = 1u << kChunkShift;
+constexpr int kSubThreads = 256;
+constexpr int kSubPerThread = 8;
+constexpr int kSubTile = kSubThreads * kSubPerThread;  // 2048 slot values per block
+
+template <int W>
+__global__ void __launch_bounds__(kSubThreads, 4)
+subpartition_kernel(const typename Slot<W>::value_t* __restrict__ grouped, const u32* __restrict__ part_cursor,
+                    u64 part_cap, u32 blocks_per_part, u32 part_shift, int k, int m, u64 nbuckets,
+                    u32 chunk_cap, u32* __restrict__ chunk_cursor, typename Slot<W>::value_t* __restrict__ fine,
+                    typename Slot<W>::value_t* __restrict__ overflow, u32 overflow_cap, Counters* ctr) {
+    typedef Slot<W> S;
+    typedef typename S::value_t V;
+    extern __shared__ __align__(16) unsigned char s_raw[];
+    const u32 nsub = 1u << (part_shift - kChunkShift);                 // chunks per partition (<= 1024)
+    u32* s_hist = reinterpret_cast<u32*>(s_raw);
+    u32* s_off = s_hist + nsub;
+    u32* s_gbase = s_off + nsub;
+    unsigned short* s_sid = reinterpret_cast<unsigned short*>(s_raw + 12 * (size_t)nsub);
+    V* s_sorted = reinterpret_cast<V*>(s_raw + ((12 * (size_t)nsub + 2 * kSubTile + 15) & ~(size_t)15));
+    __shared__ u64 s_warp[33];
+    const u32 part = blockIdx.x / blocks_per_part, jblk = blockIdx.x % blocks_per_part;
+    const u64 n = min((u64)part_cursor[part], part_cap);
+    const u64 base = (u64)jblk * kSubTile;
+    if (base >= n) return;
+    const V* __restrict__ src = grouped + (u64)part * part_cap;
+    const u64 first_chunk = (u64)part << (part_shift - kChunkShift);
+    for (u32 i = threadIdx.x; i < nsub; i += blockDim.x) s_hist[i] = 0;
+    __syncthreads();
+    V v[kSubPerThread];
+    u32 sid[kSubPerThread], rk[kSubPerThread];
+#pragma unroll
+    for (int r = 0; r < kSubPerThread; ++r) {
+        const u64 i = base + (u64)r * kSubThreads + threadIdx.x;
+        sid[r] = 0xFFFFFFFFu;
+        if (i < n) {
+            v[r] = src[i];
+            const u64 chunk = place_bucket<W>(v[r], k, m, nbuckets) >> kChunkShift;
+            sid[r] = (u32)(chunk - first_chunk) & (nsub - 1);
+            rk[r] = atomicAdd(&s_hist[sid[r]], 1u);
+        }
+    }
+    __syncthreads();
+    {
+        u32 h[4], sum = 0;
+#pragma unroll
+        for (int q = 0; q < 4; ++q) {
+            const u32 i = threadIdx.x * 4 + q;
+            h[q] = i < nsub ? s_hist[i] : 0u;
+            sum += h[q];
+        }
+        u64 total;
+        u64 run = block_exclusive_scan((u64)sum, s_warp, total);
+#pragma unroll
+        for (int q = 0; q < 4; ++q) {
+            const u32 i = threadIdx.x * 4 + q;
+            if (i < nsub) {
+                s_off[i] = (u32)run;
+                s_gbase[i] = h[q] ? atomicAdd(&chunk_cursor[first_chunk + i], h[q]) : 0u;
+            }
+            run += h[q];
+        }
+    }
+    __syncthreads();
+#pragma unroll
+    for (int r = 0; r < kSubPerThread; ++r) {
+        if (sid[r] != 0xFFFFFFFFu) {
+            const u32 pos = s_off[sid[r]] + rk[r];
+            s_sorted[pos] = v[r];
+            s_sid[pos] = (unsigned short)sid[r];
+        }
+    }
+    __syncthreads();
+    const u32 good = s_off[nsub - 1] + s_hist[nsub - 1];
+    for (u32 pos = threadIdx.x; pos < good; pos += blockDim.x) {
+        const u32 sb = s_sid[pos];
+        const u32 at = s_gbase[sb] + (pos - s_off[sb]);
+        if (at < chunk_cap) {
+            fine[(first_chunk + sb) * (u64)chunk_cap + at] = s_sorted[pos];
+        } else {                                                     // chunk buffer full: fix-up pass takes it
+            const u32 o = atomicAdd(&ctr->n_outbox, 1u);             // (n_outbox doubles as the overflow counter here)
+            if (o < overflow_cap) overflow[o] = s_sorted[pos];
+            else atomicOr(&ctr->errors, kErrInternal);
+        }
+    }
+}
+
+// one block per 64 KB chunk: build it in shared memory, write it out once
+constexpr int kBuildThreads = 512;
+constexpr int kBuildBatch = 4;          // records a thread fetches before it starts inserting (loads in flight)
+
+template <int W>
+__device__ __forceinline__ int build_insert_one(typename Slot<W>::value_t* s_tab, u32 nb, u32 b, typename Slot<W>::value_t v) {
+    typedef Slot<W> S;
+    while (b < nb) {
+#pragma unroll
+        for (int j = 0; j < S::kPerBucket; ++j) {
+            typename S::value_t cur = S::load_shared(s_tab + b * S::kPerBucket + j);
+            if (S::empty(cur)) {
+                cur = S::cas_shared(s_tab + b * S::kPerBucket + j, S::zero(), v);
+                if (S::empty(cur)) return kInsInserted;
+            }
+            if (S::same_key(cur, v)) return kInsDuplicate;
+        }
+        ++b;
+    }
+    return kInsFull;                      // the probe sequence leaves the chunk
+}
+
+template <int W>
+__global__ void __launch_bounds__(kBuildThreads)
+build_chunks_kernel(const typename Slot<W>::value_t* __restrict__ fine, const u32* __restrict__ chunk_cursor, u32 chunk_cap,
+                    typename Slot<W>::value_t* table, u64 nbuckets, int k, int m, int load_existing,
+                    typename Slot<W>::value_t* __restrict__ overflow, u32 overflow_cap, Counters* ctr) {
+    typedef Slot<W> S;
+    typedef typename S::value_t V;
+    extern __shared__ __align__(16) unsigned char s_raw[];
+    V* s_tab = reinterpret_cast<V*>(s_raw);                            // kChunkBuckets * 32 bytes
+    __shared__ u32 s_inserted, s_dups;
+    const u64 b0 = (u64)blockIdx.x << kChunkShift;
+    const u32 nb = (u32)min((u64)kChunkBuckets, nbuckets - b0);
+    const u32 nvec = nb * 2;                                           // 16-byte vectors in this chunk
+    uint4* s4 = reinterpret_cast<uint4*>(s_raw);
+    uint4* g4 = reinterpret_cast<uint4*>(table + b0 * S::kPerBucket);
+    const u32 cnt = min(chunk_cursor[blockIdx.x], chunk_cap);
+    const V* __restrict__ recs = fine + (u64)blockIdx.x * chunk_cap;
+    // first batch of records is on its way while the chunk is zeroed / loaded
+    V v[kBuildBatch];
+#pragma unroll
+    for (int r = 0; r < kBuildBatch; ++r) {
+        const u32 i = threadIdx.x + r * kBuildThreads;
+        v[r] = i < cnt ? recs[i] : S::zero();
+    }
+    if (threadIdx.x == 0) { s_inserted = 0; s_dups = 0; }
+    if (load_existing) for (u32 i = threadIdx.x; i < nvec; i += blockDim.x) s4[i] = g4[i];
+    else for (u32 i = threadIdx.x; i < nvec; i += blockDim.x) s4[i] = make_uint4(0, 0, 0, 0);
+    __syncthreads();
+    u32 inserted = 0, dups = 0;
+    for (u32 base = 0; base < cnt; base += kBuildThreads * kBuildBatch) {
+        V nxt[kBuildBatch];
+#pragma unroll
+        for (int r = 0; r < kBuildBatch; ++r) {                        // prefetch the following batch
+            const u32 i = base + kBuildThreads * kBuildBatch + threadIdx.x + r * kBuildThreads;
+            nxt[r] = i < cnt ? recs[i] : S::zero();
+        }
+#pragma unroll
+        for (int r = 0; r < kBuildBatch; ++r) {
+            if (S::empty(v[r])) continue;
+            const u32 b = (u32)(place_bucket<W>(v[r], k, m, nbuckets) - b0);      // local bucket, < nb by construction
+            const int rc = build_insert_one<W>(s_tab, nb, b, v[r]);
+            inserted += (rc == kInsInserted);
+            dups += (rc == kInsDuplicate);
+            if (rc == kInsFull) {
+                const u32 o = atomicAdd(&ctr->n_outbox, 1u);
+                if (o < overflow_cap) overflow[o] = v[r];
+                else atomicOr(&ctr->errors, kErrInternal);
+            }
+        }
+#pragma unroll
+        for (int r = 0; r < kBuildBatch; ++r) v[r] = nxt[r];
+    }
+    inserted = __reduce_add_sync(kFullMask, inserted);
+    dups = __reduce_add_sync(kFullMask, dups);
+    if (lane_id() == 0) {
+        if (inserted) atomicAdd(&s_inserted, inserted);
+        if (dups) atomicAdd(&s_dups, dups);
+    }
+    __syncthreads();
+    for (u32 i = threadIdx.x; i < nvec; i += blockDim.x) g4[i] = s4[i];
+    if (threadIdx.x == 0) {
+        if (s_inserted) atomicAdd(&ctr->n_inserted, (u64)s_inserted);
+        if (s_dups) atomicAdd(&ctr->n_duplicates, (u64)s_dups);
+    }
+}
+
+// the few records the chunk build could not place: ordinary global insert, after every chunk is final
+template <int W>
+__global__ void __launch_bounds__(256)
+insert_overflow_kernel(const typename Slot<W>::value_t* __restrict__ overflow, u32 overflow_cap, int k, int m,
+                       typename Slot<W>::value_t* table, u64 nbuckets, Counters* ctr) {
+    typedef Slot<W> S;
+    const u32 n = min(ctr->n_outbox, overflow_cap);
+    for (u32 i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) {
+        const typename S::value_t v = overflow[i];
+        const u64 b = place_bucket<W>(v, k, m, nbuckets);
+        u64 q[4];
+        load256_cg(table + b * S::kPerBucket, q);
+        const int rc = insert_one<W>(table, nbuckets, b, v, q);
+        if (rc == kInsInserted) atomicAdd(&ctr->n_inserted, 1ull);
+        else if (rc == kInsDuplicate) atomicAdd(&ctr->n_duplicates, 1ull);
+        else atomicOr(&ctr->errors, kErrTableFull);
     }
 }
 

@@ -151,6 +151,10 @@ template <> struct Slot<1> {
         return atomicCAS(addr, expect, val);
     }
     static __device__ __forceinline__ value_t load_one_nc(const value_t* p) { return __ldg(p); }
+    static __device__ __forceinline__ value_t cas_shared(value_t* addr, value_t expect, value_t val) {
+        return atomicCAS(addr, expect, val);        // ATOMS.CAS.64
+    }
+    static __device__ __forceinline__ value_t load_shared(const value_t* addr) { return *reinterpret_cast<const volatile value_t*>(addr); }
 };
 
 template <> struct Slot<2> {
@@ -233,6 +237,19 @@ template <> struct Slot<2> {
     static __device__ __forceinline__ value_t load_one_nc(const value_t* p) {
         const uint4 r = load128_stream(reinterpret_cast<const uint4*>(p));
         return u128{(u64)r.x | ((u64)r.y << 32), (u64)r.z | ((u64)r.w << 32)};
+    }
+    static __device__ __forceinline__ value_t cas_shared(value_t* addr, value_t expect, value_t val) {   // ATOMS.CAS.128
+        u128 old;
+        const unsigned saddr = (unsigned)__cvta_generic_to_shared(addr);
+        asm volatile("{\n\t.reg .b128 c, v, o;\n\tmov.b128 c, {%2, %3};\n\tmov.b128 v, {%4, %5};\n\t"
+                     "atom.shared.cas.b128 o, [%6], c, v;\n\tmov.b128 {%0, %1}, o;\n\t}"
+                     : "=l"(old.lo), "=l"(old.hi)
+                     : "l"(expect.lo), "l"(expect.hi), "l"(val.lo), "l"(val.hi), "r"(saddr) : "memory");
+        return old;
+    }
+    static __device__ __forceinline__ value_t load_shared(const value_t* addr) {
+        const volatile u64* p = reinterpret_cast<const volatile u64*>(addr);
+        return u128{p[0], p[1]};
     }
 };
 

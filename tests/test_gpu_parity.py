@@ -140,6 +140,32 @@ def test_insert_in_chunks_keeps_start_order(kh):
     assert out == d.expected()[0]
 
 
+@pytest.mark.parametrize("k,lf,chunks", [(19, 0.5, 1), (19, 0.5, 3), (19, 0.9, 1), (19, 0.97, 2), (51, 0.5, 1), (51, 0.8, 3), (31, 0.6, 2)])
+def test_chunked_shared_memory_build(kh, monkeypatch, k, lf, chunks):
+    """Large batches are built chunk by chunk in shared memory (no global atomics); batches after the first
+    load the existing chunk back in.  KH_PARTITION=1 forces the partitioned paths on a small table; KH_BUILD=0 is
+    the atomic insert_slots path -- all must give the reference's bytes."""
+    d = kmergen.Dataset(k, 300000, 900, seed=int(lf * 100) + k)
+    want = d.expected()[0]
+    monkeypatch.setenv("KH_PARTITION", "1")
+    for build in ("1", "0"):
+        monkeypatch.setenv("KH_BUILD", build)
+        out, _, nodes, st = _assemble_text(kh, d.text(), k, load_factor=lf, chunks=chunks)
+        assert out == want and nodes == d.n
+        assert st["n_inserted"] == d.n and st["n_duplicates"] == 0
+
+
+def test_chunked_build_counts_duplicates(kh, monkeypatch):
+    monkeypatch.setenv("KH_PARTITION", "1")
+    d = kmergen.Dataset(19, 200000, 300, seed=44)
+    pairs = d.pairs()
+    with kh.KmerHashTable(19, 400000) as tab:
+        tab.insert_pairs(pairs)
+        tab.insert_pairs(pairs[:150000])               # a second large batch: every record is already there
+        st = tab.stats()
+        assert st["n_inserted"] == 200000 and st["n_duplicates"] == 150000
+
+
 def test_insert_lines_path(kh):
     d = kmergen.Dataset(31, 50000, 300, seed=78)
     out, *_ = _assemble_text(kh, d.text(), 31, via="lines")
