@@ -53,6 +53,24 @@ def measured_peak_gbs() -> tuple[float, str]:
         return 6650.0, "fallback (B200_PROFILING.md)"
 
 
+def ncu_traffic_bytes(kernel_substr: str):
+    """DRAM bytes (read + write) per launch of a kernel from the committed ncu --set full capture
+    (profiles/r01_final_ncu_full_summary.csv, chr14_k19 workload); None if the file or the kernel is missing."""
+    import csv
+    p = os.path.join(ROOT, "profiles", "r01_final_ncu_full_summary.csv")
+    try:
+        rows = list(csv.reader(open(p)))
+        h, units = rows[0], rows[1]
+        ir, iw, ik = h.index("dram__bytes_read.sum"), h.index("dram__bytes_write.sum"), h.index("Kernel Name")
+        scale = {"Gbyte": 1e9, "Mbyte": 1e6, "Kbyte": 1e3, "byte": 1.0}
+        for r in rows[2:]:
+            if kernel_substr in r[ik]:
+                return float(r[ir]) * scale.get(units[ir], 1e9) + float(r[iw]) * scale.get(units[iw], 1e9)
+    except Exception:
+        pass
+    return None
+
+
 def alg_bytes_per_kmer(k: int) -> dict:
     pb = (k + 3) // 4 + 2
     # SURVEY.md 8(d): record read + insert sector read+write-back + successor sector read + output byte
@@ -72,7 +90,7 @@ class ClockSampler:
     def start(self):
         try:
             self.proc = subprocess.Popen(["nvidia-smi", f"--id={self.index}", f"--query-gpu={self.Q}",
-                                          "--format=csv,noheader,nounits", "-lms", "100"],
+                                          "--format=csv,noheader,nounits", "-lms", "20"],
                                          stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
             self.t = threading.Thread(target=lambda: self.lines.extend(self.proc.stdout), daemon=True)
             self.t.start()
@@ -242,11 +260,10 @@ def run_b200_arm(args, k: int, workload: str) -> dict | None:
         e1.record(stream)
         return e0, e1, (buf, offs, nodes)
 
+    sampler = ClockSampler(local_rank)      # sampled over warm-up + timed steps (the timed loop alone is < 0.1 s)
+    sampler.start()
     for _ in range(args.warmup):
         step_resident()
-    torch.cuda.synchronize()
-    sampler = ClockSampler(local_rank)
-    sampler.start()
     torch.cuda.synchronize()
     wall0 = time.perf_counter()
     evs, stage = [], {"ms_insert": [], "ms_walk": [], "ms_rank": [], "ms_emit": [], "ms_clear": []}
@@ -305,14 +322,14 @@ def run_b200_arm(args, k: int, workload: str) -> dict | None:
     peak, peak_src = measured_peak_gbs()
     alg = alg_bytes_per_kmer(k)
     m_ins, m_walk = float(np.mean(stage["ms_insert"])), float(np.mean(stage["ms_walk"]))
-    if m_ins >= m_walk:
-        dom, dom_ms, dom_bytes = "insert stage (partition_kernel + insert_slots_kernel)", m_ins, n * (alg["record"] + alg["insert"])
-    else:
-        dom, dom_ms, dom_bytes = "walk_kernel", m_walk, n * (alg["lookup"] + alg["output"])
+    # The insert stage is three kernels (partition, subpartition, build_chunks: ~0.8/0.75/1.2 ms), so the single
+    # dominant kernel of the step is walk_kernel; its duration is the CUDA-event time of the walk stage.
+    dom, dom_ms, dom_bytes = "walk_kernel", m_walk, n * (alg["lookup"] + alg["output"])
+    traffic = ncu_traffic_bytes("walk_kernel") if workload == "chr14_k19" and not args.n else None
     achieved = dom_bytes / (dom_ms * 1e-3) / 1e9
     path_gbs = n * alg["total"] / (ms_per_step * 1e-3) / 1e9
     try:
-        r_rand = kh.random_sector_rate(local_rank, 4 << 30, 1 << 28)
+        r_rand = kh.random_sector_rate(local_rank, 1434 << 20, 1 << 28)     # footprint = this workload's table
     except Exception:
         r_rand = None
     line = {
@@ -328,7 +345,16 @@ def run_b200_arm(args, k: int, workload: str) -> dict | None:
         "assembly_time_s": ms_per_step * 1e-3,
         "wall_s_timed_loop": wall, "gen_s": t_gen, "verified": verified,
         "roofline": {"bound": "hbm", "kernel": dom, "achieved": achieved, "peak": peak, "unit": "GB/s",
-                     "frac": achieved / peak, "traffic": None, "peak_source": peak_src,
+                     "frac": achieved / peak, "traffic": traffic,
+                     "traffic_source": "dram__bytes_read.sum + dram__bytes_write.sum, one ncu --set full capture "
+                                       "(profiles/r01_final_ncu_full_summary.csv)" if traffic else None,
+                     "peak_source": peak_src,
+                     "insert_stage": {"kernels": "partition_kernel + subpartition_kernel + build_chunks_kernel",
+                                      "ms": m_ins, "achieved": n * (alg["record"] + alg["insert"]) / (m_ins * 1e-3) / 1e9,
+                                      "frac": n * (alg["record"] + alg["insert"]) / (m_ins * 1e-3) / 1e9 / peak},
+                     "random_access_ceiling": {"lookups_per_s": n / (m_walk * 1e-3),
+                                               "measured_random_32B_reads_per_s": r_rand,
+                                               "frac": (n / (m_walk * 1e-3)) / r_rand if r_rand else None},
                      "alg_bytes_per_kmer": alg,
                      "path": {"achieved": path_gbs, "frac": path_gbs / peak,
                               "note": "N x B_alg / t(insert+traverse), SURVEY.md 8(d)"},
@@ -338,7 +364,7 @@ def run_b200_arm(args, k: int, workload: str) -> dict | None:
         "e2e": {"value": n / (e2e_ms_mean * 1e-3), "unit": UNIT, "ms_per_step": e2e_ms_mean,
                 "h2d_bytes_per_step": n * pb, "d2h_bytes_per_step": int(contig_bytes + 8 * (n_contigs + 1))},
         "pack_lines": pack,
-        "gpu_launches": 15 * args.steps,
+        "gpu_launches": 16 * args.steps,
         "clocks": clocks,
     }
     tab.close()

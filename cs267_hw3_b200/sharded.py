@@ -468,14 +468,14 @@ def bench(args, k, n_total, c_total, longn, workload, rank, world, local_rank):
         e2.record(stream)
         return e0, e1, e2, rounds
 
+    from bench import ClockSampler
+    sampler = ClockSampler(local_rank)        # warm-up + timed steps
+    sampler.start()
     for _ in range(args.warmup):
         step()
     phase_ms.clear()
     dist.barrier()
     torch.cuda.synchronize()
-    from bench import ClockSampler
-    sampler = ClockSampler(local_rank)
-    sampler.start()
     evs = []
     wall0 = time.perf_counter()
     for _ in range(args.steps):
@@ -492,6 +492,27 @@ def bench(args, k, n_total, c_total, longn, workload, rank, world, local_rank):
 
     got, nc, nn = shard.result_host()
     ok = bool(nc == exp_nc and got.size == exp_buf.size and np.array_equal(got, exp_buf))
+
+    # end to end: this rank's records start in pinned HOST memory, its contigs end in host memory
+    host_t = torch.from_numpy(host.array)
+    e2e_ms = []
+    for i in range(3):
+        shard.tab.clear()
+        comm.barrier()
+        a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        a.record(stream)
+        dev.copy_(host_t, non_blocking=True)                      # H2D of the step's input
+        sharded_insert(comm, [(dev.data_ptr(), n_local)])
+        sharded_assemble(comm)
+        out_host, _, _ = shard.result_host()                        # D2H of the step's result
+        b.record(stream)
+        torch.cuda.synchronize()
+        if i:
+            e2e_ms.append(a.elapsed_time(b))
+    te = torch.tensor([float(np.mean(e2e_ms))], device="cuda", dtype=torch.float64)
+    dist.all_reduce(te, op=dist.ReduceOp.MAX)
+    e2e_ms_max = float(te.item())
+    ok = ok and bool(np.array_equal(out_host, exp_buf))
     tot = torch.tensor([float(nn), 1.0 if ok else 0.0, float(got.size)], device="cuda", dtype=torch.float64)
     dist.all_reduce(tot, op=dist.ReduceOp.SUM)
     nodes_all, ok_all, bytes_all = tot.tolist()
@@ -525,8 +546,9 @@ def bench(args, k, n_total, c_total, longn, workload, rank, world, local_rank):
                          "nvlink_bytes_per_step": int(n_total * (world - 1) / world * (sb + 32)),
                          "nvlink_note": "(P-1)/P of the slot values cross in the all-to-all and (P-1)/P of the successor "
                                         "lookups read a 32-byte bucket from a peer"},
-            "e2e": {"value": None, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0,
-                    "note": "host-buffer leg is measured at N=1 only"},
+            "e2e": {"value": n_total / (e2e_ms_max * 1e-3), "unit": UNIT, "ms_per_step": e2e_ms_max,
+                    "h2d_bytes_per_step": int(n_total * pb), "d2h_bytes_per_step": int(bytes_all),
+                    "note": "each rank copies its block of records from pinned host memory and its contigs back"},
             "gpu_launches": (12 + evs[-1][3]) * args.steps,
             "clocks": clocks,
         }
