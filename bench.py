@@ -163,7 +163,8 @@ def run_reference_arm(args, k: int, workload: str) -> dict:
     return {
         "impl": "reference", "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": args.gpus,
         "steps": args.steps, "warmup": args.warmup, "ms_per_step": t * 1e3, "higher_is_better": True,
-        "scaling": "weak", "vs_baseline": None, "dtype": "u8 (std::string keys)", "data": "synthetic",
+        "scaling": "weak" if args.gpus == 1 else "strong", "vs_baseline": None, "dtype": "u8 (std::string keys)",
+        "data": "synthetic",
         "config": {"workload": workload, "k": k, "sample_kmers": n_s, "insert_s": float(np.mean(ins)), "total_s": t},
         "cpu_baseline": {"value": value, "unit": UNIT, "cores": 1, "kind": "reference", "sample": sample},
         "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},

@@ -32,7 +32,7 @@ ABI_SYMBOLS = [
     "kh_slot_bytes", "kh_shard_init", "kh_shard_export", "kh_shard_connect", "kh_shard_connect_local",
     "kh_shard_owner_partition", "kh_insert_slots_device", "kh_shard_walk", "kh_shard_resolve", "kh_shard_phase",
     "kh_shard_result",
-    "kh_device_alloc", "kh_device_free", "kh_copy_to_host", "kh_copy_device",
+    "kh_device_alloc", "kh_device_alloc_on", "kh_device_free", "kh_copy_to_host", "kh_copy_device",
 ]
 
 

@@ -1247,6 +1247,11 @@ int kh_device_alloc(void** ptr, uint64_t bytes) {
     if (cudaMalloc(ptr, bytes ? bytes : 1) != cudaSuccess) { cudaGetLastError(); *ptr = nullptr; return KH_ERR_NOMEM; }
     return KH_OK;
 }
+int kh_device_alloc_on(int device, void** ptr, uint64_t bytes) {
+    if (!ptr) return KH_ERR_ARG;
+    if (cudaSetDevice(device) != cudaSuccess) { cudaGetLastError(); *ptr = nullptr; return KH_ERR_CUDA; }
+    return kh_device_alloc(ptr, bytes);
+}
 int kh_device_free(void* ptr) {
     if (ptr && cudaFree(ptr) != cudaSuccess) { cudaGetLastError(); return KH_ERR_CUDA; }
     return KH_OK;

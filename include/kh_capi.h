@@ -174,7 +174,8 @@ int kh_shard_result(kh_table* t, const char** contigs_dev, const uint64_t** offs
                     uint64_t* n_contigs, uint64_t* contig_bytes, uint64_t* n_nodes);
 
 /* small device-memory helpers for hosts without their own CUDA binding */
-int kh_device_alloc(void** ptr, uint64_t bytes);
+int kh_device_alloc(void** ptr, uint64_t bytes);                 /* on the current device */
+int kh_device_alloc_on(int device, void** ptr, uint64_t bytes);
 int kh_device_free(void* ptr);
 int kh_copy_to_host(kh_table* t, void* dst_host, const void* src_dev, uint64_t bytes);
 int kh_copy_device(kh_table* t, void* dst_dev, const void* src_dev, uint64_t bytes);

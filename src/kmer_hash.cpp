@@ -8,6 +8,10 @@
 // "rank 0 of 1"; the GPU and the load factor come from the environment (KH_DEVICE,
 // KH_LOAD_FACTOR) because the positional interface has no room for them.
 //
+// KH_RANKS=P (1..8) runs the reference's P-rank flow in this one process: rank r parses lines
+// [ceil(n/P)*r, ...) (read_kmers.hpp:55-58), lives on GPU r % (visible GPUs), and writes <prefix>_<r>.dat
+// (kh/sharded_host.hpp); the printed line is rank 0's, as BUtil::print does.
+//
 // Stage mapping
 //   read_kmers (untimed, kmer_hash.cpp:122)      -> file read + K1 pack on the GPU (kh_pack_lines)
 //   initialize_kmers (timed, :131)               -> kh_insert_pairs   (records start in HOST memory,
@@ -23,6 +27,7 @@
 
 #include "butil.hpp"
 #include "hash_map.hpp"
+#include "kh/sharded_host.hpp"
 #include "kmer_t.hpp"
 #include "read_kmers.hpp"
 
@@ -79,6 +84,69 @@ int main(int argc, char** argv) {
     if (run_type == "verbose")
         BUtil::print("Initializing hash table of size %lu for %lu kmers.\n", hash_table_size, n_kmers);
 
+    int n_ranks = 1;
+    if (const char* e = std::getenv("KH_RANKS")) n_ranks = std::atoi(e);
+    using clock = std::chrono::high_resolution_clock;
+
+    if (n_ranks > 1) {
+        double lf = 0.5;
+        if (const char* e = std::getenv("KH_LOAD_FACTOR")) lf = std::atof(e);
+        const size_t per_rank = (n_kmers + n_ranks - 1) / n_ranks;
+        kh_sharded::Cluster cluster(KMER_LEN, n_ranks, per_rank, n_kmers, lf);
+        // read_kmers: every rank's block of lines, packed on its GPU (untimed, like the reference)
+        const size_t line_len = KMER_LEN + 4;
+        FILE* f = fopen(kmer_fname.c_str(), "r");
+        if (f == nullptr) throw std::runtime_error("read_kmers: could not open " + kmer_fname);
+        std::vector<std::vector<kmer_pair>> blocks(n_ranks);
+        std::vector<char> text;
+        for (int r = 0; r < n_ranks; ++r) {
+            const size_t first = std::min(n_kmers, per_rank * (size_t)r), count = std::min(per_rank, n_kmers - first);
+            text.resize(line_len * count);
+            if (fread(text.data(), 1, text.size(), f) != text.size()) throw std::runtime_error("read_kmers: short read");
+            blocks[r].resize(count);
+            must(kh_pack_lines(cluster.table(r), text.data(), count, blocks[r].data()), cluster.table(r), "pack_lines");
+        }
+        fclose(f);
+        if (run_type == "verbose") BUtil::print("Finished reading kmers.\n");
+
+        const auto start_time = clock::now();
+        std::vector<void*> dev(n_ranks, nullptr);
+        std::vector<const void*> cdev(n_ranks);
+        std::vector<uint64_t> counts(n_ranks);
+        for (int r = 0; r < n_ranks; ++r) {
+            counts[r] = blocks[r].size();
+            must(kh_device_alloc_on(cluster.device(r), &dev[r], std::max<size_t>(1, counts[r] * sizeof(kmer_pair))), cluster.table(r), "alloc");
+            must(kh_copy_device(cluster.table(r), dev[r], blocks[r].data(), counts[r] * sizeof(kmer_pair)), cluster.table(r), "H2D");
+            cdev[r] = dev[r];
+        }
+        cluster.insert(cdev, counts);                              // initialize_kmers
+        const auto insert_time = clock::now();
+        std::vector<kh_sharded::RankOutput> outs = cluster.assemble();   // assemble_contigs
+        const auto end_time = clock::now();
+        for (void* p : dev) kh_device_free(p);
+
+        const double insert_duration = std::chrono::duration<double>(insert_time - start_time).count();
+        const double assembly_duration = std::chrono::duration<double>(end_time - insert_time).count();
+        const double total_duration = std::chrono::duration<double>(end_time - start_time).count();
+        if (run_type != "test") {
+            BUtil::print("Finished inserting in %lf sec\n", insert_duration);
+            BUtil::print("Assembled in %lf total\n", total_duration);
+        } else {
+            for (int r = 0; r < n_ranks; ++r) {
+                const std::string out_name = test_prefix + "_" + std::to_string(r) + ".dat";
+                FILE* out = fopen(out_name.c_str(), "w");
+                if (out == nullptr) throw std::runtime_error("output_results: could not open " + out_name);
+                if (!outs[r].text.empty() && fwrite(outs[r].text.data(), 1, outs[r].text.size(), out) != outs[r].text.size())
+                    throw std::runtime_error("output_results: short write to " + out_name);
+                fclose(out);
+            }
+            BUtil::print("Rank %d reconstructed %d contigs with %d nodes from %d start nodes. "
+                         "(%lf read, %lf insert, %lf total)\n",
+                         0, (int)outs[0].n_contigs, (int)outs[0].n_nodes, 0, assembly_duration, insert_duration, total_duration);
+        }
+        return 0;
+    }
+
     DistributedHashMap hashmap(hash_table_size, rank_id, 1);
     kh_table* t = hashmap.handle();
 
@@ -86,7 +154,6 @@ int main(int argc, char** argv) {
     if (run_type == "verbose") BUtil::print("Finished reading kmers.\n");
     must(kh_sync(t), t, "sync");
 
-    using clock = std::chrono::high_resolution_clock;
     const auto start_time = clock::now();
     hashmap.insert_all(kmers, n_kmers);                        // initialize_kmers
     hashmap.process_requests();

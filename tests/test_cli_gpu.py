@@ -64,3 +64,22 @@ def test_cli_missing_kmer_aborts_like_the_reference(bins, tmp_path):
     inp.write_bytes(b"ACGTACGTACGTACGTACG FC\n")
     r = subprocess.run([bins[19], str(inp), "test"], cwd=tmp_path, capture_output=True, text=True)
     assert r.returncode == -6 and "Error: k-mer not found in Distributed HashMap." in r.stderr   # kmer_hash.cpp:47-49
+
+
+@pytest.mark.parametrize("k,ranks", [(19, 2), (19, 5), (51, 3), (31, 8)])
+def test_cli_multi_rank_writes_the_reference_per_rank_files(bins, tmp_path, k, ranks):
+    """KH_RANKS=P: rank r's file holds the contigs whose start line lies in its block of the input, in input order
+    (kmer_hash.cpp:27-31,64-67; read_kmers.hpp:55-58) -- and check.sh accepts the concatenation."""
+    d = kmergen.Dataset(k, 150000, 700, seed=31 + ranks)
+    inp = tmp_path / "synth.txt"
+    d.text().tofile(inp)
+    (tmp_path / "synth_solution.txt").write_bytes(d.solution())
+    env = dict(os.environ, KH_RANKS=str(ranks))
+    r = subprocess.run([bins[k], str(inp), "test", "mr"], cwd=tmp_path, capture_output=True, text=True, env=env)
+    assert r.returncode == 0, r.stdout + r.stderr
+    for rank in range(ranks):
+        assert (tmp_path / f"mr_{rank}.dat").read_bytes() == d.expected(ranks, rank)[0]
+    n0 = d.expected(ranks, 0)[1]
+    assert re.search(rf"Rank 0 reconstructed {n0} contigs with \d+ nodes from 0 start nodes\.", r.stdout)
+    r = subprocess.run([os.path.join(ROOT, "tools", "check.sh"), str(inp)], cwd=tmp_path, capture_output=True, text=True, env=env)
+    assert r.returncode == 0 and f"PASSED: {inp}" in r.stdout, r.stdout + r.stderr

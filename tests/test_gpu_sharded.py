@@ -114,3 +114,69 @@ def test_owner_function_mirror_matches_gpu():
         assert [owners.count(w) for w in range(world)] == counts
         L.kh_device_free(p)
         s.close()
+
+
+def _run_raw(k, pairs, world, n_total):
+    """insert + assemble given explicit records; returns per-rank outputs or raises ShardedError."""
+    import cs267_hw3_b200 as kh
+    from cs267_hw3_b200 import sharded as sh
+
+    n = pairs.shape[0]
+    shards = [sh.Shard(k, r, world, (n + world - 1) // world, n_total, 0.5, device=0) for r in range(world)]
+    comm = sh.LocalComm(shards)
+    comm.connect()
+    L = kh.lib()
+    blocks, bufs = [], []
+    try:
+        for r, s in enumerate(shards):
+            lo, hi = sh.block_of_rank(n, world, r)
+            p = C.c_void_p()
+            assert L.kh_device_alloc(C.byref(p), max(1, (hi - lo) * pairs.shape[1])) == 0
+            blk = np.ascontiguousarray(pairs[lo:hi])
+            s.tab._check(L.kh_copy_device(s.tab._h, p, blk.ctypes.data, blk.nbytes))
+            s.tab.sync()
+            blocks.append((p.value, hi - lo))
+            bufs.append(p)
+        sh.sharded_insert(comm, blocks)
+        sh.sharded_assemble(comm)
+        return [s.result_host() for s in shards]
+    finally:
+        comm.close()
+        for p in bufs:
+            L.kh_device_free(p)
+        for s in shards:
+            s.close()
+
+
+@pytest.mark.parametrize("world", [1, 4])
+def test_sharded_missing_successor_is_reported(world):
+    # kmer_hash.cpp:47-49 -- drop one interior k-mer: the chain through it cannot be completed
+    from cs267_hw3_b200 import sharded as sh
+    k = 19
+    d = kmergen.Dataset(k, 20000, 40, seed=9)
+    pairs = d.pairs()
+    pl = (k + 3) // 4
+    interior = np.where((pairs[:, pl] != ord("F")) & (pairs[:, pl + 1] != ord("F")))[0]
+    broken = np.delete(pairs, interior[7], axis=0)
+    with pytest.raises(sh.ShardedError) as e:
+        _run_raw(k, broken, world, 20000)
+    assert e.value.bits & 1 and "k-mer not found in Distributed HashMap" in str(e.value)
+
+
+def test_sharded_needs_truthful_backward_extensions():
+    """The migrating walk finds a shard's walker starts from the backward extensions (kmer_t.hpp:55-57).  The
+    reference never reads them except for 'F'; files that lie about them are refused, not mis-assembled."""
+    from cs267_hw3_b200 import sharded as sh
+    k = 19
+    d = kmergen.Dataset(k, 30000, 60, seed=10)
+    pairs = d.pairs().copy()
+    pl = (k + 3) // 4
+    rot = {ord("A"): ord("C"), ord("C"): ord("G"), ord("G"): ord("T"), ord("T"): ord("A")}
+    for i in range(pairs.shape[0]):
+        if pairs[i, pl] != ord("F"):
+            pairs[i, pl] = rot[int(pairs[i, pl])]
+    with pytest.raises(sh.ShardedError) as e:
+        _run_raw(k, pairs, 4, 30000)
+    assert e.value.bits & 8
+    outs = _run_raw(k, pairs, 1, 30000)           # one rank: nothing crosses, output as the reference's
+    assert outs[0][0].tobytes() == d.expected()[0]
