@@ -48,6 +48,7 @@ struct kh_table {
     int build_mode = 1;               // KH_BUILD: 1 = shared-memory chunk build for large batches, 0 = atomic insert_slots
     bool table_dirty = false;         // something was inserted since create/clear
     bool chunk_attr_set = false;
+    int debug_cap_pct = 100;          // KH_DEBUG_CAP_PCT: scale the grouping buffers' capacities (tests force the overflow paths)
     int partition_mode = -1;          // -1 auto, 0 never, 1 always (KH_PARTITION)
     u64 part_bytes = 16ull << 20;     // table bytes per partition (KH_PART_MB)
     bool part_attr_set = false;
@@ -195,7 +196,7 @@ int insert_device_impl(kh_table* t, const unsigned char* recs, u64 n, bool recor
         // a partition's expected share of n plus slack (supermers move as a unit, so the spread is a few times
         // the binomial sigma), rounded to whole insert tiles; overflow falls back to a direct insert
         const double share = (double)n * (double)std::min<u64>(t->nbuckets, 1ull << part_shift) / (double)t->nbuckets;
-        part_cap = (u64)(share + 24.0 * std::sqrt(share + 1.0) + 64.0);
+        part_cap = (u64)(share + 24.0 * std::sqrt(share + 1.0) + 64.0) * t->debug_cap_pct / 100;
         part_cap = (part_cap + kInsTile - 1) / kInsTile * kInsTile;
         bpp = (u32)(part_cap / kInsTile);
         KH_TRY(ensure(t, t->part_cursor, kMaxParts * sizeof(u32)));
@@ -217,13 +218,13 @@ int insert_device_impl(kh_table* t, const unsigned char* recs, u64 n, bool recor
         if (part_shift - kChunkShift > 10) return fail(t, KH_ERR_ARG, "table too large for the chunked build");
         nparts = (u32)(((t->nbuckets - 1) >> part_shift) + 1);
         const double share = (double)n * (double)std::min<u64>(t->nbuckets, 1ull << part_shift) / (double)t->nbuckets;
-        part_cap = (u64)(share + 24.0 * std::sqrt(share + 1.0) + 64.0);
+        part_cap = (u64)(share + 24.0 * std::sqrt(share + 1.0) + 64.0) * t->debug_cap_pct / 100;
         part_cap = (part_cap + kInsTile - 1) / kInsTile * kInsTile;
         nchunks = (t->nbuckets + kChunkBuckets - 1) >> kChunkShift;
         const double share2 = (double)n * (double)std::min<u64>(t->nbuckets, kChunkBuckets) / (double)t->nbuckets;
-        chunk_cap = (u32)(share2 + 24.0 * std::sqrt(share2 + 1.0) + 32.0);
-        chunk_cap = (chunk_cap + 3u) & ~3u;
-        overflow_cap = (u32)std::min<u64>(0x7FFFFFFFull, n / 32 + 65536);
+        chunk_cap = (u32)((u64)(share2 + 24.0 * std::sqrt(share2 + 1.0) + 32.0) * t->debug_cap_pct / 100);
+        chunk_cap = std::max(4u, (chunk_cap + 3u) & ~3u);
+        overflow_cap = (u32)std::min<u64>(0x7FFFFFFFull, t->debug_cap_pct < 100 ? n + 65536 : n / 32 + 65536);
         bpp2 = (u32)((part_cap + kSubTile - 1) / kSubTile);
         const u32 nsub = 1u << (part_shift - kChunkShift);
         sub_smem = ((12 * (size_t)nsub + 2 * kSubTile + 15) & ~(size_t)15) + (size_t)kSubTile * sizeof(V);
@@ -809,6 +810,7 @@ int kh_create(int k, uint64_t n_expected, double load_factor, int device, kh_tab
     // measured: the shared-memory build wins for 64-bit slots (2.85 vs 3.03 ms) and loses for 128-bit slots
     // (4.6 vs 4.1 ms: twice the bytes through the two grouping passes), so it is the default only for K <= 29
     t->build_mode = env_int("KH_BUILD", t->W == 1 ? 1 : 0);
+    t->debug_cap_pct = std::max(1, env_int("KH_DEBUG_CAP_PCT", 100));
     t->ins_mode = env_int("KH_INS_MODE", 1);
     t->warm_ahead = env_int("KH_WARM_AHEAD", 1);
     v = env_int("KH_PART_MB", 0);

@@ -25,6 +25,10 @@ namespace kh {
 constexpr int kMaxRanks = 8;
 constexpr u32 kRankShift = 28;
 constexpr u32 kLocalMask = (1u << kRankShift) - 1u;
+// pointer jumping across GPUs: a link whose pointer already is its contig's tail is flagged in the top bit of the
+// distance word, so later rounds do not pay a remote read for it
+constexpr u32 kLinkFinalBit = 0x80000000u;
+constexpr u32 kLinkDistMask = 0x7FFFFFFFu;
 
 struct Peers {
     const void* table[kMaxRanks];
@@ -370,9 +374,10 @@ contig_lengths_sharded_kernel(const Peers pe, const u64* link, u32 n_split, u32 
         const u32 pc = (u32)(lc >> 32);
         u32 tail_gid = ((u32)pe.rank << kRankShift) | (u32)(n_split + c), pre = 0;
         bool ok = true;
-        if (pc != kLinkTail) {
-            tail_gid = pc; pre = (u32)lc;
-            ok = pc < kLinkClaimed && (u32)(__ldcg(peer_link(pe, pc)) >> 32) == kLinkTail;
+        if (pc != kLinkTail && pc != kLinkClaimed) {
+            tail_gid = pc; pre = (u32)lc & kLinkDistMask;
+            const u32 tp = pc < kLinkFirstMarker ? (u32)(__ldcg(peer_link(pe, pc)) >> 32) : 0u;
+            ok = tp == kLinkTail || tp == kLinkClaimed;       // another rank may already have claimed its own tails
         }
         if (!ok) {
             atomicOr(&ctr->errors, kErrCycle);
@@ -394,7 +399,7 @@ claim_tails_sharded_kernel(const Peers pe, const u64* link, u32 n_split, u32 n_s
     for (u64 c = (u64)blockIdx.x * blockDim.x + threadIdx.x; c < n_starts; c += (u64)gridDim.x * blockDim.x) {
         if (contig_len[c] == 0) continue;
         const u32 pc = (u32)(__ldcg(link + n_split + c) >> 32);
-        const u32 tail_gid = (pc == kLinkTail) ? (((u32)pe.rank << kRankShift) | (u32)(n_split + c)) : pc;
+        const u32 tail_gid = (pc == kLinkTail || pc == kLinkClaimed) ? (((u32)pe.rank << kRankShift) | (u32)(n_split + c)) : pc;
         const u64 want = (u64)kLinkTail << 32;
         const u64 old = atomicCAS(peer_link(pe, tail_gid), want,
                                   ((u64)kLinkClaimed << 32) | (((u32)pe.rank << kRankShift) | (u32)c));
@@ -428,8 +433,9 @@ emit_segments_sharded_kernel(const Peers pe, const u64* __restrict__ link, const
                 const u32 pre = pe.contig_pre[r][c];
                 u32 pos = pre;
                 if (!is_tail) {
-                    if ((u32)li > pre) { atomicOr(&ctr->errors, kErrConverge); ok = false; }
-                    else pos = pre - (u32)li;
+                    const u32 dist = (u32)li & kLinkDistMask;
+                    if (dist > pre) { atomicOr(&ctr->errors, kErrConverge); ok = false; }
+                    else pos = pre - dist;
                 }
                 if (ok) {
                     const u64 off = pe.contig_off[r][c] + (u64)k + pos;
@@ -867,16 +873,21 @@ rank_round_mig_kernel(const Peers pe, u64* link, MigLayout lay, u32 n_starts, Co
     for (u64 i = (u64)blockIdx.x * blockDim.x + threadIdx.x; i < end; i += (u64)gridDim.x * blockDim.x) {
         if (!mig_live_id((u32)i, lay, n_boundary, next_seg, n_starts)) continue;
         const u64 li = __ldcg(link + i);
-        const u32 pi = (u32)(li >> 32);
+        const u32 pi = (u32)(li >> 32), si = (u32)li;
         if (pi >= kLinkFirstMarker) {
             if (pi == kLinkPending) atomicOr(&ctr->errors, kErrInternal);     // a link nobody resolved
             continue;
         }
+        if (si & kLinkFinalBit) continue;                     // already points at its tail: no remote read
         const u64 lp = __ldcg(peer_link(pe, pi));
-        const u32 pp = (u32)(lp >> 32);
-        if (pp == kLinkTail) continue;
+        const u32 pp = (u32)(lp >> 32), sp = (u32)lp;
+        if (pp == kLinkTail || pp == kLinkClaimed) {          // pi is the tail
+            __stcg(link + i, li | kLinkFinalBit);
+            continue;
+        }
         if (pp >= kLinkFirstMarker) { atomicOr(&ctr->errors, kErrInternal); continue; }
-        __stcg(link + i, ((u64)pp << 32) | (u32)((u32)li + (u32)lp));
+        // jump; if the segment we jumped over was final, its pointer is the tail and so is ours now
+        __stcg(link + i, ((u64)pp << 32) | (u32)((si + (sp & kLinkDistMask)) | (sp & kLinkFinalBit)));
         moved = true;
     }
     if (__any_sync(kFullMask, moved) && lane_id() == 0) *changed = 1;
@@ -907,8 +918,9 @@ emit_segments_mig_kernel(const Peers pe, const u64* __restrict__ link, const uns
                 const u32 pre = pe.contig_pre[r][c];
                 u32 pos = pre;
                 if (!is_tail) {
-                    if ((u32)li > pre) { atomicOr(&ctr->errors, kErrConverge); ok = false; }
-                    else pos = pre - (u32)li;
+                    const u32 dist = (u32)li & kLinkDistMask;
+                    if (dist > pre) { atomicOr(&ctr->errors, kErrConverge); ok = false; }
+                    else pos = pre - dist;
                 }
                 if (ok) {
                     const u64 off = pe.contig_off[r][c] + (u64)k + pos;

@@ -397,11 +397,15 @@ def sharded_assemble(comm, max_rounds: int = 40, timings: dict | None = None) ->
         if not comm.any(moved):
             break
     lap("rank_rounds")
-    for ph, name in ((2, "lengths"), (3, "claims"), (4, "offsets"), (5, "emit")):
-        for s in shards:
+    for ph in (2, 3, 4):                                  # lengths, tail claims, offsets: no barrier needed in between
+        for s in shards:                                  # (lengths accepts tails another rank has already claimed)
             s.phase(ph)
-        comm.barrier()
-        lap(name)
+    comm.barrier()
+    lap("lengths_claims_offsets")
+    for s in shards:
+        s.phase(5)                                        # emit: every GPU copies its segments into the owner rank's buffer
+    comm.barrier()
+    lap("emit")
     bits = comm.bits_or([s.phase(6) for s in shards])
     lap("collect")
     if bits:

@@ -130,10 +130,11 @@ class Cluster {
             barrier();
             if (!any) break;
         }
-        for (int phase = 2; phase <= 5; ++phase) {           // lengths, tail claims, offsets, emit
+        for (int phase = 2; phase <= 4; ++phase)             // lengths, tail claims, offsets: no barrier needed in between
             for (int r = 0; r < world_; ++r) must(kh_shard_phase(t_[r], phase, nullptr), t_[r], "finish");
-            barrier();
-        }
+        barrier();
+        for (int r = 0; r < world_; ++r) must(kh_shard_phase(t_[r], 5, nullptr), t_[r], "emit");
+        barrier();
         int bits = 0;
         for (int r = 0; r < world_; ++r) {
             int b = 0;

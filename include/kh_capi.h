@@ -168,7 +168,8 @@ int kh_shard_walk(kh_table* t, const void** links_dev_out, uint64_t* counts_out,
 int kh_shard_resolve(kh_table* t, const void* links_dev, uint64_t n);
 /* remaining phases, each followed by a barrier across ranks: 1 a batch of pointer-jumping rounds
  * (flag_out = "the last one still moved something"; repeat until no rank reports movement),
- * 2 contig lengths, 3 claim tails, 4 offsets, 5 emit, 6 collect (flag_out = device error bits) */
+ * 2 contig lengths, 3 claim tails, 4 offsets (2-4 need no barrier between them, one after 4), 5 emit, barrier,
+ * 6 collect (flag_out = device error bits) */
 int kh_shard_phase(kh_table* t, int phase, int* flag_out);
 int kh_shard_result(kh_table* t, const char** contigs_dev, const uint64_t** offsets_dev,
                     uint64_t* n_contigs, uint64_t* contig_bytes, uint64_t* n_nodes);

@@ -155,6 +155,21 @@ def test_chunked_shared_memory_build(kh, monkeypatch, k, lf, chunks):
         assert st["n_inserted"] == d.n and st["n_duplicates"] == 0
 
 
+@pytest.mark.parametrize("build", ["1", "0"])
+@pytest.mark.parametrize("pct", ["70", "20"])
+def test_grouping_buffer_overflow_paths(kh, monkeypatch, build, pct):
+    """The grouping buffers are sized for the expected share plus slack; the rare record that does not fit is
+    inserted directly (atomic path) or through the fix-up list (chunked build).  KH_DEBUG_CAP_PCT shrinks the
+    buffers so a large part of the input takes those paths -- the result must not change."""
+    monkeypatch.setenv("KH_PARTITION", "1")
+    monkeypatch.setenv("KH_BUILD", build)
+    monkeypatch.setenv("KH_DEBUG_CAP_PCT", pct)
+    for k in (19, 51):
+        d = kmergen.Dataset(k, 250000, 700, seed=int(pct) + k)
+        out, _, nodes, st = _assemble_text(kh, d.text(), k, chunks=2)
+        assert out == d.expected()[0] and nodes == d.n and st["n_inserted"] == d.n
+
+
 def test_chunked_build_counts_duplicates(kh, monkeypatch):
     monkeypatch.setenv("KH_PARTITION", "1")
     d = kmergen.Dataset(19, 200000, 300, seed=44)
