@@ -227,15 +227,13 @@ int insert_device_impl(kh_table* t, const unsigned char* recs, u64 n, bool recor
         overflow_cap = (u32)std::min<u64>(0x7FFFFFFFull, t->debug_cap_pct < 100 ? n + 65536 : n / 32 + 65536);
         bpp2 = (u32)((part_cap + kSubTile - 1) / kSubTile);
         const u32 nsub = 1u << (part_shift - kChunkShift);
-        sub_smem = ((12 * (size_t)nsub + 2 * kSubTile + 15) & ~(size_t)15) + (size_t)kSubTile * sizeof(V);
+        sub_smem = 8 * (size_t)nsub + 16;
         KH_TRY(ensure(t, t->grouped, (u64)nparts * part_cap * sizeof(V)));
         KH_TRY(ensure(t, t->fine, nchunks * (u64)chunk_cap * sizeof(V)));
         KH_TRY(ensure(t, t->chunk_cursor, nchunks * sizeof(u32)));
         KH_TRY(ensure(t, t->overflow, (u64)overflow_cap * sizeof(V)));
         if (!t->chunk_attr_set) {
             KH_CUDA(t, cudaFuncSetAttribute(build_chunks_kernel<W>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(kChunkBuckets * 32)));
-            KH_CUDA(t, cudaFuncSetAttribute(subpartition_kernel<W>, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                            (int)(((12 * (size_t)1024 + 2 * kSubTile + 15) & ~(size_t)15) + (size_t)kSubTile * sizeof(V))));
             t->chunk_attr_set = true;
         }
     }

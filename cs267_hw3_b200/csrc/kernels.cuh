@@ -393,6 +393,8 @@ constexpr int kSubThreads = 256;
 constexpr int kSubPerThread = 8;
 constexpr int kSubTile = kSubThreads * kSubPerThread;  // 2048 slot values per block
 
+// After the block-wide rank/reserve each thread writes its values straight to their destination run (L2 merges
+// the sector writes); staging a sorted copy in shared memory first was measured slower (2.71 vs 2.52 ms insert).
 template <int W>
 __global__ void __launch_bounds__(kSubThreads, 4)
 subpartition_kernel(const typename Slot<W>::value_t* __restrict__ grouped, const u32* __restrict__ part_cursor,
@@ -404,11 +406,7 @@ subpartition_kernel(const typename Slot<W>::value_t* __restrict__ grouped, const
     extern __shared__ __align__(16) unsigned char s_raw[];
     const u32 nsub = 1u << (part_shift - kChunkShift);                 // chunks per partition (<= 1024)
     u32* s_hist = reinterpret_cast<u32*>(s_raw);
-    u32* s_off = s_hist + nsub;
-    u32* s_gbase = s_off + nsub;
-    unsigned short* s_sid = reinterpret_cast<unsigned short*>(s_raw + 12 * (size_t)nsub);
-    V* s_sorted = reinterpret_cast<V*>(s_raw + ((12 * (size_t)nsub + 2 * kSubTile + 15) & ~(size_t)15));
-    __shared__ u64 s_warp[33];
+    u32* s_gbase = s_hist + nsub;
     const u32 part = blockIdx.x / blocks_per_part, jblk = blockIdx.x % blocks_per_part;
     const u64 n = min((u64)part_cursor[part], part_cap);
     const u64 base = (u64)jblk * kSubTile;
@@ -422,54 +420,31 @@ subpartition_kernel(const typename Slot<W>::value_t* __restrict__ grouped, const
 #pragma unroll
     for (int r = 0; r < kSubPerThread; ++r) {
         const u64 i = base + (u64)r * kSubThreads + threadIdx.x;
+        v[r] = i < n ? src[i] : S::zero();
+    }
+#pragma unroll
+    for (int r = 0; r < kSubPerThread; ++r) {
         sid[r] = 0xFFFFFFFFu;
-        if (i < n) {
-            v[r] = src[i];
+        if (!S::empty(v[r])) {
             const u64 chunk = place_bucket<W>(v[r], k, m, nbuckets) >> kChunkShift;
             sid[r] = (u32)(chunk - first_chunk) & (nsub - 1);
             rk[r] = atomicAdd(&s_hist[sid[r]], 1u);
         }
     }
     __syncthreads();
-    {
-        u32 h[4], sum = 0;
-#pragma unroll
-        for (int q = 0; q < 4; ++q) {
-            const u32 i = threadIdx.x * 4 + q;
-            h[q] = i < nsub ? s_hist[i] : 0u;
-            sum += h[q];
-        }
-        u64 total;
-        u64 run = block_exclusive_scan((u64)sum, s_warp, total);
-#pragma unroll
-        for (int q = 0; q < 4; ++q) {
-            const u32 i = threadIdx.x * 4 + q;
-            if (i < nsub) {
-                s_off[i] = (u32)run;
-                s_gbase[i] = h[q] ? atomicAdd(&chunk_cursor[first_chunk + i], h[q]) : 0u;
-            }
-            run += h[q];
-        }
-    }
+    // reserve one run per (block, chunk); s_gbase = position of this block's run inside the chunk's buffer
+    for (u32 i = threadIdx.x; i < nsub; i += blockDim.x)
+        s_gbase[i] = s_hist[i] ? atomicAdd(&chunk_cursor[first_chunk + i], s_hist[i]) : 0u;
     __syncthreads();
 #pragma unroll
     for (int r = 0; r < kSubPerThread; ++r) {
-        if (sid[r] != 0xFFFFFFFFu) {
-            const u32 pos = s_off[sid[r]] + rk[r];
-            s_sorted[pos] = v[r];
-            s_sid[pos] = (unsigned short)sid[r];
-        }
-    }
-    __syncthreads();
-    const u32 good = s_off[nsub - 1] + s_hist[nsub - 1];
-    for (u32 pos = threadIdx.x; pos < good; pos += blockDim.x) {
-        const u32 sb = s_sid[pos];
-        const u32 at = s_gbase[sb] + (pos - s_off[sb]);
+        if (sid[r] == 0xFFFFFFFFu) continue;
+        const u32 at = s_gbase[sid[r]] + rk[r];
         if (at < chunk_cap) {
-            fine[(first_chunk + sb) * (u64)chunk_cap + at] = s_sorted[pos];
+            fine[(first_chunk + sid[r]) * (u64)chunk_cap + at] = v[r];
         } else {                                                     // chunk buffer full: fix-up pass takes it
-            const u32 o = atomicAdd(&ctr->n_outbox, 1u);             // (n_outbox doubles as the overflow counter here)
-            if (o < overflow_cap) overflow[o] = s_sorted[pos];
+            const u32 o = atomicAdd(&ctr->n_outbox, 1u);
+            if (o < overflow_cap) overflow[o] = v[r];
             else atomicOr(&ctr->errors, kErrInternal);
         }
     }
