@@ -80,6 +80,7 @@ struct kh_table {
     int shard_migrate = 1;            // KH_SHARD_WALK=peer selects the peer-lookup walk instead of the migrating walk
     MigLayout lay = {};
     DevBuf seg_of_slot, boundary_list, outbox, outbox_grouped;
+    DevBuf owner_byte;                // owner rank of every record of the block being partitioned (0xFF = rejected)
     u64 shard_n_starts_max = 0;
 };
 
@@ -461,7 +462,7 @@ int shard_init_impl(kh_table* t, int rank, int world, u64 n_local_max, u64 n_tot
     int bps = 0, bps2 = 0;
     KH_CUDA(t, cudaOccupancyMaxActiveBlocksPerMultiprocessor(&bps, walk_sharded_kernel<W>, kWalkThreads, 0));
     KH_CUDA(t, cudaOccupancyMaxActiveBlocksPerMultiprocessor(&bps2, walk_mig_kernel<W>, kWalkThreads, 0));
-    bps = std::min(bps, bps2);
+    bps = t->shard_migrate ? bps2 : bps;
     if (bps < 1) return fail(t, KH_ERR_CUDA, "walk kernel does not fit on an SM");
     t->shard_walk_blocks = (unsigned)(t->sm_count * bps);
     const u64 nwarps = (u64)t->shard_walk_blocks * (kWalkThreads / 32);
@@ -507,6 +508,7 @@ int shard_init_impl(kh_table* t, int rank, int world, u64 n_local_max, u64 n_tot
     KH_TRY(ensure(t, t->scan_blocks, ((std::max(ntiles, n_starts_max + 1) + kScanTile - 1) / kScanTile + 2) * sizeof(u64)));
     KH_TRY(ensure(t, t->grouped, (n_local_max + 1) * sizeof(V)));
     KH_TRY(ensure(t, t->owner_ctr, 3 * kMaxRanks * sizeof(u64)));
+    KH_TRY(ensure(t, t->owner_byte, n_local_max + 1));
     KH_TRY(ensure(t, t->changed_flag, 16));
     Peers& pe = t->peers;
     memset(&pe, 0, sizeof(pe));
@@ -532,7 +534,8 @@ int shard_owner_partition_impl(kh_table* t, const unsigned char* recs, u64 n, co
     KH_CUDA(t, cudaEventRecord(t->ev[EV_INS0], t->stream));
     KH_CUDA(t, cudaMemsetAsync(octr, 0, 3 * kMaxRanks * sizeof(u64), t->stream));
     owner_count_kernel<W><<<(unsigned)ntiles, kInsThreads, (size_t)kInsTile * t->pb, t->stream>>>(
-        recs, n, t->k, t->olen, world, static_cast<u32*>(t->mask.p), static_cast<u32*>(t->tile_counts.p), octr, t->d_ctr);
+        recs, n, t->k, t->olen, world, static_cast<u32*>(t->mask.p), static_cast<u32*>(t->tile_counts.p), octr,
+        static_cast<unsigned char*>(t->owner_byte.p), t->d_ctr);
     KH_CUDA(t, cudaGetLastError());
     KH_TRY(device_scan(t, static_cast<u32*>(t->tile_counts.p), ntiles, static_cast<u64*>(t->tile_offs.p), &t->d_ctr->scan_total));
     u64 host_counts[kMaxRanks];
@@ -544,7 +547,8 @@ int shard_owner_partition_impl(kh_table* t, const unsigned char* recs, u64 n, co
     for (int w = 0; w < kMaxRanks; ++w) { base[w] = run; run += host_counts[w]; counts_out[w] = host_counts[w]; }
     KH_CUDA(t, cudaMemcpyAsync(octr + kMaxRanks, base, sizeof(base), cudaMemcpyHostToDevice, t->stream));
     owner_scatter_kernel<W><<<(unsigned)ntiles, kInsThreads, (size_t)kInsTile * t->pb, t->stream>>>(
-        recs, n, t->k, t->olen, world, octr + kMaxRanks, octr + 2 * kMaxRanks, static_cast<V*>(t->grouped.p));
+        recs, n, t->k, static_cast<const unsigned char*>(t->owner_byte.p), world, octr + kMaxRanks, octr + 2 * kMaxRanks,
+        static_cast<V*>(t->grouped.p));
     const u64 fresh = t->h_ctr->scan_total;
     if (t->n_starts + fresh > t->shard_n_starts_max) return fail(t, KH_ERR_ARG, "more start nodes than kh_shard_init reserved (n_starts_max)");
     if (fresh) {
@@ -608,7 +612,8 @@ int shard_walk_impl(kh_table* t, const void** entries_out, u64* counts_out) {
     u64* octr = static_cast<u64*>(t->owner_ctr.p);
     KH_CUDA(t, cudaMemsetAsync(octr, 0, 3 * kMaxRanks * sizeof(u64), t->stream));
     const unsigned gb = (unsigned)t->sm_count * 4;
-    outbox_count_kernel<W><<<gb, 256, 0, t->stream>>>(static_cast<const OutEntry<W>*>(t->outbox.p), t->d_ctr, lay.outbox_cap, octr);
+    outbox_count_kernel<W><<<gb, 256, 0, t->stream>>>(static_cast<OutEntry<W>*>(t->outbox.p), t->d_ctr, lay.outbox_cap, t->k, t->olen,
+                                                     t->peers.rank, t->peers.world, octr);
     u64 host_counts[kMaxRanks];
     KH_CUDA(t, cudaMemcpyAsync(host_counts, octr, sizeof(host_counts), cudaMemcpyDeviceToHost, t->stream));
     KH_CUDA(t, cudaStreamSynchronize(t->stream));
@@ -830,7 +835,7 @@ int kh_destroy(kh_table* t) {
     for (DevBuf* b : bufs) if (b->p) cudaFree(b->p);
     for (auto& row : t->ipc_opened) for (void* q : row) if (q) cudaIpcCloseMemHandle(q);
     if (t->owner_ctr.p) cudaFree(t->owner_ctr.p);
-    for (DevBuf* b : {&t->seg_of_slot, &t->boundary_list, &t->outbox, &t->outbox_grouped}) if (b->p) cudaFree(b->p);
+    for (DevBuf* b : {&t->seg_of_slot, &t->boundary_list, &t->outbox, &t->outbox_grouped, &t->owner_byte}) if (b->p) cudaFree(b->p);
     if (t->changed_flag.p) cudaFree(t->changed_flag.p);
     if (t->table) cudaFree(t->table);
     if (t->d_ctr) cudaFree(t->d_ctr);

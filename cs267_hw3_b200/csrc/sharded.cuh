@@ -48,12 +48,13 @@ __device__ __forceinline__ u32 owner_of(typename Slot<W>::value_t v, int world, 
 }
 
 // ---- K7: group records by owner ---------------------------------------------------------
-// pass 1: per-owner counts + start bitmask / per-tile start counts (same tiles as insert_kernel)
+// pass 1: per-owner counts + start bitmask / per-tile start counts (same tiles as insert_kernel).  The owner of
+// every record is kept (one byte) so that pass 2 does not repeat the minimizer scan.
 template <int W>
 __global__ void __launch_bounds__(kInsThreads)
 owner_count_kernel(const unsigned char* __restrict__ recs, u64 n, int k, int mo, int world,
                    u32* __restrict__ start_mask, u32* __restrict__ tile_starts, u64* __restrict__ owner_counts,
-                   Counters* ctr) {
+                   unsigned char* __restrict__ owner_byte, Counters* ctr) {
     typedef Slot<W> S;
     typedef typename S::value_t V;
     extern __shared__ __align__(16) unsigned char s_rec[];
@@ -74,6 +75,7 @@ owner_count_kernel(const unsigned char* __restrict__ recs, u64 n, int k, int mo,
         if (live) v = S::from_record(s_rec + j * pb, k, pl, ok);
         if (!ok) { err |= kErrBadInput; live = false; }
         const u32 o = live ? owner_of<W>(v, world, k, mo) : 0u;
+        if (j < cnt) owner_byte[rec0 + j] = live ? (unsigned char)o : (unsigned char)0xFF;
         // warp-aggregate per owner (world <= 8)
         for (int w = 0; w < world; ++w) {
             const u32 bo = __ballot_sync(kFullMask, live && o == (u32)w);
@@ -99,7 +101,7 @@ owner_count_kernel(const unsigned char* __restrict__ recs, u64 n, int k, int mo,
 // pass 2: scatter slot values to their owner's group (owner_base = exclusive prefix of the counts)
 template <int W>
 __global__ void __launch_bounds__(kInsThreads)
-owner_scatter_kernel(const unsigned char* __restrict__ recs, u64 n, int k, int mo, int world,
+owner_scatter_kernel(const unsigned char* __restrict__ recs, u64 n, int k, const unsigned char* __restrict__ owner_byte, int world,
                      const u64* __restrict__ owner_base, u64* __restrict__ owner_cursor,
                      typename Slot<W>::value_t* __restrict__ grouped) {
     typedef Slot<W> S;
@@ -121,10 +123,11 @@ owner_scatter_kernel(const unsigned char* __restrict__ recs, u64 n, int k, int m
         bool ok = true;
         own[r] = 0xFFFFFFFFu;
         if (j < cnt) {
-            v[r] = S::from_record(s_rec + j * pb, k, pl, ok);
-            if (ok) {
-                own[r] = owner_of<W>(v[r], world, k, mo);
-                rk[r] = atomicAdd(&s_cnt[own[r]], 1u);
+            const u32 o = owner_byte[rec0 + j];
+            if (o < (u32)world) {
+                v[r] = S::from_record(s_rec + j * pb, k, pl, ok);
+                own[r] = o;
+                rk[r] = atomicAdd(&s_cnt[o], 1u);
             }
         }
     }
@@ -488,6 +491,7 @@ struct MigLayout {
 
 constexpr u32 kOutBatch = 256;          // outbox entries a warp reserves per global atomic
 constexpr u32 kOutVoid = 0xFFu;          // dest of a reserved-but-unused outbox entry
+constexpr u32 kOutUnrouted = 0xFEu;      // dest not computed yet: the grouping pass derives it from the key
 template <int W> struct OutEntry;
 template <> struct alignas(16) OutEntry<1> { u64 key; u32 src; u32 dest; };
 template <> struct alignas(16) OutEntry<2> { u128 key; u32 src; u32 dest; u64 pad; };
@@ -622,7 +626,7 @@ struct MigWalkParams {
 };
 
 template <int W>
-__global__ void __launch_bounds__(kWalkThreads)
+__global__ void __launch_bounds__(kWalkThreads, W == 1 ? 6 : 4)
 walk_mig_kernel(const MigWalkParams p) {
     typedef Slot<W> S;
     typedef typename S::value_t V;
@@ -644,7 +648,6 @@ walk_mig_kernel(const MigWalkParams p) {
     V cur = S::zero(), chk = S::zero();
     u32 seg = 0, n = 0, steps = 0, limit = 256;
     u64 acc = 0;
-    MinState ms{0, 0, 0};               // owner minimizer of `cur`, carried along the chain
 
     auto close = [&](u32 next) {       // next: global id, kLinkTail or kLinkPending
         if (n & 7u) *reinterpret_cast<u64*>(p.tmp + (u64)seg * p.seg_chars + (n & ~7u)) = acc;
@@ -680,7 +683,6 @@ walk_mig_kernel(const MigWalkParams p) {
                     else active = true;
                 }
                 chk = cur;
-                if (active && p.mo) ms = min_scan<W>(cur, p.k, p.mo);
             }
             w_next += min((u32)__popc(idle), avail);
         }
@@ -710,10 +712,13 @@ walk_mig_kernel(const MigWalkParams p) {
             }
             o_next += want;
         }
-        // ---- one step; a lane whose successor lives elsewhere parks (key, dest) for the outbox ----
+        // ---- one step.  Inserts are routed by owner, so a k-mer stored here IS local: look it up in the local
+        // table first; only a miss leaves the GPU.  The lane parks the key for the outbox, and the dense grouping
+        // pass (outbox_count_kernel) derives the destination from it -- the owner function (a minimizer scan) is
+        // ~150 instructions and would run here with a handful of lanes active.
         bool send = false;
         V send_key = S::zero();
-        u32 send_dest = 0, send_src = 0;
+        u32 send_src = 0;
         if (active) {
             const u32 f = S::fwd(cur);
             if (f == kExtF) {
@@ -726,16 +731,8 @@ walk_mig_kernel(const MigWalkParams p) {
                     acc = 0;
                 }
                 const V nk = S::next_key(cur, p.k);
-                u64 oh;
-                if (p.mo) { ms = min_step<W>(ms, nk, p.k, p.mo); oh = owner_hash_from_minimizer(ms.val); }
-                else oh = S::owner_hash(nk);
-                const u32 owner = (u32)__umul64hi(oh, (u64)p.world);
-                if (owner != (u32)p.rank) {
-                    send = true; send_key = nk; send_dest = owner; send_src = my_bits | seg;
-                    close(kLinkPending);
-                } else {
-                    const u64 home = (p.m == 0) ? bucket_of(S::hash(nk), p.nbuckets)
-                                                : place_bucket_from<W>(p.m == p.mo ? oh : fmix64(minimizer_value<W>(nk, p.k, p.m) + 0x632BE59BD9B4E019ull), nk, p.nbuckets);
+                {
+                    const u64 home = place_bucket<W>(nk, p.k, p.m, p.nbuckets);
                     V nxt = S::zero();
                     u64 b = home; int s = -1;
                     for (u64 tries = 0; tries < p.nbuckets && s < 0; ++tries) {
@@ -754,8 +751,13 @@ walk_mig_kernel(const MigWalkParams p) {
                         if (s < 0) b = (b + 1 == p.nbuckets) ? 0 : b + 1;
                     }
                     if (s < 0) {
-                        atomicOr(&p.ctr->errors, kErrNotFound);
-                        close(kLinkTail);
+                        if (p.world > 1) {                                  // not here: its owner resolves it (or reports it missing)
+                            send = true; send_key = nk; send_src = my_bits | seg;
+                            close(kLinkPending);
+                        } else {
+                            atomicOr(&p.ctr->errors, kErrNotFound);         // kmer_hash.cpp:47-49
+                            close(kLinkTail);
+                        }
                     } else if (s == 0 && (b & split_mask) == 0) {
                         close(my_bits | (u32)(b >> p.split_shift));
                     } else {
@@ -786,7 +788,7 @@ walk_mig_kernel(const MigWalkParams p) {
                 const u32 at = x_next + __popc(sends & lt_mask);
                 if (at < p.lay.outbox_cap) {
                     OutEntry<W> e;
-                    e.key = send_key; e.src = send_src; e.dest = send_dest;
+                    e.key = send_key; e.src = send_src; e.dest = kOutUnrouted;
                     outbox[at] = e;
                 } else {
                     atomicOr(&p.ctr->errors, kErrInternal);
@@ -802,17 +804,38 @@ walk_mig_kernel(const MigWalkParams p) {
 }
 
 // ---- outbox -> groups per destination (count, then scatter) ----------------------------------------
+// One tile = kOutTile entries: destinations are ranked in shared memory, then one global atomic per destination
+// reserves the tile's run in the group (a per-entry atomicAdd on `world` addresses serialises in L2).
+constexpr int kOutPerThread = 4;
+constexpr int kOutTile = 256 * kOutPerThread;
 template <int W>
 __global__ void __launch_bounds__(256)
-outbox_count_kernel(const OutEntry<W>* __restrict__ outbox, const Counters* __restrict__ ctr, u32 cap, u64* __restrict__ counts) {
+outbox_count_kernel(OutEntry<W>* __restrict__ outbox, Counters* __restrict__ ctr, u32 cap, int k, int mo, int rank, int world,
+                    u64* __restrict__ counts) {
     __shared__ u32 s_cnt[kMaxRanks];
     if (threadIdx.x < kMaxRanks) s_cnt[threadIdx.x] = 0;
     __syncthreads();
     const u32 n = min(ctr->n_outbox, cap);
-    for (u32 i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x)
-    {
-        const u32 d = outbox[i].dest;
-        if (d < (u32)kMaxRanks) atomicAdd(&s_cnt[d], 1u);
+    u32 mine[kMaxRanks];
+#pragma unroll
+    for (int w = 0; w < kMaxRanks; ++w) mine[w] = 0;
+    for (u32 i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) {
+        u32 d = outbox[i].dest;
+        if (d == kOutUnrouted) {                   // parked by the walk after a local miss: route it now
+            d = owner_of<W>(outbox[i].key, world, k, mo);
+            if (d == (u32)rank) {                  // it would live here, and it does not: the k-mer is in no table
+                atomicOr(&ctr->errors, kErrNotFound);          // kmer_hash.cpp:47-49
+                d = kOutVoid;
+            }
+            outbox[i].dest = d;
+        }
+#pragma unroll
+        for (int w = 0; w < kMaxRanks; ++w) mine[w] += (d == (u32)w);
+    }
+#pragma unroll
+    for (int w = 0; w < kMaxRanks; ++w) {
+        const u32 tot = __reduce_add_sync(kFullMask, mine[w]);
+        if (lane_id() == 0 && tot) atomicAdd(&s_cnt[w], tot);
     }
     __syncthreads();
     if (threadIdx.x < kMaxRanks && s_cnt[threadIdx.x]) atomicAdd(&counts[threadIdx.x], (u64)s_cnt[threadIdx.x]);
@@ -821,11 +844,38 @@ template <int W>
 __global__ void __launch_bounds__(256)
 outbox_scatter_kernel(const OutEntry<W>* __restrict__ outbox, const Counters* __restrict__ ctr, u32 cap,
                       const u64* __restrict__ base, u64* __restrict__ cursor, OutEntry<W>* __restrict__ grouped) {
+    __shared__ u32 s_cnt[kMaxRanks];
+    __shared__ u64 s_base[kMaxRanks];
     const u32 n = min(ctr->n_outbox, cap);
-    for (u32 i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) {
-        const OutEntry<W> e = outbox[i];
-        const u32 d = e.dest;
-        if (d < (u32)kMaxRanks) grouped[base[d] + atomicAdd(&cursor[d], 1ull)] = e;
+    const u32 ntiles = (n + kOutTile - 1) / kOutTile;
+    for (u32 tile = blockIdx.x; tile < ntiles; tile += gridDim.x) {
+        if (threadIdx.x < kMaxRanks) s_cnt[threadIdx.x] = 0;
+        __syncthreads();
+        OutEntry<W> e[kOutPerThread];
+        u32 rk[kOutPerThread];
+#pragma unroll
+        for (int r = 0; r < kOutPerThread; ++r) {
+            const u32 i = tile * kOutTile + r * 256 + threadIdx.x;
+            u32 d = 0xFFFFFFFFu;
+            if (i < n) { e[r] = outbox[i]; d = e[r].dest; }
+            if (d >= (u32)kMaxRanks) d = 0xFFFFFFFFu;              // voided entry (kOutVoid) or past the end
+            e[r].dest = d;
+            // lanes of a warp that share a destination take consecutive ranks from one shared-memory atomic
+            const unsigned same = __match_any_sync(kFullMask, d);
+            const int leader = __ffs(same) - 1;
+            u32 first = 0;
+            if ((int)lane_id() == leader && d != 0xFFFFFFFFu) first = atomicAdd(&s_cnt[d], (u32)__popc(same));
+            rk[r] = __shfl_sync(kFullMask, first, leader) + (u32)__popc(same & ((1u << lane_id()) - 1u));
+        }
+        __syncthreads();
+        if (threadIdx.x < kMaxRanks)
+            s_base[threadIdx.x] = base[threadIdx.x] +
+                                  (s_cnt[threadIdx.x] ? atomicAdd(&cursor[threadIdx.x], (u64)s_cnt[threadIdx.x]) : 0ull);
+        __syncthreads();
+#pragma unroll
+        for (int r = 0; r < kOutPerThread; ++r)
+            if (e[r].dest != 0xFFFFFFFFu) grouped[s_base[e[r].dest] + rk[r]] = e[r];
+        __syncthreads();
     }
 }
 
