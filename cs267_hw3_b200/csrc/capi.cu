@@ -80,6 +80,8 @@ struct kh_table {
     int shard_migrate = 1;            // KH_SHARD_WALK=peer selects the peer-lookup walk instead of the migrating walk
     MigLayout lay = {};
     DevBuf seg_of_slot, boundary_list, outbox, outbox_grouped;
+    DevBuf shard_parts;               // owner-side chunked build: received slot values grouped by 8 MB table region
+    int shard_build = 1;              // KH_SHARD_BUILD: 1 = build the owner's table chunk by chunk in shared memory (large shards), 2 = always, 0 = never
     DevBuf owner_byte;                // owner rank of every record of the block being partitioned (0xFF = rejected)
     u64 shard_n_starts_max = 0;
 };
@@ -234,7 +236,8 @@ int insert_device_impl(kh_table* t, const unsigned char* recs, u64 n, bool recor
         KH_TRY(ensure(t, t->chunk_cursor, nchunks * sizeof(u32)));
         KH_TRY(ensure(t, t->overflow, (u64)overflow_cap * sizeof(V)));
         if (!t->chunk_attr_set) {
-            KH_CUDA(t, cudaFuncSetAttribute(build_chunks_kernel<W>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(kChunkBuckets * 32)));
+            KH_CUDA(t, cudaFuncSetAttribute(build_chunks_kernel<W, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(kChunkBuckets * 32)));
+            KH_CUDA(t, cudaFuncSetAttribute(build_chunks_kernel<W, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(kChunkBuckets * 32)));
             t->chunk_attr_set = true;
         }
     }
@@ -253,12 +256,12 @@ int insert_device_impl(kh_table* t, const unsigned char* recs, u64 n, bool recor
             static_cast<V*>(t->grouped.p), static_cast<V*>(t->table), static_cast<u32*>(t->mask.p),
             static_cast<u32*>(t->tile_counts.p), static_cast<V*>(t->overflow.p), overflow_cap, t->d_ctr);
         subpartition_kernel<W><<<nparts * bpp2, kSubThreads, sub_smem, t->stream>>>(
-            static_cast<const V*>(t->grouped.p), static_cast<const u32*>(t->part_cursor.p), part_cap, bpp2, part_shift,
-            t->k, t->mlen, t->nbuckets, chunk_cap, static_cast<u32*>(t->chunk_cursor.p), static_cast<V*>(t->fine.p),
+            static_cast<const V*>(t->grouped.p), static_cast<const u32*>(t->part_cursor.p), 0, part_cap, bpp2, kChunkShift,
+            1u << (part_shift - kChunkShift), t->k, t->mlen, t->nbuckets, chunk_cap, static_cast<u32*>(t->chunk_cursor.p), static_cast<V*>(t->fine.p),
             static_cast<V*>(t->overflow.p), overflow_cap, t->d_ctr);
-        build_chunks_kernel<W><<<(unsigned)nchunks, kBuildThreads, kChunkBuckets * 32, t->stream>>>(
+        build_chunks_kernel<W, false><<<(unsigned)nchunks, kBuildThreads, kChunkBuckets * 32, t->stream>>>(
             static_cast<const V*>(t->fine.p), static_cast<const u32*>(t->chunk_cursor.p), chunk_cap, static_cast<V*>(t->table),
-            t->nbuckets, t->k, t->mlen, t->table_dirty ? 1 : 0, static_cast<V*>(t->overflow.p), overflow_cap, t->d_ctr);
+            t->nbuckets, t->k, t->mlen, t->table_dirty ? 1 : 0, static_cast<V*>(t->overflow.p), overflow_cap, t->d_ctr, BoundaryReg{});
         insert_overflow_kernel<W><<<64, 256, 0, t->stream>>>(static_cast<const V*>(t->overflow.p), overflow_cap, t->k, t->mlen,
                                                             static_cast<V*>(t->table), t->nbuckets, t->d_ctr);
     } else {
@@ -567,7 +570,59 @@ int insert_slots_impl(kh_table* t, const void* slots, u64 n) {
     typedef typename Slot<W>::value_t V;
     if (n == 0) return KH_OK;
     const unsigned blocks = (unsigned)((n + kInsTile - 1) / kInsTile);
-    if (t->shard_on && t->shard_migrate)
+    // A whole shard arriving into a clean table larger than L2 is built chunk by chunk in shared memory (kernels.cuh,
+    // chunked build): two grouping passes over the received values, no global atomics, boundary starts registered
+    // in a dense sweep of every finished chunk.  Anything else takes the atomic insert below.
+    const bool chunked = t->shard_on && t->shard_migrate && t->shard_build && !t->table_dirty && n < 0xFFF00000ull &&
+                         (t->shard_build == 2 ||       // 2 = always (tests: small tables take the same path)
+                          (t->table_bytes > (64ull << 20) && n * 8 >= t->nbuckets * (u64)t->per_bucket));
+    if (chunked) {
+        u32 part_shift = kChunkShift + 7;                               // 128 chunks (8 MB of table) per region
+        while (((t->nbuckets - 1) >> part_shift) + 1 > (u64)kMaxParts) ++part_shift;
+        if (part_shift - kChunkShift > 10) return fail(t, KH_ERR_ARG, "table too large for the chunked build");
+        const u32 nparts = (u32)(((t->nbuckets - 1) >> part_shift) + 1);
+        const double share = (double)n * (double)std::min<u64>(t->nbuckets, 1ull << part_shift) / (double)t->nbuckets;
+        u64 part_cap = (u64)(share + 24.0 * std::sqrt(share + 1.0) + 64.0) * t->debug_cap_pct / 100;
+        part_cap = (part_cap + kInsTile - 1) / kInsTile * kInsTile;
+        const u64 nchunks = (t->nbuckets + kChunkBuckets - 1) >> kChunkShift;
+        const double share2 = (double)n * (double)std::min<u64>(t->nbuckets, kChunkBuckets) / (double)t->nbuckets;
+        u32 chunk_cap = (u32)((u64)(share2 + 24.0 * std::sqrt(share2 + 1.0) + 32.0) * t->debug_cap_pct / 100);
+        chunk_cap = std::max(4u, (chunk_cap + 3u) & ~3u);
+        const u32 overflow_cap = (u32)std::min<u64>(0x7FFFFFFFull, t->debug_cap_pct < 100 ? n + 65536 : n / 32 + 65536);
+        const u32 bpp2 = (u32)((part_cap + kSubTile - 1) / kSubTile);
+        const u32 nsub = 1u << (part_shift - kChunkShift);
+        KH_TRY(ensure(t, t->part_cursor, kMaxParts * sizeof(u32)));
+        KH_TRY(ensure(t, t->shard_parts, (u64)nparts * part_cap * sizeof(V)));
+        KH_TRY(ensure(t, t->fine, nchunks * (u64)chunk_cap * sizeof(V)));
+        KH_TRY(ensure(t, t->chunk_cursor, nchunks * sizeof(u32)));
+        KH_TRY(ensure(t, t->overflow, (u64)overflow_cap * sizeof(V)));
+        if (!t->chunk_attr_set) {
+            KH_CUDA(t, cudaFuncSetAttribute(build_chunks_kernel<W, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(kChunkBuckets * 32)));
+            KH_CUDA(t, cudaFuncSetAttribute(build_chunks_kernel<W, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(kChunkBuckets * 32)));
+            t->chunk_attr_set = true;
+        }
+        KH_CUDA(t, cudaMemsetAsync(t->part_cursor.p, 0, kMaxParts * sizeof(u32), t->stream));
+        KH_CUDA(t, cudaMemsetAsync(t->chunk_cursor.p, 0, nchunks * sizeof(u32), t->stream));
+        KH_CUDA(t, cudaMemsetAsync(&t->d_ctr->n_outbox, 0, sizeof(u32), t->stream));
+        V* parts = static_cast<V*>(t->shard_parts.p);
+        V* over = static_cast<V*>(t->overflow.p);
+        const unsigned l1_blocks = (unsigned)((n + kSubTile - 1) / kSubTile);
+        subpartition_kernel<W><<<l1_blocks, kSubThreads, 8 * (size_t)nparts + 16, t->stream>>>(      // level 1: by 8 MB region
+            static_cast<const V*>(slots), nullptr, n, 0, l1_blocks, part_shift, nparts, t->k, t->mlen, t->nbuckets,
+            (u32)part_cap, static_cast<u32*>(t->part_cursor.p), parts, over, overflow_cap, t->d_ctr);
+        subpartition_kernel<W><<<nparts * bpp2, kSubThreads, 8 * (size_t)nsub + 16, t->stream>>>(    // level 2: by 64 KB chunk
+            parts, static_cast<const u32*>(t->part_cursor.p), 0, part_cap, bpp2, kChunkShift, nsub, t->k, t->mlen, t->nbuckets,
+            chunk_cap, static_cast<u32*>(t->chunk_cursor.p), static_cast<V*>(t->fine.p), over, overflow_cap, t->d_ctr);
+        BoundaryReg br;
+        br.seg_of_slot = static_cast<u32*>(t->seg_of_slot.p); br.boundary_list = t->boundary_list.p; br.bcap = t->lay.bcap;
+        br.rank = t->peers.rank; br.world = t->peers.world; br.mo = t->olen;
+        build_chunks_kernel<W, true><<<(unsigned)nchunks, kBuildThreads, kChunkBuckets * 32, t->stream>>>(
+            static_cast<const V*>(t->fine.p), static_cast<const u32*>(t->chunk_cursor.p), chunk_cap, static_cast<V*>(t->table),
+            t->nbuckets, t->k, t->mlen, 0, over, overflow_cap, t->d_ctr, br);
+        insert_overflow_shard_kernel<W><<<64, 256, 0, t->stream>>>(
+            over, overflow_cap, t->k, t->mlen, t->olen, t->peers.rank, t->peers.world, static_cast<V*>(t->table), t->nbuckets,
+            static_cast<u32*>(t->seg_of_slot.p), static_cast<V*>(t->boundary_list.p), t->lay.bcap, t->d_ctr);
+    } else if (t->shard_on && t->shard_migrate)
         insert_slots_shard_kernel<W><<<blocks, kInsThreads, 0, t->stream>>>(
             static_cast<const V*>(slots), n, t->k, t->mlen, t->olen, t->peers.rank, t->peers.world, static_cast<V*>(t->table),
             t->nbuckets, static_cast<u32*>(t->seg_of_slot.p), static_cast<V*>(t->boundary_list.p), t->lay.bcap, t->d_ctr);
@@ -575,6 +630,7 @@ int insert_slots_impl(kh_table* t, const void* slots, u64 n) {
         insert_slots_direct_kernel<W><<<blocks, kInsThreads, 0, t->stream>>>(
             static_cast<const V*>(slots), n, t->k, t->mlen, static_cast<V*>(t->table), t->nbuckets, t->d_ctr);
     KH_CUDA(t, cudaGetLastError());
+    t->table_dirty = true;
     KH_CUDA(t, cudaEventRecord(t->ev[EV_INS1], t->stream));
     t->have_ins = true;
     return KH_OK;
@@ -813,6 +869,7 @@ int kh_create(int k, uint64_t n_expected, double load_factor, int device, kh_tab
     // measured: the shared-memory build wins for 64-bit slots (2.85 vs 3.03 ms) and loses for 128-bit slots
     // (4.6 vs 4.1 ms: twice the bytes through the two grouping passes), so it is the default only for K <= 29
     t->build_mode = env_int("KH_BUILD", t->W == 1 ? 1 : 0);
+    t->shard_build = env_int("KH_SHARD_BUILD", 1);
     t->debug_cap_pct = std::max(1, env_int("KH_DEBUG_CAP_PCT", 100));
     t->ins_mode = env_int("KH_INS_MODE", 1);
     t->warm_ahead = env_int("KH_WARM_AHEAD", 1);
@@ -835,7 +892,7 @@ int kh_destroy(kh_table* t) {
     for (DevBuf* b : bufs) if (b->p) cudaFree(b->p);
     for (auto& row : t->ipc_opened) for (void* q : row) if (q) cudaIpcCloseMemHandle(q);
     if (t->owner_ctr.p) cudaFree(t->owner_ctr.p);
-    for (DevBuf* b : {&t->seg_of_slot, &t->boundary_list, &t->outbox, &t->outbox_grouped, &t->owner_byte}) if (b->p) cudaFree(b->p);
+    for (DevBuf* b : {&t->seg_of_slot, &t->boundary_list, &t->outbox, &t->outbox_grouped, &t->owner_byte, &t->shard_parts}) if (b->p) cudaFree(b->p);
     if (t->changed_flag.p) cudaFree(t->changed_flag.p);
     if (t->table) cudaFree(t->table);
     if (t->d_ctr) cudaFree(t->d_ctr);

@@ -395,24 +395,27 @@ constexpr int kSubTile = kSubThreads * kSubPerThread;  // 2048 slot values per b
 
 // After the block-wide rank/reserve each thread writes its values straight to their destination run (L2 merges
 // the sector writes); staging a sorted copy in shared memory first was measured slower (2.71 vs 2.52 ms insert).
+// The kernel splits input partition `part` (values whose home lies in units [part*nsub, (part+1)*nsub), a unit being
+// 2^unit_shift buckets) into one buffer per unit.  Level 2 of the chunked build uses it with unit = chunk; the sharded
+// path also uses it as level 1 on the flat array of received slot values (part_cursor == nullptr: one input
+// "partition" of n_flat values, unit = 8 MB table region).
 template <int W>
 __global__ void __launch_bounds__(kSubThreads, 4)
-subpartition_kernel(const typename Slot<W>::value_t* __restrict__ grouped, const u32* __restrict__ part_cursor,
-                    u64 part_cap, u32 blocks_per_part, u32 part_shift, int k, int m, u64 nbuckets,
+subpartition_kernel(const typename Slot<W>::value_t* __restrict__ grouped, const u32* __restrict__ part_cursor, u64 n_flat,
+                    u64 part_cap, u32 blocks_per_part, u32 unit_shift, u32 nsub, int k, int m, u64 nbuckets,
                     u32 chunk_cap, u32* __restrict__ chunk_cursor, typename Slot<W>::value_t* __restrict__ fine,
                     typename Slot<W>::value_t* __restrict__ overflow, u32 overflow_cap, Counters* ctr) {
     typedef Slot<W> S;
     typedef typename S::value_t V;
     extern __shared__ __align__(16) unsigned char s_raw[];
-    const u32 nsub = 1u << (part_shift - kChunkShift);                 // chunks per partition (<= 1024)
-    u32* s_hist = reinterpret_cast<u32*>(s_raw);
+    u32* s_hist = reinterpret_cast<u32*>(s_raw);                       // nsub <= 1024 units per input partition
     u32* s_gbase = s_hist + nsub;
     const u32 part = blockIdx.x / blocks_per_part, jblk = blockIdx.x % blocks_per_part;
-    const u64 n = min((u64)part_cursor[part], part_cap);
+    const u64 n = part_cursor ? min((u64)part_cursor[part], part_cap) : n_flat;
     const u64 base = (u64)jblk * kSubTile;
     if (base >= n) return;
     const V* __restrict__ src = grouped + (u64)part * part_cap;
-    const u64 first_chunk = (u64)part << (part_shift - kChunkShift);
+    const u64 first_chunk = (u64)part * nsub;
     for (u32 i = threadIdx.x; i < nsub; i += blockDim.x) s_hist[i] = 0;
     __syncthreads();
     V v[kSubPerThread];
@@ -426,8 +429,8 @@ subpartition_kernel(const typename Slot<W>::value_t* __restrict__ grouped, const
     for (int r = 0; r < kSubPerThread; ++r) {
         sid[r] = 0xFFFFFFFFu;
         if (!S::empty(v[r])) {
-            const u64 chunk = place_bucket<W>(v[r], k, m, nbuckets) >> kChunkShift;
-            sid[r] = (u32)(chunk - first_chunk) & (nsub - 1);
+            const u64 chunk = place_bucket<W>(v[r], k, m, nbuckets) >> unit_shift;
+            sid[r] = min((u32)(chunk - first_chunk), nsub - 1u);
             rk[r] = atomicAdd(&s_hist[sid[r]], 1u);
         }
     }
@@ -472,16 +475,27 @@ __device__ __forceinline__ int build_insert_one(typename Slot<W>::value_t* s_tab
     return kInsFull;                      // the probe sequence leaves the chunk
 }
 
-template <int W>
+// Sharded tables also register their BOUNDARY starts here (the k-mers a local walk starts from: backward ext 'F', or
+// a predecessor that another GPU owns).  That is a pure function of the slot value, so it is decided in one dense
+// sweep over the finished chunk -- every lane busy -- instead of per insert; ids are handed out with shared-memory
+// counters and ONE global atomic per chunk.  Requires a clean table (every occupied slot of the chunk is new).
+struct BoundaryReg {
+    u32* seg_of_slot;       // slot position -> boundary id
+    void* boundary_list;    // boundary id -> slot value
+    u32 bcap;
+    int rank, world, mo;
+};
+
+template <int W, bool SHARD>
 __global__ void __launch_bounds__(kBuildThreads)
 build_chunks_kernel(const typename Slot<W>::value_t* __restrict__ fine, const u32* __restrict__ chunk_cursor, u32 chunk_cap,
                     typename Slot<W>::value_t* table, u64 nbuckets, int k, int m, int load_existing,
-                    typename Slot<W>::value_t* __restrict__ overflow, u32 overflow_cap, Counters* ctr) {
+                    typename Slot<W>::value_t* __restrict__ overflow, u32 overflow_cap, Counters* ctr, const BoundaryReg br) {
     typedef Slot<W> S;
     typedef typename S::value_t V;
     extern __shared__ __align__(16) unsigned char s_raw[];
     V* s_tab = reinterpret_cast<V*>(s_raw);                            // kChunkBuckets * 32 bytes
-    __shared__ u32 s_inserted, s_dups;
+    __shared__ u32 s_inserted, s_dups, s_nbound, s_bbase;
     const u64 b0 = (u64)blockIdx.x << kChunkShift;
     const u32 nb = (u32)min((u64)kChunkBuckets, nbuckets - b0);
     const u32 nvec = nb * 2;                                           // 16-byte vectors in this chunk
@@ -496,7 +510,7 @@ build_chunks_kernel(const typename Slot<W>::value_t* __restrict__ fine, const u3
         const u32 i = threadIdx.x + r * kBuildThreads;
         v[r] = i < cnt ? recs[i] : S::zero();
     }
-    if (threadIdx.x == 0) { s_inserted = 0; s_dups = 0; }
+    if (threadIdx.x == 0) { s_inserted = 0; s_dups = 0; s_nbound = 0; }
     if (load_existing) for (u32 i = threadIdx.x; i < nvec; i += blockDim.x) s4[i] = g4[i];
     else for (u32 i = threadIdx.x; i < nvec; i += blockDim.x) s4[i] = make_uint4(0, 0, 0, 0);
     __syncthreads();
@@ -535,6 +549,44 @@ build_chunks_kernel(const typename Slot<W>::value_t* __restrict__ fine, const u3
     if (threadIdx.x == 0) {
         if (s_inserted) atomicAdd(&ctr->n_inserted, (u64)s_inserted);
         if (s_dups) atomicAdd(&ctr->n_duplicates, (u64)s_dups);
+    }
+    if (SHARD) {
+        constexpr int kSweep = (int)(kChunkBuckets * S::kPerBucket) / kBuildThreads;      // slots per thread
+        const u32 nslots = nb * S::kPerBucket;
+        u32 is_bnd = 0;                        // bit r: slot threadIdx.x + r * kBuildThreads is a boundary start
+        unsigned short lid[kSweep];            // its id within this chunk
+#pragma unroll
+        for (int r = 0; r < kSweep; ++r) {
+            const u32 i = threadIdx.x + r * kBuildThreads;
+            bool bnd = false;
+            if (i < nslots) {
+                const V v = s_tab[i];
+                if (!S::empty(v)) {
+                    bnd = S::back(v) == kExtF;
+                    if (!bnd && br.world > 1) bnd = owner_of<W>(S::prev_key(v, k), br.world, k, br.mo) != (u32)br.rank;
+                }
+            }
+            const u32 bal = __ballot_sync(kFullMask, bnd);
+            u32 first = 0;
+            if (lane_id() == 0 && bal) first = atomicAdd(&s_nbound, (u32)__popc(bal));
+            first = __shfl_sync(kFullMask, first, 0);
+            lid[r] = (unsigned short)(first + __popc(bal & ((1u << lane_id()) - 1u)));
+            is_bnd |= (bnd ? 1u : 0u) << r;
+        }
+        __syncthreads();
+        if (threadIdx.x == 0) s_bbase = s_nbound ? atomicAdd(&ctr->n_boundary, s_nbound) : 0u;
+        __syncthreads();
+        V* __restrict__ blist = static_cast<V*>(br.boundary_list);
+        u32 err = 0;
+#pragma unroll
+        for (int r = 0; r < kSweep; ++r) {
+            if (!((is_bnd >> r) & 1u)) continue;
+            const u32 i = threadIdx.x + r * kBuildThreads;
+            const u32 id = s_bbase + lid[r];
+            if (id < br.bcap) { blist[id] = s_tab[i]; br.seg_of_slot[b0 * S::kPerBucket + i] = id; }
+            else err = kErrInternal;
+        }
+        if (err) atomicOr(&ctr->errors, err);
     }
 }
 

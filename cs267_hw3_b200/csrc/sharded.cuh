@@ -42,11 +42,6 @@ struct Peers {
     int world, rank;
 };
 
-template <int W>
-__device__ __forceinline__ u32 owner_of(typename Slot<W>::value_t v, int world, int k, int m) {
-    return (u32)__umul64hi(owner_hash_of<W>(v, k, m), (u64)world);
-}
-
 // ---- K7: group records by owner ---------------------------------------------------------
 // pass 1: per-owner counts + start bitmask / per-tile start counts (same tiles as insert_kernel).  The owner of
 // every record is kept (one byte) so that pass 2 does not repeat the minimizer scan.
@@ -566,6 +561,52 @@ insert_slots_shard_kernel(const typename Slot<W>::value_t* __restrict__ slots, u
         if (s_inserted) atomicAdd(&ctr->n_inserted, (u64)s_inserted);
         if (s_dups) atomicAdd(&ctr->n_duplicates, (u64)s_dups);
         if (s_err) atomicOr(&ctr->errors, s_err);
+    }
+}
+
+// the few values the chunked owner-side build could not place (see build_chunks_kernel): ordinary global insert,
+// after every chunk is final, with the same boundary registration as insert_slots_shard_kernel
+template <int W>
+__global__ void __launch_bounds__(256)
+insert_overflow_shard_kernel(const typename Slot<W>::value_t* __restrict__ overflow, u32 overflow_cap, int k, int m, int mo,
+                             int rank, int world, typename Slot<W>::value_t* table, u64 nbuckets,
+                             u32* __restrict__ seg_of_slot, typename Slot<W>::value_t* __restrict__ boundary_list,
+                             u32 bcap, Counters* ctr) {
+    typedef Slot<W> S;
+    typedef typename S::value_t V;
+    const u32 n = min(ctr->n_outbox, overflow_cap);
+    for (u32 base = blockIdx.x * blockDim.x; base < n; base += gridDim.x * blockDim.x) {      // warp-uniform trip count
+        const u32 i = base + threadIdx.x;
+        bool bnd = false;
+        V v = S::zero();
+        u64 pos = 0;
+        if (i < n) {
+            v = overflow[i];
+            const u64 b = place_bucket<W>(v, k, m, nbuckets);
+            u64 q[4];
+            load256_cg(table + b * S::kPerBucket, q);
+            const int rc = insert_one<W>(table, nbuckets, b, v, q, &pos);
+            if (rc == kInsInserted) {
+                atomicAdd(&ctr->n_inserted, 1ull);
+                bnd = S::back(v) == kExtF;
+                if (!bnd && world > 1) bnd = owner_of<W>(S::prev_key(v, k), world, k, mo) != (u32)rank;
+            } else if (rc == kInsDuplicate) {
+                atomicAdd(&ctr->n_duplicates, 1ull);
+            } else {
+                atomicOr(&ctr->errors, kErrTableFull);
+            }
+        }
+        const u32 bal = __ballot_sync(kFullMask, bnd);
+        if (bal) {
+            u32 first = 0;
+            if (lane_id() == 0) first = atomicAdd(&ctr->n_boundary, (u32)__popc(bal));
+            first = __shfl_sync(kFullMask, first, 0);
+            if (bnd) {
+                const u32 id = first + __popc(bal & ((1u << lane_id()) - 1u));
+                if (id < bcap) { boundary_list[id] = v; seg_of_slot[pos] = id; }
+                else atomicOr(&ctr->errors, kErrInternal);
+            }
+        }
     }
 }
 

@@ -359,6 +359,12 @@ __host__ __device__ __forceinline__ u64 bucket_of(u64 h, u64 nbuckets) {
 #endif
 }
 
+// rank (GPU) that stores a k-mer: hash_map.hpp:28-30's get_target_rank with a supermer-preserving hash
+template <int W>
+__host__ __device__ __forceinline__ u32 owner_of(typename Slot<W>::value_t v, int world, int k, int m) {
+    return (u32)bucket_of(owner_hash_of<W>(v, k, m), (u64)world);
+}
+
 // Home bucket of a k-mer.  With locality (m != 0) the REGION -- kRegionBuckets consecutive buckets: one
 // 128-byte line of 16 slots for 64-bit slots, four lines of 32 slots for 128-bit slots -- is chosen by
 // the minimizer, and the bucket inside the region by the key itself: the members of a supermer spread

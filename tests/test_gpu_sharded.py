@@ -88,6 +88,30 @@ def test_sharded_medium():
     _run(51, 1_000_000, 9_500, 8, seed=8)
 
 
+@pytest.mark.parametrize("mode", ["0", "2"])
+@pytest.mark.parametrize("k,world", [(19, 1), (19, 2), (19, 5), (31, 3), (51, 2), (51, 8)])
+def test_owner_side_build_modes(monkeypatch, k, world, mode):
+    """KH_SHARD_BUILD: 0 = atomic insert of the received slot values, 2 = always the chunked shared-memory build
+    (default 1 picks it for shards larger than L2).  Same per-rank bytes either way."""
+    monkeypatch.setenv("KH_SHARD_BUILD", mode)
+    _run(k, 90000, 700, world, seed=20 + world)
+
+
+@pytest.mark.parametrize("pct", ["1", "40"])
+def test_owner_side_build_overflow_paths(monkeypatch, pct):
+    """Undersized grouping buffers (KH_DEBUG_CAP_PCT): values that do not fit go through the overflow fix-up,
+    which registers boundary starts exactly like the main path."""
+    monkeypatch.setenv("KH_SHARD_BUILD", "2")
+    monkeypatch.setenv("KH_DEBUG_CAP_PCT", pct)
+    _run(19, 120000, 900, 3, seed=31)
+    _run(51, 60000, 300, 2, seed=32)
+
+
+def test_owner_side_build_default_large_shard():
+    # shard tables of 160 MB: the default picks the chunked build
+    _run(19, 20_000_000, 190_000, 2, seed=33)
+
+
 def test_owner_function_mirror_matches_gpu():
     """cs267_hw3_b200.sharded.owner_of_slot (host mirror used for planning and the gloo tests) == the GPU's grouping."""
     import cs267_hw3_b200 as kh
@@ -148,10 +172,12 @@ def _run_raw(k, pairs, world, n_total):
             s.close()
 
 
+@pytest.mark.parametrize("mode", ["1", "2"])
 @pytest.mark.parametrize("world", [1, 4])
-def test_sharded_missing_successor_is_reported(world):
+def test_sharded_missing_successor_is_reported(monkeypatch, world, mode):
     # kmer_hash.cpp:47-49 -- drop one interior k-mer: the chain through it cannot be completed
     from cs267_hw3_b200 import sharded as sh
+    monkeypatch.setenv("KH_SHARD_BUILD", mode)
     k = 19
     d = kmergen.Dataset(k, 20000, 40, seed=9)
     pairs = d.pairs()
