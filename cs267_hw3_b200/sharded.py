@@ -544,16 +544,17 @@ def bench(args, k, n_total, c_total, longn, workload, rank, world, local_rank):
                           "traverse_phases_host_ms_rank0": {k2: v / args.steps for k2, v in phase_ms.items()}},
             "rank_rounds": evs[-1][3], "assembly_time_s": ms_total * 1e-3, "wall_s_timed_loop": wall, "gen_s": t_gen,
             "verified": verified,
-            "roofline": {"bound": "hbm", "kernel": "walk_sharded_kernel + insert_slots_direct_kernel (whole path)",
+            "roofline": {"bound": "hbm", "kernel": "whole path (walk_mig_kernel + build_chunks_kernel dominate on each GPU)",
                          "achieved": path_gbs, "peak": peak * world, "unit": "GB/s", "frac": path_gbs / (peak * world),
                          "traffic": None, "peak_source": peak_src + f" x {world} GPUs", "alg_bytes_per_kmer": alg,
-                         "nvlink_bytes_per_step": int(n_total * (world - 1) / world * (sb + 32)),
-                         "nvlink_note": "(P-1)/P of the slot values cross in the all-to-all and (P-1)/P of the successor "
-                                        "lookups read a 32-byte bucket from a peer"},
+                         "nvlink_bytes_per_step": int(n_total * (world - 1) / world * sb),
+                         "nvlink_note": "(P-1)/P of the slot values cross in the insert all-to-all; lookups never leave "
+                                        "the owner GPU (migrating walk) -- chain hand-overs (one 16/32-byte entry per "
+                                        "supermer boundary), pointer jumping and the contig text cross in addition"},
             "e2e": {"value": n_total / (e2e_ms_max * 1e-3), "unit": UNIT, "ms_per_step": e2e_ms_max,
                     "h2d_bytes_per_step": int(n_total * pb), "d2h_bytes_per_step": int(bytes_all),
                     "note": "each rank copies its block of records from pinned host memory and its contigs back"},
-            "gpu_launches": (12 + evs[-1][3]) * args.steps,
+            "gpu_launches": (23 + evs[-1][3]) * args.steps,      # per rank: 10 insert, 6 walk + links, rounds, 7 finish
             "clocks": clocks,
         }
     comm.close()
