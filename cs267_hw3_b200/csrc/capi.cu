@@ -722,7 +722,9 @@ int shard_phase_impl(kh_table* t, int phase, int* flag_out) {
     }
     case 1: {   // a batch of pointer-jumping rounds; stale peer reads are valid, so no barrier between them
         u32* flag = static_cast<u32*>(t->changed_flag.p);
-        const int batch = 4;
+        // chains of ~100 segments need 7 doubling rounds plus one that sees nothing move: the first batch is 8,
+        // so the common case costs ONE host round trip; longer chains add batches of 4
+        const int batch = t->stats.rank_rounds == 0 ? 8 : 4;
         for (int r = 0; r < batch; ++r) {
             KH_CUDA(t, cudaMemsetAsync(flag, 0, sizeof(u32), t->stream));
             if (t->shard_migrate)

@@ -258,6 +258,10 @@ class LocalComm:
     def any(self, flags: list[int]) -> bool:
         return any(flags)
 
+    def any_after_barrier(self, flags: list[int]) -> bool:
+        self.barrier()
+        return any(flags)
+
     def bits_or(self, bits: list[int]) -> int:
         out = 0
         for b in bits:
@@ -333,6 +337,11 @@ class TorchComm:
         self.dist.all_reduce(t, op=self.dist.ReduceOp.MAX)
         return bool(t.item() > 0)
 
+    def any_after_barrier(self, flags: list[int]) -> bool:
+        # the all-reduce is enqueued behind this rank's kernels and completes only when every rank has reached
+        # it in its own stream: it IS the barrier, no second collective needed
+        return self.any(flags)
+
     def bits_or(self, bits: list[int]) -> int:
         b = bits[0]
         t = self.torch.tensor([float((b >> i) & 1) for i in range(8)], device=self.dev)
@@ -389,13 +398,11 @@ def sharded_assemble(comm, max_rounds: int = 40, timings: dict | None = None) ->
         s.resolve(ptr, n)                                 # local lookup + one peer store into the sender's link
     comm.barrier()
     lap("links")
-    rounds = 0
-    while rounds < max_rounds:
-        moved = [s.phase(1) for s in shards]              # a batch of rounds, no barrier needed inside it
-        rounds += 4
-        comm.barrier()
-        if not comm.any(moved):
+    for _ in range(max_rounds):
+        moved = [s.phase(1) for s in shards]              # a batch of rounds (8, then 4), no barrier needed inside it
+        if not comm.any_after_barrier(moved):
             break
+    rounds = shards[0].tab.stats()["rank_rounds"]
     lap("rank_rounds")
     for ph in (2, 3, 4):                                  # lengths, tail claims, offsets: no barrier needed in between
         for s in shards:                                  # (lengths accepts tails another rank has already claimed)
