@@ -296,55 +296,6 @@ template <> __host__ __device__ __forceinline__ u64 minimizer_value<2>(u128 v, i
 // GPUs, and a shorter m-mer means a longer window, i.e. longer runs of k-mers that stay on one GPU.
 __host__ __device__ __forceinline__ int owner_minimizer_len(int k) { return k <= 14 ? k : 7; }
 
-// Running minimizer along a chain: the successor's m-mers are the current ones shifted left by one plus a new
-// rightmost one, so the minimizer only needs a full rescan when the old one falls off the left end.
-struct MinState {
-    int pos;        // position of the minimizer (0 = leftmost m-mer)
-    u32 g;          // its order value
-    u64 val;        // the m-mer
-};
-template <int W> __host__ __device__ __forceinline__ u64 rightmost_mmer(typename Slot<W>::value_t v, int m);
-template <> __host__ __device__ __forceinline__ u64 rightmost_mmer<1>(u64 v, int m) {
-    return (v >> 6) & ((m >= 32) ? ~0ull : ((1ull << (2 * m)) - 1ull));
-}
-template <> __host__ __device__ __forceinline__ u64 rightmost_mmer<2>(u128 v, int m) {
-    return ((v.lo >> 6) | (v.hi << 58)) & ((m >= 32) ? ~0ull : ((1ull << (2 * m)) - 1ull));
-}
-template <int W> __host__ __device__ __forceinline__ MinState min_scan(typename Slot<W>::value_t v, int k, int m);
-template <> __host__ __device__ __forceinline__ MinState min_scan<1>(u64 v, int k, int m) {
-    const u64 key = v >> 6, mask = (m >= 32) ? ~0ull : ((1ull << (2 * m)) - 1ull);
-    MinState st{0, 0xFFFFFFFFu, 0};
-    int pos = 0;
-    for (int s = 2 * (k - m); s >= 0; s -= 2, ++pos) {
-        const u64 x = (key >> s) & mask;
-        const u32 g = mmer_order(x);
-        if (g < st.g) { st.g = g; st.val = x; st.pos = pos; }
-    }
-    return st;
-}
-template <> __host__ __device__ __forceinline__ MinState min_scan<2>(u128 v, int k, int m) {
-    const u64 lo = (v.lo >> 6) | (v.hi << 58), hi = v.hi >> 6, mask = (m >= 32) ? ~0ull : ((1ull << (2 * m)) - 1ull);
-    MinState st{0, 0xFFFFFFFFu, 0};
-    int pos = 0;
-    for (int s = 2 * (k - m); s >= 0; s -= 2, ++pos) {
-        const u64 x = (s >= 64 ? (hi >> (s - 64)) : (s == 0 ? lo : ((lo >> s) | (hi << (64 - s))))) & mask;
-        const u32 g = mmer_order(x);
-        if (g < st.g) { st.g = g; st.val = x; st.pos = pos; }
-    }
-    return st;
-}
-// state of `next` (= current k-mer shifted by one base) from the state of the current k-mer
-template <int W>
-__host__ __device__ __forceinline__ MinState min_step(MinState st, typename Slot<W>::value_t next, int k, int m) {
-    if (st.pos == 0) return min_scan<W>(next, k, m);          // the old minimizer left the window
-    st.pos -= 1;
-    const u64 x = rightmost_mmer<W>(next, m);
-    const u32 g = mmer_order(x);
-    if (g < st.g) { st.g = g; st.val = x; st.pos = k - m; }   // strictly smaller: ties keep the leftmost
-    return st;
-}
-__host__ __device__ __forceinline__ u64 owner_hash_from_minimizer(u64 mval) { return fmix64(mval + 0x632BE59BD9B4E019ull); }
-
 // hash that selects the owning GPU, and hash that selects the home bucket (independent of each other)
 template <int W> __host__ __device__ __forceinline__ u64 owner_hash_of(typename Slot<W>::value_t v, int k, int m) {
     return m ? fmix64(minimizer_value<W>(v, k, m) + 0x632BE59BD9B4E019ull) : Slot<W>::owner_hash(v);
