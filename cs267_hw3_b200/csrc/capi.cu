@@ -174,8 +174,11 @@ __global__ void init_assemble_kernel(Counters* c, u32 first_overflow_seg) {
     for (int i = 0; i < 40; ++i) c->flags[i] = 0;
 }
 
+// from_record_staged reads whole aligned words around a record: keep 16 bytes behind every staging area
+constexpr size_t kStageSlack = 16;
+
 static size_t partition_smem(int W, u32 nparts, int pb) {
-    const size_t un = std::max<size_t>((size_t)kPartTile * (W == 1 ? 8 : 16), (size_t)kPartTile * pb);
+    const size_t un = std::max<size_t>((size_t)kPartTile * (W == 1 ? 8 : 16), (size_t)kPartTile * pb) + kStageSlack;
     return ((12 * (size_t)nparts + 2 * kPartTile + 15) & ~(size_t)15) + un;
 }
 
@@ -243,7 +246,7 @@ int insert_device_impl(kh_table* t, const unsigned char* recs, u64 n, bool recor
     }
     if (record_start) KH_CUDA(t, cudaEventRecord(t->ev[EV_INS0], t->stream));
     if (!part) {
-        insert_kernel<W><<<(unsigned)ntiles, kInsThreads, (size_t)kInsTile * t->pb, t->stream>>>(
+        insert_kernel<W><<<(unsigned)ntiles, kInsThreads, (size_t)kInsTile * t->pb + kStageSlack, t->stream>>>(
             recs, n, t->k, t->mlen, static_cast<V*>(t->table), t->nbuckets, static_cast<u32*>(t->mask.p),
             static_cast<u32*>(t->tile_counts.p), t->d_ctr);
     } else if (chunked) {
@@ -536,7 +539,7 @@ int shard_owner_partition_impl(kh_table* t, const unsigned char* recs, u64 n, co
     const u64 ntiles = (n + kInsTile - 1) / kInsTile;
     KH_CUDA(t, cudaEventRecord(t->ev[EV_INS0], t->stream));
     KH_CUDA(t, cudaMemsetAsync(octr, 0, 3 * kMaxRanks * sizeof(u64), t->stream));
-    owner_count_kernel<W><<<(unsigned)ntiles, kInsThreads, (size_t)kInsTile * t->pb, t->stream>>>(
+    owner_count_kernel<W><<<(unsigned)ntiles, kInsThreads, (size_t)kInsTile * t->pb + kStageSlack, t->stream>>>(
         recs, n, t->k, t->olen, world, static_cast<u32*>(t->mask.p), static_cast<u32*>(t->tile_counts.p), octr,
         static_cast<unsigned char*>(t->owner_byte.p), t->d_ctr);
     KH_CUDA(t, cudaGetLastError());
@@ -549,7 +552,7 @@ int shard_owner_partition_impl(kh_table* t, const unsigned char* recs, u64 n, co
     u64 base[kMaxRanks], run = 0;
     for (int w = 0; w < kMaxRanks; ++w) { base[w] = run; run += host_counts[w]; counts_out[w] = host_counts[w]; }
     KH_CUDA(t, cudaMemcpyAsync(octr + kMaxRanks, base, sizeof(base), cudaMemcpyHostToDevice, t->stream));
-    owner_scatter_kernel<W><<<(unsigned)ntiles, kInsThreads, (size_t)kInsTile * t->pb, t->stream>>>(
+    owner_scatter_kernel<W><<<(unsigned)ntiles, kInsThreads, (size_t)kInsTile * t->pb + kStageSlack, t->stream>>>(
         recs, n, t->k, static_cast<const unsigned char*>(t->owner_byte.p), world, octr + kMaxRanks, octr + 2 * kMaxRanks,
         static_cast<V*>(t->grouped.p));
     const u64 fresh = t->h_ctr->scan_total;

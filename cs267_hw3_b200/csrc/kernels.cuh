@@ -170,7 +170,7 @@ insert_kernel(const unsigned char* __restrict__ recs, u64 n, int k, int m,
         live[r] = j < cnt;
         bool ok = true;
         v[r] = S::zero();
-        if (live[r]) v[r] = S::from_record(s_rec + j * pb, k, pl, ok);
+        if (live[r]) v[r] = S::from_record_staged(s_rec + j * pb, k, pl, ok);
         if (!ok) { err |= kErrBadInput; live[r] = false; }
         b[r] = live[r] ? place_bucket<W>(v[r], k, m, nbuckets) : 0;
         if (live[r]) load256_cg(table + b[r] * S::kPerBucket, q[r]);      // 4 independent sector reads in flight
@@ -296,7 +296,7 @@ partition_kernel(const unsigned char* __restrict__ recs, u64 n, int k, int m, u6
         bool ok = true, live = j < cnt;
         pid[r] = 0xFFFFFFFFu;
         v[r] = S::zero();
-        if (live) v[r] = S::from_record(s_rec + j * pb, k, pl, ok);
+        if (live) v[r] = S::from_record_staged(s_rec + j * pb, k, pl, ok);
         if (!ok) { err |= kErrBadInput; live = false; }
         if (live) {
             pid[r] = (u32)(place_bucket<W>(v[r], k, m, nbuckets) >> part_shift);
@@ -457,20 +457,32 @@ subpartition_kernel(const typename Slot<W>::value_t* __restrict__ grouped, const
 constexpr int kBuildThreads = 512;
 constexpr int kBuildBatch = 4;          // records a thread fetches before it starts inserting (loads in flight)
 
+// Insert into the chunk in shared memory.  The whole bucket is read at once and the first empty slot is picked
+// without branches, then ONE ATOMS.CAS claims it; only a lost race (another thread took that slot meanwhile) or a full
+// bucket loops.  Probing slot by slot instead ran with ~7 of 32 lanes active and was 60 % of this kernel's issued
+// instructions.  Slots of a bucket fill in order and are never emptied, so every occupied slot precedes every empty one.
 template <int W>
 __device__ __forceinline__ int build_insert_one(typename Slot<W>::value_t* s_tab, u32 nb, u32 b, typename Slot<W>::value_t v) {
     typedef Slot<W> S;
+    typedef typename S::value_t V;
+    const unsigned s_base = (unsigned)__cvta_generic_to_shared(s_tab);
     while (b < nb) {
+        u64 q[4];
+        lds_bucket(s_base + b * 32u, q);
+        int j = -1;
+        bool dup = false;
 #pragma unroll
-        for (int j = 0; j < S::kPerBucket; ++j) {
-            typename S::value_t cur = S::load_shared(s_tab + b * S::kPerBucket + j);
-            if (S::empty(cur)) {
-                cur = S::cas_shared(s_tab + b * S::kPerBucket + j, S::zero(), v);
-                if (S::empty(cur)) return kInsInserted;
-            }
-            if (S::same_key(cur, v)) return kInsDuplicate;
+        for (int i = S::kPerBucket - 1; i >= 0; --i) {            // descending: the smallest empty index wins
+            const V c = S::from_bucket(q, i);
+            if (S::empty(c)) j = i;
+            else if (S::same_key(c, v)) dup = true;
         }
-        ++b;
+        if (dup) return kInsDuplicate;
+        if (j < 0) { ++b; continue; }                             // bucket full: linear probing, next bucket
+        const V old = S::cas_shared(s_tab + b * S::kPerBucket + j, S::zero(), v);
+        if (S::empty(old)) return kInsInserted;
+        if (S::same_key(old, v)) return kInsDuplicate;
+        // lost the slot to another thread: look at the bucket again
     }
     return kInsFull;                      // the probe sequence leaves the chunk
 }

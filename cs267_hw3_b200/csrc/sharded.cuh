@@ -67,7 +67,7 @@ owner_count_kernel(const unsigned char* __restrict__ recs, u64 n, int k, int mo,
         const u32 j = threadIdx.x + r * kInsThreads;
         bool live = j < cnt, ok = true;
         V v = S::zero();
-        if (live) v = S::from_record(s_rec + j * pb, k, pl, ok);
+        if (live) v = S::from_record_staged(s_rec + j * pb, k, pl, ok);
         if (!ok) { err |= kErrBadInput; live = false; }
         const u32 o = live ? owner_of<W>(v, world, k, mo) : 0u;
         if (j < cnt) owner_byte[rec0 + j] = live ? (unsigned char)o : (unsigned char)0xFF;
@@ -120,7 +120,7 @@ owner_scatter_kernel(const unsigned char* __restrict__ recs, u64 n, int k, const
         if (j < cnt) {
             const u32 o = owner_byte[rec0 + j];
             if (o < (u32)world) {
-                v[r] = S::from_record(s_rec + j * pb, k, pl, ok);
+                v[r] = S::from_record_staged(s_rec + j * pb, k, pl, ok);
                 own[r] = o;
                 rk[r] = atomicAdd(&s_cnt[o], 1u);
             }

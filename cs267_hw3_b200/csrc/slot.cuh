@@ -33,16 +33,40 @@ struct alignas(16) u128 {
     u64 lo, hi;
 };
 
+// Extension letter -> code, branch-free (a switch here diverges inside every record parse: it was ~24 % of
+// partition_kernel's issued instructions).  The low five bits of the letter index a table of 3-bit codes:
+// A(1)->0  C(3)->1  F(6)->4  G(7)->2  T(20)->3, kExtBad everywhere else.
+constexpr u64 ext_lut_entry(u64 lut, int idx, u64 code) { return (lut & ~(7ull << (3 * idx))) | (code << (3 * idx)); }
+constexpr u64 kExtLut = ext_lut_entry(ext_lut_entry(ext_lut_entry(ext_lut_entry(ext_lut_entry(
+                            0x7FFFFFFFFFFFFFFFull, 1, 0), 3, 1), 6, 4), 7, 2), 20, 3);
 __host__ __device__ __forceinline__ u32 ext_code(unsigned char c) {
-    switch (c) {
-    case 'A': return 0;
-    case 'C': return 1;
-    case 'G': return 2;
-    case 'T': return 3;
-    case 'F': return kExtF;
-    default: return kExtBad;
-    }
+    const u32 i = c & 31u;
+    const bool letter = (c & 0xE0u) == 0x40u && i <= 20u;
+    return letter ? ((u32)(kExtLut >> (3u * i)) & 7u) : kExtBad;
 }
+#ifdef __CUDACC__
+// Eight / sixteen bytes starting at an arbitrarily aligned SHARED-memory address, as big-endian integers (byte 0 most
+// significant), from aligned 32-bit loads + funnel shifts.  Reads up to 15 bytes past `p`'s last needed byte's word:
+// callers stage records with 16 bytes of slack behind them.
+__device__ __forceinline__ u64 lds_be64(const unsigned char* p) {
+    const uintptr_t a = reinterpret_cast<uintptr_t>(p);
+    const u32* w = reinterpret_cast<const u32*>(a & ~(uintptr_t)3);
+    const u32 sh = ((u32)a & 3u) * 8u;
+    const u32 w0 = w[0], w1 = w[1], w2 = w[2];
+    const u32 b0 = __funnelshift_r(w0, w1, sh), b1 = __funnelshift_r(w1, w2, sh);      // bytes 0-3, 4-7 (little-endian words)
+    return ((u64)__byte_perm(b0, 0, 0x0123) << 32) | (u64)__byte_perm(b1, 0, 0x0123);
+}
+__device__ __forceinline__ void lds_be128(const unsigned char* p, u64& hi, u64& lo) {
+    const uintptr_t a = reinterpret_cast<uintptr_t>(p);
+    const u32* w = reinterpret_cast<const u32*>(a & ~(uintptr_t)3);
+    const u32 sh = ((u32)a & 3u) * 8u;
+    const u32 w0 = w[0], w1 = w[1], w2 = w[2], w3 = w[3], w4 = w[4];
+    const u32 b0 = __funnelshift_r(w0, w1, sh), b1 = __funnelshift_r(w1, w2, sh);
+    const u32 b2 = __funnelshift_r(w2, w3, sh), b3 = __funnelshift_r(w3, w4, sh);
+    hi = ((u64)__byte_perm(b0, 0, 0x0123) << 32) | (u64)__byte_perm(b1, 0, 0x0123);
+    lo = ((u64)__byte_perm(b2, 0, 0x0123) << 32) | (u64)__byte_perm(b3, 0, 0x0123);
+}
+#endif
 __host__ __device__ __forceinline__ unsigned char ext_char(u32 code) {
     // "ACGTF" packed little-endian
     return (unsigned char)((0x4654474341ull >> (8 * code)) & 0xFF);
@@ -94,6 +118,12 @@ __device__ __forceinline__ u128 cas128(u128* addr, u128 cmp, u128 val) {    // A
     return old;
 }
 
+// one 32-byte bucket of a table chunk held in SHARED memory: two LDS.128, re-read on every call (other threads CAS it)
+__device__ __forceinline__ void lds_bucket(unsigned saddr, u64 (&q)[4]) {
+    asm volatile("ld.volatile.shared.v2.u64 {%0,%1}, [%2];" : "=l"(q[0]), "=l"(q[1]) : "r"(saddr) : "memory");
+    asm volatile("ld.volatile.shared.v2.u64 {%0,%1}, [%2+16];" : "=l"(q[2]), "=l"(q[3]) : "r"(saddr) : "memory");
+}
+
 // ---- slot traits -------------------------------------------------------------------------
 template <int W> struct Slot;
 
@@ -122,6 +152,16 @@ template <> struct Slot<1> {
         ok = (b != kExtBad) && (f != kExtBad);
         return (key << 6) | ((u64)(b & 7u) << 3) | (u64)((f + 1u) & 7u);
     }
+#ifdef __CUDACC__
+    // same, for a record staged in shared memory with >= 16 bytes of slack behind the staging area: the key comes
+    // from three aligned word loads instead of a byte loop (the top 2K bits of the big-endian bytes ARE the key)
+    static __device__ __forceinline__ value_t from_record_staged(const unsigned char* rec, int k, int pl, bool& ok) {
+        const u64 key = lds_be64(rec) >> (64 - 2 * k);
+        const u32 b = ext_code(rec[pl]), f = ext_code(rec[pl + 1]);
+        ok = (b != kExtBad) && (f != kExtBad);
+        return (key << 6) | ((u64)(b & 7u) << 3) | (u64)((f + 1u) & 7u);
+    }
+#endif
     // packed k-mer bytes (pkmer_t) -> key bits only (ext field 0)
     static __host__ __device__ __forceinline__ value_t from_packed(const unsigned char* p, int k, int pl) {
         u64 be = 0;
@@ -202,6 +242,17 @@ template <> struct Slot<2> {
         v.lo |= ((u64)(b & 7u) << 3) | (u64)((f + 1u) & 7u);
         return v;
     }
+#ifdef __CUDACC__
+    static __device__ __forceinline__ value_t from_record_staged(const unsigned char* rec, int k, int pl, bool& ok) {
+        u64 hi, lo;
+        lds_be128(rec, hi, lo);
+        u128 v = shr(u128{lo, hi}, 122 - 2 * k);        // key << 6; 0 <= 122 - 2K <= 62 for 30 <= K <= 61
+        const u32 b = ext_code(rec[pl]), f = ext_code(rec[pl + 1]);
+        ok = (b != kExtBad) && (f != kExtBad);
+        v.lo = (v.lo & ~63ull) | ((u64)(b & 7u) << 3) | (u64)((f + 1u) & 7u);
+        return v;
+    }
+#endif
     static __host__ __device__ __forceinline__ value_t from_packed(const unsigned char* p, int k, int pl) {
         return shl(shr(be_bytes(p, pl), 8 * pl - 2 * k), 6);
     }
