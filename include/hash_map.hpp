@@ -16,6 +16,7 @@
 #include <string>
 #include <vector>
 
+#include "kh/stream_reader.hpp"
 #include "kh_capi.h"
 #include "kmer_t.hpp"
 
@@ -52,6 +53,22 @@ class DistributedHashMap {
     // which the reference does right after insert_all (kmer_hash.cpp:27-31).
     void insert_all(const std::vector<kmer_pair>& items) { insert_all(items.data(), items.size()); }
     void insert_all(const kmer_pair* items, size_t n) { check(kh_insert_pairs(table_, items, n), "insert_all"); }
+
+    // read_kmers (read_kmers.hpp:54-79) + insert_all fused and streamed: lines [first_line, first_line + n_lines) of
+    // the file go through a ring of pinned chunk buffers straight into kh_insert_lines (K1 pack + K2 insert on the
+    // GPU) while a background thread reads the next chunk (kh/stream_reader.hpp).  Table, start-node order and hence
+    // the output are those of read_kmers + insert_all on the same lines.  Returns the number of lines inserted.
+    size_t insert_file(const std::string& fname, size_t first_line, size_t n_lines, const kh_stream::Options& opt = {}) {
+        return kh_stream::for_each_chunk(
+            fname, KMER_LEN, first_line, n_lines, opt,
+            [this](size_t bytes) {
+                void* p = nullptr;
+                check(kh_host_alloc(&p, bytes), "pinned chunk buffer");
+                return p;
+            },
+            [](void* p) { kh_host_free(p); },
+            [this](const char* text, size_t n, size_t) { check(kh_insert_lines(table_, text, n), "insert_file"); });
+    }
 
     // hash_map.hpp:83-107.  The key is the k-mer as a string of KMER_LEN letters.
     bool find(const std::string& key, kmer_pair& result) {

@@ -18,6 +18,10 @@
 //                                                   exactly like the reference's std::vector<kmer_pair>)
 //   assemble_contigs (timed, :135)               -> kh_assemble       (contigs end in HOST memory)
 //   output_results (untimed, :147)               -> one fwrite of the contig text
+//
+// KH_STREAM=1 (single rank): the file is not read up front; DistributedHashMap::insert_file streams it through pinned
+// chunk buffers into the GPU pack + insert while a background thread reads ahead (kh/stream_reader.hpp).  The
+// "insert" time then INCLUDES reading and parsing the file, which the reference leaves outside its timer.
 #include <chrono>
 #include <cstdio>
 #include <cstdlib>
@@ -150,12 +154,24 @@ int main(int argc, char** argv) {
     DistributedHashMap hashmap(hash_table_size, rank_id, 1);
     kh_table* t = hashmap.handle();
 
-    kmer_pair* kmers = read_and_pack(t, kmer_fname, n_kmers);
-    if (run_type == "verbose") BUtil::print("Finished reading kmers.\n");
+    bool stream = false;
+    if (const char* e = std::getenv("KH_STREAM")) stream = std::atoi(e) != 0;
+    kmer_pair* kmers = nullptr;
+    if (!stream) {
+        kmers = read_and_pack(t, kmer_fname, n_kmers);
+        if (run_type == "verbose") BUtil::print("Finished reading kmers.\n");
+    }
     must(kh_sync(t), t, "sync");
 
     const auto start_time = clock::now();
-    hashmap.insert_all(kmers, n_kmers);                        // initialize_kmers
+    if (stream) {
+        kh_stream::Options opt;
+        if (const char* e = std::getenv("KH_STREAM_CHUNK_LINES")) opt.chunk_lines = std::strtoull(e, nullptr, 10);
+        hashmap.insert_file(kmer_fname, 0, n_kmers, opt);      // read_kmers + initialize_kmers, overlapped
+        if (run_type == "verbose") BUtil::print("Finished reading kmers.\n");
+    } else {
+        hashmap.insert_all(kmers, n_kmers);                    // initialize_kmers
+    }
     hashmap.process_requests();
     const auto insert_time = clock::now();
 
@@ -185,6 +201,6 @@ int main(int argc, char** argv) {
                      "(%lf read, %lf insert, %lf total)\n",
                      rank_id, (int)n_contigs, (int)n_nodes, 0, assembly_duration, insert_duration, total_duration);
     }
-    kh_host_free(kmers);
+    if (kmers) kh_host_free(kmers);
     return 0;
 }

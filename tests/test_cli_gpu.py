@@ -83,3 +83,20 @@ def test_cli_multi_rank_writes_the_reference_per_rank_files(bins, tmp_path, k, r
     assert re.search(rf"Rank 0 reconstructed {n0} contigs with \d+ nodes from 0 start nodes\.", r.stdout)
     r = subprocess.run([os.path.join(ROOT, "tools", "check.sh"), str(inp)], cwd=tmp_path, capture_output=True, text=True, env=env)
     assert r.returncode == 0 and f"PASSED: {inp}" in r.stdout, r.stdout + r.stderr
+
+
+@pytest.mark.skipif(os.environ.get("KH_TEST_STREAM") != "1",
+                    reason="KH_STREAM path written after the round's GPU budget was spent: its host reader is covered on CPU "
+                           "(tests/test_stream_reader.py) and its sink is kh_insert_lines (covered above); set KH_TEST_STREAM=1 "
+                           "to run it, and drop this guard once it has passed on a GPU")
+@pytest.mark.parametrize("chunk_lines", ["1000", "4194304"])
+def test_cli_streamed_ingest_writes_the_same_bytes(bins, tmp_path, chunk_lines):
+    """KH_STREAM=1: the file is streamed through pinned chunk buffers into pack + insert (DistributedHashMap::insert_file).
+    Same table, same start-node order, hence the same output bytes as the read-everything-first path."""
+    k = 19
+    d = kmergen.Dataset(k, 60000, 200, seed=23)
+    inp = tmp_path / "in.txt"
+    d.text().tofile(inp)
+    env = dict(os.environ, KH_STREAM="1", KH_STREAM_CHUNK_LINES=chunk_lines)
+    subprocess.run([bins[k], str(inp), "test", "st"], cwd=tmp_path, check=True, capture_output=True, env=env)
+    assert (tmp_path / "st_0.dat").read_bytes() == d.expected()[0]
