@@ -424,7 +424,6 @@ def sharded_assemble(comm, max_rounds: int = 40, timings: dict | None = None) ->
 def bench(args, k, n_total, c_total, longn, workload, rank, world, local_rank):
     """Strong scaling of the N=1 workload: the same synthetic file, block-partitioned over the ranks
     (read_kmers.hpp:55-58), table hash-sharded over the GPUs."""
-    import json
     import time
 
     import torch

@@ -6,10 +6,8 @@ import re
 import subprocess
 import tempfile
 
-import numpy as np
 import pytest
 
-import oracle
 from conftest import ROOT
 
 INCLUDE = os.path.join(ROOT, "include")
