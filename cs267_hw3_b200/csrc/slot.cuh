@@ -385,6 +385,113 @@ __host__ __device__ __forceinline__ u64 place_bucket(typename Slot<W>::value_t v
     return place_bucket_from<W>(fmix64(minimizer_value<W>(v, k, m) + 0x632BE59BD9B4E019ull), v, nbuckets);
 }
 
+// =============================================================================================
+// Chunk table ("ctable", ctable.cuh): placement by minimizer at CHUNK granularity
+// =============================================================================================
+// The home CHUNK of a k-mer -- a run of buckets that one thread block builds in shared memory -- is a hash of
+// the k-mer's minimizer; the bucket inside the chunk is a hash of the key.  Consecutive k-mers of a contig
+// share their minimizer for a "supermer" (~(w+1)/2 k-mers for a window of w m-mers), so they live in the same
+// chunk and their successor links are followed in shared memory while the chunk is built; only one lookup per
+// supermer ever goes to HBM (tools/probes/chunk_placement_sim.cpp is the CPU gate for balance and run length).
+//
+// The minimizer is the m-mer (m <= 16, so it fits 32 bits) with the smallest value of (x ^ seed) * odd among
+// the `win` RIGHTMOST m-mers of the k-mer (win <= 32); that value is a bijection of the m-mer, so the minimum
+// itself identifies the minimizer and is what gets hashed.
+constexpr u32 kIdxBits = 14;                     // top bits of a ctable slot: 1 + index of the segment that STARTS at this k-mer (0: none)
+constexpr u32 kMinSeed = 0x5BD1E995u;
+constexpr u32 kMinMul = 0x9E3779B1u;
+
+__host__ __device__ __forceinline__ int ct_minimizer_len(int k) { return k >= 31 ? 15 : (k >= 23 ? 13 : (k >= 17 ? k - 6 : k)); }
+__host__ __device__ __forceinline__ int ct_window(int k) { const int w = k - ct_minimizer_len(k) + 1; return w > 32 ? 32 : w; }
+// K range the chunk table supports: the slot must have kIdxBits spare bits above the key, and the window must be worth it
+__host__ __device__ __forceinline__ bool ct_supported(int k) { return k >= 17 && k <= 54; }
+__host__ __device__ __forceinline__ int ct_slot_words(int k) { return (2 * k + 6 + (int)kIdxBits <= 64) ? 1 : 2; }
+
+__host__ __device__ __forceinline__ u32 ct_funnel_r(u32 lo, u32 hi, u32 s) {          // bits [s, s+32) of hi:lo, 0 <= s < 32
+#ifdef __CUDA_ARCH__
+    return __funnelshift_r(lo, hi, s);
+#else
+    return s ? ((lo >> s) | (hi << (32 - s))) : lo;
+#endif
+}
+// key words: a = bits 0..31 of the key (the LAST bases), b, c, d the following 32-bit words
+__host__ __device__ __forceinline__ u32 ct_min_hash_words(u32 a, u32 b, u32 c, u32 d, int m, int win) {
+    const u32 mmask = (m >= 16) ? 0xFFFFFFFFu : ((1u << (2 * m)) - 1u);
+    u32 best = 0xFFFFFFFFu;
+    int rem = win;
+    for (int it = 0; it < 2; ++it) {
+#pragma unroll
+        for (int j = 0; j < 16; ++j) {
+            const u32 x = ct_funnel_r(a, b, 2u * j) & mmask;
+            u32 h = (x ^ kMinSeed) * kMinMul;
+            h = (j < rem) ? h : 0xFFFFFFFFu;
+            best = h < best ? h : best;
+        }
+        if (rem <= 16) break;
+        rem -= 16; a = b; b = c; c = d; d = 0;
+    }
+    return best;
+}
+template <int W> __host__ __device__ __forceinline__ u32 ct_min_hash(typename Slot<W>::value_t v, int m, int win);
+template <> __host__ __device__ __forceinline__ u32 ct_min_hash<1>(u64 v, int m, int win) {      // v: key << 6, no index bits
+    const u64 key = v >> 6;
+    return ct_min_hash_words((u32)key, (u32)(key >> 32), 0u, 0u, m, win);
+}
+template <> __host__ __device__ __forceinline__ u32 ct_min_hash<2>(u128 v, int m, int win) {
+    const u64 lo = (v.lo >> 6) | (v.hi << 58), hi = v.hi >> 6;
+    return ct_min_hash_words((u32)lo, (u32)(lo >> 32), (u32)hi, (u32)(hi >> 32), m, win);
+}
+
+// slot helpers that know about the index bits
+template <int W> struct CtSlot;
+template <> struct CtSlot<1> {
+    typedef u64 V;
+    static __host__ __device__ __forceinline__ V strip(V v) { return v & (~0ull >> kIdxBits); }
+    static __host__ __device__ __forceinline__ u32 idx(V v) { return (u32)(v >> (64 - kIdxBits)); }
+    static __host__ __device__ __forceinline__ V with_idx(V v, u32 i) { return strip(v) | ((u64)i << (64 - kIdxBits)); }
+    static __host__ __device__ __forceinline__ bool same_key(V a, V b) { return (((a ^ b) << kIdxBits) >> (kIdxBits + 6)) == 0ull; }
+    static __host__ __device__ __forceinline__ u32 hash32(V key) { return (u32)(fmix64(key >> 6) >> 32); }      // key: stripped
+};
+template <> struct CtSlot<2> {
+    typedef u128 V;
+    static __host__ __device__ __forceinline__ V strip(V v) { return u128{v.lo, v.hi & (~0ull >> kIdxBits)}; }
+    static __host__ __device__ __forceinline__ u32 idx(V v) { return (u32)(v.hi >> (64 - kIdxBits)); }
+    static __host__ __device__ __forceinline__ V with_idx(V v, u32 i) { return u128{v.lo, (v.hi & (~0ull >> kIdxBits)) | ((u64)i << (64 - kIdxBits))}; }
+    static __host__ __device__ __forceinline__ bool same_key(V a, V b) { return (((a.hi ^ b.hi) << kIdxBits) | ((a.lo ^ b.lo) >> 6)) == 0ull; }
+    static __host__ __device__ __forceinline__ u32 hash32(V key) {
+        return (u32)(fmix64((key.lo >> 6) ^ (key.hi * 0x9E3779B97F4A7C15ull) ^ (key.hi >> 29)) >> 32);
+    }
+};
+// bucket inside a chunk of nb buckets
+__host__ __device__ __forceinline__ u32 ct_bucket_in_chunk(u32 h32, u32 nb) { return (u32)(((u64)h32 * nb) >> 32); }
+
+// chunk geometry shared by host and device
+struct CtGeom {
+    int k, m, win;
+    int world, rank;
+    u32 chunks_per_rank;        // C
+    u32 cpr_shift;              // a region = 2^cpr_shift chunks (the unit of the first grouping pass)
+    u32 regions_per_rank;       // R = ceil(C / 2^cpr_shift);  world * R <= kCtMaxRegions
+    u32 max_buckets;            // buckets a chunk may have (shared-memory budget of the build kernel)
+    u32 lf_inv_q16;             // 65536 / load factor
+};
+constexpr u32 kCtMaxRegions = 1024;
+// minimizer hash -> (owner rank, local chunk) without a division: h * world = owner . fraction, fraction * C = chunk
+__host__ __device__ __forceinline__ void ct_place(u32 minhash, const CtGeom& g, u32& owner, u32& chunk) {
+    const u64 h = fmix64((u64)minhash + 0x632BE59BD9B4E019ull);
+#ifdef __CUDA_ARCH__
+    owner = (u32)__umul64hi(h, (u64)g.world);
+    chunk = (u32)__umul64hi(h * (u64)g.world, (u64)g.chunks_per_rank);
+#else
+    owner = (u32)(((unsigned __int128)h * (u64)g.world) >> 64);
+    chunk = (u32)(((unsigned __int128)(h * (u64)g.world) * (u64)g.chunks_per_rank) >> 64);
+#endif
+}
+
+constexpr u32 kLinkMissing = 0xFFFFFFFBu;   // ctable: the successor k-mer is in no table (raised only if a start-rooted contig ends here)
+constexpr u32 kLinkConverge = 0xFFFFFFFAu;  // ctable: the successor k-mer sits in the middle of another segment (it has two predecessors)
+constexpr u32 kLinkCtFirstMarker = kLinkConverge;
+
 // Error bits accumulated on the device (Counters::errors)
 enum : u32 {
     kErrNotFound = 1u, kErrTableFull = 2u, kErrCycle = 4u, kErrBadInput = 8u,
@@ -410,6 +517,7 @@ struct Counters {
     u32 n_boundary;       // sharded: nodes of this shard whose predecessor lives on another GPU (walker starts)
     u32 n_outbox;         // sharded: pending links produced by the local walk
     u32 flags[40];
+    u64 n_starts_dev;     // ctable: start nodes registered so far (kept on the device: no host round trip per insert)
 };
 
 }  // namespace kh

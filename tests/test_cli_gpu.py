@@ -85,10 +85,6 @@ def test_cli_multi_rank_writes_the_reference_per_rank_files(bins, tmp_path, k, r
     assert r.returncode == 0 and f"PASSED: {inp}" in r.stdout, r.stdout + r.stderr
 
 
-@pytest.mark.skipif(os.environ.get("KH_TEST_STREAM") != "1",
-                    reason="KH_STREAM path written after the round's GPU budget was spent: its host reader is covered on CPU "
-                           "(tests/test_stream_reader.py) and its sink is kh_insert_lines (covered above); set KH_TEST_STREAM=1 "
-                           "to run it, and drop this guard once it has passed on a GPU")
 @pytest.mark.parametrize("chunk_lines", ["1000", "4194304"])
 def test_cli_streamed_ingest_writes_the_same_bytes(bins, tmp_path, chunk_lines):
     """KH_STREAM=1: the file is streamed through pinned chunk buffers into pack + insert (DistributedHashMap::insert_file).
