@@ -5,8 +5,10 @@
 
 A "step" is one pass of the hot path over one batch of synthetic input: empty table ->
 insert every k-mer + find the start nodes -> walk every contig -> contig text materialised.
-At N=1 the workload is BASELINE.json configs[1]: the human-chr14 shape re-cut at K=19
-(89 710 742 unique 19-mers in 860 329 contigs, 64-bit keys), synthetic (tools/kmer_gen.cpp).
+The workload is BASELINE.json configs[2]/[3]: the human-chr14 shape at K=51 (89 710 742 unique 51-mers in
+860 329 contigs, 4 934 090 810 bytes of text, 128-bit slots), synthetic (tools/kmer_gen.cpp), the same file at
+every N (strong scaling).  configs[1] (the same shape re-cut at K=19, 64-bit slots) is measured in the same run
+and reported under "shapes".
 
 One JSON line on stdout (rank 0); see README/DESIGN.md for the keys.  `value` has the packed
 records resident in HBM when the clock starts (as the reference has them resident in host RAM);
@@ -201,34 +203,36 @@ def cpu_baseline_leg(k: int, workload: str, budget_s: float = 20.0) -> dict:
 
 
 # ------------------------------------------------------------------ B200 arm --------------
-def run_b200_arm(args, k: int, workload: str) -> dict | None:
+def ncu_traffic_for(kernel_substr: str, workload: str):
+    """DRAM bytes (read + write) per launch of a kernel from this round's committed ncu --set full capture of the same
+    bench command (profiles/r02_ncu_full_summary_<workload>.csv); None if there is none."""
+    import csv
+    p = os.path.join(ROOT, "profiles", f"r02_ncu_full_summary_{workload}.csv")
+    try:
+        rows = list(csv.reader(open(p)))
+        h, units = rows[0], rows[1]
+        ir, iw, ik = h.index("dram__bytes_read.sum"), h.index("dram__bytes_write.sum"), h.index("Kernel Name")
+        scale = {"Gbyte": 1e9, "Mbyte": 1e6, "Kbyte": 1e3, "byte": 1.0}
+        for r in rows[2:]:
+            if kernel_substr in r[ik]:
+                return float(r[ir]) * scale.get(units[ir], 1e9) + float(r[iw]) * scale.get(units[iw], 1e9), p
+    except Exception:
+        pass
+    return None, None
+
+
+def measure_shape_n1(args, workload: str, steps: int, warmup: int, local_rank: int, full: bool) -> dict:
+    """One workload on one GPU: `steps` timed steps with the records resident in HBM, then the host-buffer leg."""
     import torch
-    import torch.distributed as dist
 
     import cs267_hw3_b200 as kh
     from tools import kmergen
 
-    world = int(os.environ.get("WORLD_SIZE", "1"))
-    rank = int(os.environ.get("RANK", "0"))
-    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
-    if not torch.cuda.is_available() or kh.device_count() < 1:
-        raise RuntimeError("bench.py: no CUDA device; the B200 arm has no CPU fallback")
-    torch.cuda.set_device(local_rank)
-    if world > 1:
-        os.environ["NCCL_DEBUG"] = "WARN"      # the VERSION banner would land on stdout next to the JSON line
-        dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
-    if world != args.gpus:
-        raise RuntimeError(f"--gpus {args.gpus} but WORLD_SIZE={world}: launch with torch.distributed.run")
-
-    _, n, c, longn = WORKLOADS[workload]
+    k, n, c, longn = WORKLOADS[workload]
     if args.n:
         c = max(1, int(round(args.n * c / n)))
         n = args.n
     pb = kh.pair_bytes(k)
-    if world > 1:
-        from cs267_hw3_b200 import sharded
-        return sharded.bench(args, k, n, c, longn, workload, rank, world, local_rank)
-
     t_gen = time.time()
     data = kmergen.Dataset(k, n, c, seed=SEED, long_nodes=longn)
     host = kh.PinnedBuffer(n * pb)
@@ -263,12 +267,14 @@ def run_b200_arm(args, k: int, workload: str) -> dict | None:
 
     sampler = ClockSampler(local_rank)      # sampled over warm-up + timed steps (the timed loop alone is < 0.1 s)
     sampler.start()
-    for _ in range(args.warmup):
+    for _ in range(warmup):
         step_resident()
     torch.cuda.synchronize()
+    launches0 = tab.stats()["n_launches"]
     wall0 = time.perf_counter()
-    evs, stage = [], {"ms_insert": [], "ms_walk": [], "ms_rank": [], "ms_emit": [], "ms_clear": []}
-    for _ in range(args.steps):
+    keys = ["ms_insert", "ms_stage", "ms_build", "ms_walk", "ms_rank", "ms_emit", "ms_clear"]
+    evs, stage = [], {key: [] for key in keys}
+    for _ in range(steps):
         e0, e1, out = step_resident()
         evs.append((e0, e1))
         st = tab.stats()
@@ -276,104 +282,166 @@ def run_b200_arm(args, k: int, workload: str) -> dict | None:
             stage[key].append(st[key])
     torch.cuda.synchronize()
     wall = time.perf_counter() - wall0
+    launches = tab.stats()["n_launches"] - launches0
     clocks = sampler.stop()
     ms = [a.elapsed_time(b) for a, b in evs]
     ms_per_step = float(np.mean(ms))
     _, _, n_contigs, contig_bytes, n_nodes = out
+    st_last = tab.stats()
 
-    # correctness gate: re-run the traversal of the last timed step into host memory and compare the
-    # contig set with the generator's own solution (order-independent digest) + node/contig counts
+    # correctness gate: re-run the traversal into host memory and compare the contig set with the generator's own
+    # solution (order-independent digest) + node/contig counts
     buf, offs, nodes = tab.assemble(copy=False)
     verified = bool(n_nodes == n and n_contigs == c and nodes == n and kmergen.digest_lines(buf) == exp_digest)
 
-    # end-to-end through host buffers
-    for _ in range(0 if args.no_e2e else min(args.warmup, 2)):
-        step_e2e()
-    torch.cuda.synchronize()
-    e2e_ms = []
-    for _ in range(1 if args.no_e2e else max(1, min(args.steps, 5))):
-        e0, e1, (buf, offs, nodes) = step_e2e()
+    # end to end through host buffers: kh_insert_pairs (pinned records, chunked H2D overlapped with the staging
+    # kernels) + kh_assemble (contigs copied back to pinned host memory)
+    e2e = None
+    if not args.no_e2e:
+        for _ in range(min(warmup, 2)):
+            step_e2e()
         torch.cuda.synchronize()
-        e2e_ms.append(e0.elapsed_time(e1))
-    e2e_ms_mean = float(np.mean(e2e_ms))
-    verified = verified and bool(nodes == n and kmergen.digest_lines(buf) == exp_digest)
+        e2e_ms = []
+        for _ in range(max(1, min(steps, 5))):
+            e0, e1, (buf, offs, nodes) = step_e2e()
+            torch.cuda.synchronize()
+            e2e_ms.append(e0.elapsed_time(e1))
+        e2e_ms_mean = float(np.mean(e2e_ms))
+        verified = verified and bool(nodes == n and kmergen.digest_lines(buf) == exp_digest)
+        e2e = {"value": n / (e2e_ms_mean * 1e-3), "unit": UNIT, "ms_per_step": e2e_ms_mean,
+               "h2d_bytes_per_step": n * pb, "d2h_bytes_per_step": int(contig_bytes + 8 * (n_contigs + 1))}
 
     # K1 (north star item a): text lines -> kmer_pair records on the GPU, device-resident text, bounded sample
     pack = None
-    try:
-        n_pack = min(n, 16_000_000)
-        text = torch.from_numpy(data.text(0, n_pack)).cuda()
-        packed = torch.empty(n_pack * pb, dtype=torch.uint8, device="cuda")
-        for _ in range(2):
-            tab.pack_lines_device(text.data_ptr(), n_pack, packed.data_ptr())
-        p0, p1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-        p0.record(stream)
-        for _ in range(5):
-            tab.pack_lines_device(text.data_ptr(), n_pack, packed.data_ptr())
-        p1.record(stream)
-        torch.cuda.synchronize()
-        pms = p0.elapsed_time(p1) / 5
-        same = bool(np.array_equal(packed.cpu().numpy(), host.array[: n_pack * pb]))
-        pack = {"lines": n_pack, "ms": pms, "lines_per_s": n_pack / (pms * 1e-3),
-                "gbs": n_pack * (k + 4 + pb) / (pms * 1e-3) / 1e9, "matches_generator_records": same}
-        del text, packed
-    except Exception as e:          # secondary number: never fail the bench line over it
-        pack = {"error": str(e)}
+    if full:
+        try:
+            n_pack = min(n, 16_000_000)
+            text = torch.from_numpy(data.text(0, n_pack)).cuda()
+            packed = torch.empty(n_pack * pb, dtype=torch.uint8, device="cuda")
+            for _ in range(2):
+                tab.pack_lines_device(text.data_ptr(), n_pack, packed.data_ptr())
+            p0, p1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            p0.record(stream)
+            for _ in range(5):
+                tab.pack_lines_device(text.data_ptr(), n_pack, packed.data_ptr())
+            p1.record(stream)
+            torch.cuda.synchronize()
+            pms = p0.elapsed_time(p1) / 5
+            same = bool(np.array_equal(packed.cpu().numpy(), host.array[: n_pack * pb]))
+            pack = {"lines": n_pack, "ms": pms, "lines_per_s": n_pack / (pms * 1e-3),
+                    "gbs": n_pack * (k + 4 + pb) / (pms * 1e-3) / 1e9, "matches_generator_records": same}
+            del text, packed
+        except Exception as e:          # secondary number: never fail the bench line over it
+            pack = {"error": str(e)}
 
     peak, peak_src = measured_peak_gbs()
     alg = alg_bytes_per_kmer(k)
-    m_ins, m_walk = float(np.mean(stage["ms_insert"])), float(np.mean(stage["ms_walk"]))
-    # The insert stage is three kernels (partition, subpartition, build_chunks: ~0.8/0.75/1.2 ms), so the single
-    # dominant kernel of the step is walk_kernel; its duration is the CUDA-event time of the walk stage.
-    dom, dom_ms, dom_bytes = "walk_kernel", m_walk, n * (alg["lookup"] + alg["output"])
-    traffic = ncu_traffic_bytes("walk_kernel") if workload == "chr14_k19" and not args.n else None
+    sm = {k2: float(np.mean(v)) for k2, v in stage.items()}
+    chunk_table = sm["ms_build"] > 0
+    if chunk_table:
+        # The step's dominant kernel is ct_build_kernel: it inserts every k-mer (one table sector read + written back:
+        # 64 B), follows every successor link (the 32-B lookup, served from shared memory) and produces the contig
+        # characters (1 B) -- SURVEY.md 8(d)'s B_alg minus the record read, which belongs to ct_stage_kernel.
+        dom, dom_ms, dom_bytes = "ct_build_kernel", sm["ms_build"], n * (alg["insert"] + alg["lookup"] + alg["output"])
+    else:
+        dom, dom_ms, dom_bytes = "walk_kernel", sm["ms_walk"], n * (alg["lookup"] + alg["output"])
+    traffic, traffic_src = ncu_traffic_for(dom, workload) if not args.n else (None, None)
     achieved = dom_bytes / (dom_ms * 1e-3) / 1e9
     path_gbs = n * alg["total"] / (ms_per_step * 1e-3) / 1e9
-    try:
-        r_rand = kh.random_sector_rate(local_rank, 1434 << 20, 1 << 28)     # footprint = this workload's table
-    except Exception:
-        r_rand = None
-    line = {
-        "metric": METRIC, "value": n / (ms_per_step * 1e-3), "unit": UNIT, "n_gpus": 1,
-        "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms_per_step, "higher_is_better": True,
-        "scaling": "weak", "vs_baseline": None, "dtype": "u64" if k <= 29 else "u128", "data": "synthetic",
-        "config": {"workload": workload, "k": k, "n_kmers": n, "n_contigs": c, "load_factor": args.load_factor,
-                   "seed": SEED, "l2": "inputs (records + table) far larger than L2; table re-zeroed between steps",
+    slot_b = st_last["slot_bits"] // 8
+    out = {
+        "ms_per_step": ms_per_step, "value": n / (ms_per_step * 1e-3), "ms_each_step": ms,
+        "config": {"workload": workload, "k": k, "n_kmers": n, "n_contigs": c, "load_factor": args.load_factor, "seed": SEED,
+                   "table": ("chunk table (csrc/ctable.cuh): staged by region, built + contracted per chunk in shared memory"
+                             if chunk_table else "plain open-addressing table"),
+                   "slot_bytes": slot_b,
+                   "l2": "inputs (records, staging buffers, table) far larger than L2; every step starts from an empty table",
                    "table_clear": "between steps, outside the per-step event pair (the reference constructs its map "
                                   "before its timer, kmer_hash.cpp:119-129); ms_clear reported in stages",
                    "timing": "CUDA events on the launching stream around each step, mean of steps"},
-        "stages_ms": {k2: float(np.mean(v)) for k2, v in stage.items()},
-        "assembly_time_s": ms_per_step * 1e-3,
-        "wall_s_timed_loop": wall, "gen_s": t_gen, "verified": verified,
+        "stages_ms": dict(sm, ms_seal_and_links_etc=None) if False else sm,
+        "n_segments": int(st_last["n_segments"]), "rank_rounds": int(st_last["rank_rounds"]),
+        "assembly_time_s": ms_per_step * 1e-3, "wall_s_timed_loop": wall, "gen_s": t_gen, "verified": verified,
         "roofline": {"bound": "hbm", "kernel": dom, "achieved": achieved, "peak": peak, "unit": "GB/s",
                      "frac": achieved / peak, "traffic": traffic,
-                     "traffic_source": "dram__bytes_read.sum + dram__bytes_write.sum, one ncu --set full capture "
-                                       "(profiles/r01_final_ncu_full_summary.csv)" if traffic else None,
+                     "traffic_source": ("dram__bytes_read.sum + dram__bytes_write.sum per launch, ncu --set full capture of this "
+                                        "command: " + os.path.relpath(traffic_src, ROOT)) if traffic else None,
                      "peak_source": peak_src,
-                     "insert_stage": {"kernels": "partition_kernel + subpartition_kernel + build_chunks_kernel",
-                                      "ms": m_ins, "achieved": n * (alg["record"] + alg["insert"]) / (m_ins * 1e-3) / 1e9,
-                                      "frac": n * (alg["record"] + alg["insert"]) / (m_ins * 1e-3) / 1e9 / peak},
-                     "random_access_ceiling": {"lookups_per_s": n / (m_walk * 1e-3),
-                                               "measured_random_32B_reads_per_s": r_rand,
-                                               "frac": (n / (m_walk * 1e-3)) / r_rand if r_rand else None},
+                     "units_per_launch": n, "alg_bytes_per_unit": dom_bytes // n, "kernel_ms": dom_ms,
                      "alg_bytes_per_kmer": alg,
+                     "insert_stage": {"kernels": "ct_stage + ct_scatter + ct_layout + ct_build (the build also does the traverse's lookups)"
+                                      if chunk_table else "partition + subpartition + build_chunks / insert_slots",
+                                      "ms": sm["ms_insert"]},
                      "path": {"achieved": path_gbs, "frac": path_gbs / peak,
                               "note": "N x B_alg / t(insert+traverse), SURVEY.md 8(d)"},
                      "probes_per_s": 2 * n / (ms_per_step * 1e-3),
-                     "sector_ceiling_per_s": peak * 1e9 / 32,
-                     "random_sector_rate_measured_per_s": r_rand},
-        "e2e": {"value": n / (e2e_ms_mean * 1e-3), "unit": UNIT, "ms_per_step": e2e_ms_mean,
-                "h2d_bytes_per_step": n * pb, "d2h_bytes_per_step": int(contig_bytes + 8 * (n_contigs + 1))},
-        "pack_lines": pack,
-        "gpu_launches": 16 * args.steps,
-        "clocks": clocks,
+                     "sector_ceiling_per_s": peak * 1e9 / 32},
+        "e2e": e2e, "pack_lines": pack, "gpu_launches": int(launches), "clocks": clocks,
     }
     tab.close()
     host.free()
+    del dev
+    torch.cuda.empty_cache()
+    return out
+
+
+def run_b200_arm(args, workload: str) -> dict | None:
+    import torch
+    import torch.distributed as dist
+
+    import cs267_hw3_b200 as kh
+
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    rank = int(os.environ.get("RANK", "0"))
+    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+    if not torch.cuda.is_available() or kh.device_count() < 1:
+        raise RuntimeError("bench.py: no CUDA device; the B200 arm has no CPU fallback")
+    torch.cuda.set_device(local_rank)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
+    if world != args.gpus:
+        raise RuntimeError(f"--gpus {args.gpus} but WORLD_SIZE={world}: launch with torch.distributed.run")
+    second = [w for w in (args.also or []) if w != workload]
+    if world > 1:
+        from cs267_hw3_b200 import sharded
+        line = sharded.bench(args, workload, rank, world, local_rank, args.steps, args.warmup)
+        shapes = {w: sharded.bench(args, w, rank, world, local_rank, max(3, min(args.steps, 5)), 3) for w in second}
+        if rank == 0:
+            line["shapes"] = {w: {k2: v[k2] for k2 in ("value", "ms_per_step", "stages_ms", "e2e", "verified", "roofline", "config", "scaling")}
+                              for w, v in shapes.items()}
+        sharded.shutdown()
+        return line if rank == 0 else None
+
+    m = measure_shape_n1(args, workload, args.steps, args.warmup, local_rank, full=True)
+    k = WORKLOADS[workload][0]
+    line = {
+        "metric": METRIC, "value": m["value"], "unit": UNIT, "n_gpus": 1,
+        "steps": args.steps, "warmup": args.warmup, "ms_per_step": m["ms_per_step"], "higher_is_better": True,
+        "scaling": "weak", "vs_baseline": None, "dtype": "u64" if m["config"]["slot_bytes"] == 8 else "u128", "data": "synthetic",
+    }
+    for key in ("config", "stages_ms", "n_segments", "rank_rounds", "assembly_time_s", "wall_s_timed_loop", "gen_s", "verified",
+                "roofline", "e2e", "pack_lines", "gpu_launches", "clocks"):
+        line[key] = m[key]
+    if second:
+        line["shapes"] = {}
+        for w in second:
+            s2 = measure_shape_n1(args, w, max(3, min(args.steps, 5)), 3, local_rank, full=False)
+            line["shapes"][w] = {k2: s2[k2] for k2 in ("value", "ms_per_step", "stages_ms", "e2e", "verified", "roofline", "config",
+                                                       "n_segments", "rank_rounds", "gpu_launches")}
     if not args.no_cpu_baseline:
         line["cpu_baseline"] = cpu_baseline_leg(k, workload)
     else:
         line["cpu_baseline"] = {"value": None, "unit": UNIT, "cores": 1, "kind": "reference", "sample": "skipped"}
+    try:        # the same (unmodified) reference on the FULL file, measured once in the build container (tests/golden/make_full_digests.py)
+        with open(os.path.join(ROOT, "tests", "golden", "chr14_full.json")) as f:
+            full = json.load(f).get(workload)
+        if full:
+            line["cpu_baseline"]["full_file_run"] = {
+                "value": full["n_kmers"] / full["reference_total_s"], "unit": UNIT, "sample_kmers": full["n_kmers"],
+                "insert_s": full["reference_insert_s"], "total_s": full["reference_total_s"], "cores": 1,
+                "where": full["host"] + " -- NOT this GPU box's host; fixture tests/golden/chr14_full.json"}
+    except Exception:
+        pass
     return line
 
 
@@ -388,11 +456,17 @@ def main():
     ap.add_argument("--load-factor", type=float, default=0.5)
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-e2e", action="store_true", help="skip the host-buffer leg (profiling runs)")
+    ap.add_argument("--also", nargs="*", default=None, choices=sorted(WORKLOADS),
+                    help="further workloads measured in the same run and reported under \"shapes\" (default: chr14_k19)")
     ap.add_argument("--scaling", default="strong", choices=["strong", "weak"],
                     help="N>1 only: strong = the N=1 file split over the GPUs (default); weak = one such file per GPU (K>=31)")
     args = ap.parse_args()
     args.warmup = max(args.warmup, 3) if args.impl == "b200" else args.warmup
-    workload = args.workload or "chr14_k19"      # the same file at every N (strong scaling over the sharded table)
+    # BASELINE.json configs[2]/[3]: the reference's real chr14 shape is K=51 (results/results_parallel_kmer51.txt);
+    # the same file at every N (strong scaling over the sharded table).  configs[1] (K=19) rides along as a sub-record.
+    workload = args.workload or "chr14_k51"
+    if args.also is None:
+        args.also = ["chr14_k19"] if (args.workload is None and not args.n) else []
     k = WORKLOADS[workload][0]
     rank = int(os.environ.get("RANK", "0"))
     if args.impl == "reference":
@@ -400,7 +474,7 @@ def main():
             return
         line = run_reference_arm(args, k, workload)
     else:
-        line = run_b200_arm(args, k, workload)
+        line = run_b200_arm(args, workload)
     if line is not None and rank == 0:
         print(json.dumps(line), flush=True)
 

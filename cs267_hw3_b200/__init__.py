@@ -29,9 +29,9 @@ ABI_SYMBOLS = [
     "kh_find", "kh_find_device", "kh_assemble", "kh_assemble_device", "kh_get_stats", "kh_last_error",
     "kh_host_alloc", "kh_host_free", "kh_measure_random_sector_rate",
     # sharded (multi-GPU) path
-    "kh_slot_bytes", "kh_shard_init", "kh_shard_export", "kh_shard_connect", "kh_shard_connect_local",
-    "kh_shard_owner_partition", "kh_insert_slots_device", "kh_shard_walk", "kh_shard_resolve", "kh_shard_phase",
-    "kh_shard_result",
+    "kh_slot_bytes", "kh_shard_init", "kh_shard_export_count", "kh_shard_export", "kh_shard_connect", "kh_shard_connect_local",
+    "kh_shard_begin", "kh_shard_insert", "kh_shard_assemble", "kh_shard_assemble_parts", "kh_shard_assemble_part",
+    "kh_shard_finish", "kh_shard_result", "kh_debug_buffer",
     "kh_device_alloc", "kh_device_alloc_on", "kh_device_free", "kh_copy_to_host", "kh_copy_device",
 ]
 
@@ -50,6 +50,7 @@ class Stats(C.Structure):
         ("rank_rounds", C.c_uint32), ("slot_bits", C.c_uint32),
         ("ms_insert", C.c_float), ("ms_assemble", C.c_float), ("ms_walk", C.c_float),
         ("ms_rank", C.c_float), ("ms_emit", C.c_float), ("ms_pack", C.c_float), ("ms_clear", C.c_float),
+        ("ms_build", C.c_float), ("ms_stage", C.c_float), ("n_launches", C.c_uint64),
     ]
 
     def as_dict(self) -> dict:

@@ -51,7 +51,7 @@ def build_cli(ks=(19, 31, 51), force: bool = False) -> list[str]:
     for k in ks:
         out = os.path.join(ROOT, f"kmer_hash_{k}")
         if force or _stale(out, [src, LIB, *hdrs]):
-            _run(["g++", "-O2", "-std=c++17", f"-DKMER_LEN={k}", "-I" + os.path.join(ROOT, "include"), src,
+            _run(["g++", "-O2", "-std=c++17", "-pthread", f"-DKMER_LEN={k}", "-I" + os.path.join(ROOT, "include"), src,
                   "-L" + PKG, "-lkh_b200", "-Wl,-rpath," + PKG, "-o", out])
         outs.append(out)
     return outs

@@ -16,7 +16,7 @@
 
 #include "../../include/kh_capi.h"
 #include "kernels.cuh"
-#include "sharded.cuh"
+#include "ctable.cuh"
 
 using namespace kh;
 
@@ -27,7 +27,7 @@ struct DevBuf {
     size_t cap = 0;
 };
 
-enum { EV_INS0, EV_INS1, EV_AS0, EV_WALK, EV_RANK, EV_AS1, EV_PACK0, EV_PACK1, EV_CLR0, EV_CLR1, EV_COUNT };
+enum { EV_INS0, EV_INS1, EV_AS0, EV_WALK, EV_RANK, EV_AS1, EV_PACK0, EV_PACK1, EV_CLR0, EV_CLR1, EV_STAGE1, EV_BUILD0, EV_BUILD1, EV_COUNT };
 
 }  // namespace
 
@@ -63,27 +63,28 @@ struct kh_table {
     u32 split_shift = 5, seg_chars = 64;     // every 32nd bucket's first slot is a splitter (tools/probes/sweep_walk.sh)
     cudaEvent_t ev[EV_COUNT] = {};
     cudaEvent_t ev_copied[2] = {}, ev_consumed[2] = {};
-    bool have_ins = false, have_as = false, have_pack = false, have_clr = false;
+    bool have_ins = false, have_as = false, have_pack = false, have_clr = false, have_build = false, have_stage = false;
+    u64 n_launches = 0;               // kernels launched by this handle since create (kh_get_stats)
     kh_stats stats = {};
     std::string err;
     int sm_count = 148, walk_blocks_per_sm = 0, rank_blocks_per_sm = 0;
     u64 last_contig_bytes = 0, last_n_contigs = 0;
-    // ---- sharded (multi-GPU) mode ----
-    bool shard_on = false;
-    Peers peers = {};
-    void* ipc_opened[kMaxRanks][6] = {};
-    u64 shard_n_local_max = 0, shard_n_total = 0, shard_seg_cap = 0, shard_out_cap = 0;
-    u32 shard_n_split = 0;
-    DevBuf owner_ctr;                 // u64[3*kMaxRanks]: counts | base | cursor
-    DevBuf changed_flag;              // u32
-    unsigned shard_walk_blocks = 0;
-    int shard_migrate = 1;            // KH_SHARD_WALK=peer selects the peer-lookup walk instead of the migrating walk
-    MigLayout lay = {};
-    DevBuf seg_of_slot, boundary_list, outbox, outbox_grouped;
-    DevBuf shard_parts;               // owner-side chunked build: received slot values grouped by 8 MB table region
-    int shard_build = 1;              // KH_SHARD_BUILD: 1 = build the owner's table chunk by chunk in shared memory (large shards), 2 = always, 0 = never
-    DevBuf owner_byte;                // owner rank of every record of the block being partitioned (0xFF = rejected)
-    u64 shard_n_starts_max = 0;
+    // ---- chunk table (ctable.cuh): large tables, and every sharded (multi-GPU) handle ----
+    struct CtState {
+        bool on = false, sealed = false, sharded = false, attr_set = false, connected = false;
+        bool assembled = false;           // the segment lists were consumed by a traverse: the next one re-seals
+        CtGeom g = {};
+        CtCaps caps = {};
+        CtPeers pe = {};
+        u32 epoch = 0;                    // barriers passed (all ranks call them in lockstep)
+        u64 n_local_max = 0, n_total = 0, n_starts_max = 0, out_cap = 0;
+        u64 n_starts_host = 0;            // non-sharded handles learn it at every insert (they sync anyway)
+        u32 bprs = 1;                     // scatter blocks per (region, source) buffer
+        DevBuf stage_vals, stage_tags, stage_cnt, reg_cursor, extra_vals, extra_chunk, extra_cnt, fine, chunk_cursor,
+               chunk_base, pool_off, seg_base, ext_key, meta, pool, inbox, inbox_cnt, out_cursor, flags;
+        void* ipc_opened[kMaxRanks][16] = {};
+    } ct;
+    int ct_env = 1;                   // KH_CT: 0 never, 1 tables of >= 2^20 k-mers (and every sharded handle), 2 always
 };
 
 namespace {
@@ -161,6 +162,7 @@ int device_scan(kh_table* t, const u32* in, u64 n, u64* out, u64* total_dev) {
     scan_reduce_kernel<<<(unsigned)nsb, kScanThreads, 0, t->stream>>>(in, n, bs);
     scan_spine_kernel<<<1, 1024, 0, t->stream>>>(bs, nsb, total_dev);
     scan_apply_kernel<<<(unsigned)nsb, kScanThreads, 0, t->stream>>>(in, n, bs, out);
+    t->n_launches += 3;
     KH_CUDA(t, cudaGetLastError());
     return KH_OK;
 }
@@ -291,6 +293,7 @@ int insert_device_impl(kh_table* t, const unsigned char* recs, u64 n, bool recor
                 part_shift, ahead, t->k, t->mlen, static_cast<V*>(t->table), t->nbuckets, t->d_ctr);
     }
     t->table_dirty = true;
+    t->n_launches += !part ? 1 : (chunked ? 4 : 3);
     KH_CUDA(t, cudaGetLastError());
     KH_TRY(device_scan(t, static_cast<u32*>(t->tile_counts.p), ntiles, static_cast<u64*>(t->tile_offs.p),
                        &t->d_ctr->scan_total));
@@ -309,13 +312,23 @@ int insert_device_impl(kh_table* t, const unsigned char* recs, u64 n, bool recor
             static_cast<V*>(t->starts.p), t->n_starts);
         KH_CUDA(t, cudaGetLastError());
         t->n_starts += fresh;
+        ++t->n_launches;
     }
     KH_CUDA(t, cudaEventRecord(t->ev[EV_INS1], t->stream));
     t->have_ins = true;
     return KH_OK;
 }
 
+template <int W> int ct_insert_plain(kh_table* t, const unsigned char* recs, u64 n, bool record_start);
+template <int W> int ct_assemble_plain(kh_table* t);
+template <int W> int ct_seal_plain(kh_table* t);
+
 int insert_device(kh_table* t, const void* recs, u64 n, bool record_start = true) {
+    if (t->ct.on) {
+        if (t->ct.sharded) return fail(t, KH_ERR_ARG, "sharded handle: use kh_shard_insert");
+        return t->W == 1 ? ct_insert_plain<1>(t, static_cast<const unsigned char*>(recs), n, record_start)
+                         : ct_insert_plain<2>(t, static_cast<const unsigned char*>(recs), n, record_start);
+    }
     return t->W == 1 ? insert_device_impl<1>(t, static_cast<const unsigned char*>(recs), n, record_start)
                      : insert_device_impl<2>(t, static_cast<const unsigned char*>(recs), n, record_start);
 }
@@ -328,6 +341,7 @@ int pack_device(kh_table* t, const void* text_dev, u64 n_lines, void* pairs_dev)
     pack_lines_kernel<<<(unsigned)nblk, kPackLines, smem, t->stream>>>(
         static_cast<const unsigned char*>(text_dev), n_lines, t->k, static_cast<unsigned char*>(pairs_dev), t->d_ctr);
     KH_CUDA(t, cudaGetLastError());
+    ++t->n_launches;
     return KH_OK;
 }
 
@@ -394,6 +408,7 @@ int assemble_impl(kh_table* t) {
             static_cast<u64*>(t->contig_off.p), t->d_ctr, out_cap, static_cast<char*>(t->out.p));
     }
     KH_CUDA(t, cudaGetLastError());
+    t->n_launches += 4 + (n_starts ? 1 : 0);        // init, walk, rank, emit_segments (+ emit_heads); the scan counted itself
     KH_CUDA(t, cudaEventRecord(t->ev[EV_AS1], t->stream));
     t->have_as = true;
 
@@ -415,7 +430,13 @@ int assemble_impl(kh_table* t) {
     return KH_OK;
 }
 
-int assemble_device(kh_table* t) { return t->W == 1 ? assemble_impl<1>(t) : assemble_impl<2>(t); }
+int assemble_device(kh_table* t) {
+    if (t->ct.on) {
+        if (t->ct.sharded) return fail(t, KH_ERR_ARG, "sharded handle: use kh_shard_assemble");
+        return t->W == 1 ? ct_assemble_plain<1>(t) : ct_assemble_plain<2>(t);
+    }
+    return t->W == 1 ? assemble_impl<1>(t) : assemble_impl<2>(t);
+}
 
 float elapsed(cudaEvent_t a, cudaEvent_t b) {
     float ms = 0.f;
@@ -446,356 +467,401 @@ int set_option(kh_table* t, const std::string& name, int64_t value) {
 
 }  // namespace
 
-// ============================================================================ sharded ====
-enum { SH_TABLE, SH_LINK, SH_SEGLEN, SH_PRE, SH_OFF, SH_OUT, SH_NBUF };
+// ============================================================================ chunk table ====
+// Host side of ctable.cuh.  A handle is either a plain table (small tables: insert_kernel / walk_kernel above)
+// or a chunk table (ct.on).  Every sharded handle is a chunk table; a plain handle with world = 1 uses the very
+// same code with itself as its only peer.
+namespace {
 
-int shard_require(kh_table* t) {
-    if (!t->shard_on) return fail(t, KH_ERR_ARG, "handle is not in sharded mode (call kh_shard_init first)");
-    return KH_OK;
+enum { CTX_STAGE_VALS, CTX_STAGE_TAGS, CTX_STAGE_CNT, CTX_EXTRA_VALS, CTX_EXTRA_CHUNK, CTX_EXTRA_CNT, CTX_LINK, CTX_META,
+       CTX_INBOX, CTX_INBOX_CNT, CTX_PRE, CTX_OFF, CTX_OUT, CTX_FLAGS, CTX_NBUF };
+
+size_t ct_stage_smem(int W, u32 nreg, int pb) {
+    const size_t un = std::max<size_t>((size_t)kPartTile * (W == 1 ? 8 : 16), (size_t)kPartTile * pb) + kStageSlack;
+    return ((12 * (size_t)nreg + 4 * kPartTile + 15) & ~(size_t)15) + un;
 }
 
-template <int W> int shard_phase_impl(kh_table* t, int phase, int* flag_out);
+void ct_set_self(kh_table* t) {
+    auto& c = t->ct;
+    CtPeers& pe = c.pe;
+    const int r = pe.rank;
+    pe.stage_vals[r] = c.stage_vals.p; pe.stage_tags[r] = static_cast<unsigned short*>(c.stage_tags.p);
+    pe.stage_cnt[r] = static_cast<u32*>(c.stage_cnt.p);
+    pe.extra_vals[r] = c.extra_vals.p; pe.extra_chunk[r] = static_cast<u32*>(c.extra_chunk.p);
+    pe.extra_cnt[r] = static_cast<u32*>(c.extra_cnt.p);
+    pe.link[r] = static_cast<u64*>(t->link.p); pe.meta[r] = static_cast<u64*>(c.meta.p);
+    pe.inbox[r] = c.inbox.p; pe.inbox_cnt[r] = static_cast<u32*>(c.inbox_cnt.p);
+    pe.contig_pre[r] = static_cast<u32*>(t->contig_pre.p); pe.contig_off[r] = static_cast<u64*>(t->contig_off.p);
+    pe.out[r] = static_cast<char*>(t->out.p); pe.out_cap[r] = c.out_cap;
+    pe.flags[r] = static_cast<u32*>(c.flags.p);
+}
 
+// Fix the geometry and (re)allocate everything whose size is known up front.  Sharded handles allocate ALL their
+// buffers here: nothing inside a step may block the host (another rank's barrier kernel may be waiting for work this
+// host thread has not enqueued yet).
 template <int W>
-int shard_init_impl(kh_table* t, int rank, int world, u64 n_local_max, u64 n_total, u64 n_starts_max) {
+int ct_setup(kh_table* t, int rank, int world, u64 n_local_max, u64 n_total, u64 n_starts_max, bool sharded) {
     typedef typename Slot<W>::value_t V;
-    if (world < 1 || world > kMaxRanks || rank < 0 || rank >= world) return fail(t, KH_ERR_ARG, "1 <= world <= 8 and 0 <= rank < world");
-    n_starts_max = std::min<u64>(std::max<u64>(n_starts_max, 1), n_local_max + 1);
-    t->shard_n_local_max = n_local_max; t->shard_n_total = n_total; t->shard_n_starts_max = n_starts_max;
-    t->shard_migrate = 1;
-    if (const char* e = getenv("KH_SHARD_WALK")) t->shard_migrate = (std::string(e) == "peer") ? 0 : 1;
-    t->shard_n_split = (u32)(((t->nbuckets - 1) >> t->split_shift) + 1);
-    int bps = 0, bps2 = 0;
-    KH_CUDA(t, cudaOccupancyMaxActiveBlocksPerMultiprocessor(&bps, walk_sharded_kernel<W>, kWalkThreads, 0));
-    KH_CUDA(t, cudaOccupancyMaxActiveBlocksPerMultiprocessor(&bps2, walk_mig_kernel<W>, kWalkThreads, 0));
-    bps = t->shard_migrate ? bps2 : bps;
-    if (bps < 1) return fail(t, KH_ERR_CUDA, "walk kernel does not fit on an SM");
-    t->shard_walk_blocks = (unsigned)(t->sm_count * bps);
-    const u64 nwarps = (u64)t->shard_walk_blocks * (kWalkThreads / 32);
-    const u64 n_exp = std::max<u64>(t->n_expected, 1);          // k-mers this shard is sized for
-    u64 seg_cap = 0, tmp_rows = 0;
-    if (t->shard_migrate) {
-        // boundary starts: nodes whose predecessor lives elsewhere -- a fraction ~2/(w+1) * (P-1)/P of the shard
-        // with a minimizer window of w m-mers (everything when the owner is a plain key hash) -- plus the start
-        // nodes (backward ext 'F') that hash here.  Twice the expectation, capped by the shard itself.
-        const int w = t->olen ? t->k - t->olen + 1 : 1;
-        const double frac = world == 1 ? 0.0 : (w <= 1 ? 1.0 : std::min(1.0, 4.0 / (w + 1)));
-        const u64 bcap = std::min<u64>(n_exp, (u64)(frac * (double)n_exp)) + 2 * n_starts_max + 1024;
-        const u64 ocap = 2 * (n_exp / t->seg_chars + 1) + (u64)kSegBatch * nwarps + 64;
-        const u64 walk_cap = (u64)t->shard_n_split + bcap + ocap;
-        seg_cap = walk_cap + n_starts_max;
-        if (seg_cap >= (u64)kLocalMask - 16) return fail(t, KH_ERR_ARG, "too many walk segments per GPU for 28-bit local ids");
-        t->lay.n_split = t->shard_n_split; t->lay.bcap = (u32)bcap; t->lay.walk_cap = (u32)walk_cap;
-        t->lay.hcap = (u32)n_starts_max; t->lay.outbox_cap = (u32)std::min<u64>(0xFFFFFF00ull, 2 * seg_cap + (u64)kOutBatch * (nwarps + 1));
-        tmp_rows = walk_cap;
-        KH_TRY(ensure(t, t->seg_of_slot, t->nbuckets * t->per_bucket * sizeof(u32)));
-        KH_TRY(ensure(t, t->boundary_list, (bcap + 1) * sizeof(V)));
-        KH_TRY(ensure(t, t->outbox, ((u64)t->lay.outbox_cap + 1) * sizeof(OutEntry<W>)));
-        KH_TRY(ensure(t, t->outbox_grouped, (seg_cap + 1) * sizeof(OutEntry<W>)));
-    } else {
-        seg_cap = (u64)t->shard_n_split + n_starts_max + 2 * (n_total / t->seg_chars + 1) + (u64)kSegBatch * nwarps + 64;
-        if (seg_cap >= (u64)kLocalMask - 16) return fail(t, KH_ERR_ARG, "too many walk segments per GPU for 28-bit local ids");
-        tmp_rows = seg_cap;
+    auto& c = t->ct;
+    const u64 n_exp = std::max<u64>(t->n_expected, 1);
+    const u32 slots_max = CtBuild<W>::kMaxSlots, per_bucket = (u32)Slot<W>::kPerBucket;
+    const double mu = std::min(t->lf / 1.35, 0.55) * slots_max;                   // mean k-mers per chunk (see chunk_placement_sim.cpp)
+    const u64 C64 = std::max<u64>(1, (u64)std::ceil((double)n_exp / mu));
+    u32 shift = 6;
+    while ((u64)world * ((C64 + (1ull << shift) - 1) >> shift) > kCtMaxRegions) ++shift;
+    if (shift > 10) return fail(t, KH_ERR_ARG, "table too large for one GPU's chunk table (more than 2^20 chunks)");
+    c.g.k = t->k; c.g.m = ct_minimizer_len(t->k); c.g.win = ct_window(t->k);
+    c.g.world = world; c.g.rank = rank;
+    c.g.chunks_per_rank = (u32)C64; c.g.cpr_shift = shift;
+    c.g.regions_per_rank = (u32)((C64 + (1ull << shift) - 1) >> shift);
+    c.g.max_buckets = CtBuild<W>::kMaxBuckets;
+    c.g.lf_inv_q16 = (u32)std::min(65536.0 * 64.0, 65536.0 / t->lf + 0.5);
+    const u64 C = C64, R = c.g.regions_per_rank;
+    c.n_local_max = n_local_max; c.n_total = n_total; c.n_starts_max = n_starts_max; c.sharded = sharded;
+    // table: every chunk gets ceil(load / lf) slots rounded up to whole buckets
+    const u64 nb_alloc = (u64)((long double)n_exp / (long double)t->lf / per_bucket) + C + 64;
+    if (!t->table || t->table_bytes < nb_alloc * 32) {
+        if (t->table) { KH_CUDA(t, cudaStreamSynchronize(t->stream)); KH_CUDA(t, cudaFree(t->table)); t->table = nullptr; }
+        KH_CUDA(t, cudaMalloc(&t->table, nb_alloc * 32));
+        t->table_bytes = nb_alloc * 32;
     }
-    t->shard_seg_cap = seg_cap;
-    t->shard_out_cap = n_total + n_starts_max * (u64)(t->k + 1) + 64;
-    const u64 ntiles = (n_local_max + kInsTile - 1) / kInsTile + 1;
-    KH_TRY(ensure(t, t->link, seg_cap * sizeof(u64)));
-    KH_TRY(ensure(t, t->seglen, seg_cap));
-    KH_TRY(ensure(t, t->tmp, tmp_rows * (u64)t->seg_chars + 16));
-    KH_TRY(ensure(t, t->contig_len, (n_starts_max + 1) * sizeof(u32)));
-    KH_TRY(ensure(t, t->contig_pre, (n_starts_max + 1) * sizeof(u32)));
-    KH_TRY(ensure(t, t->contig_off, (n_starts_max + 1) * sizeof(u64)));
-    KH_TRY(ensure(t, t->out, t->shard_out_cap));
-    KH_TRY(ensure(t, t->starts, (n_starts_max + 1) * sizeof(V)));
-    KH_TRY(ensure(t, t->mask, ntiles * (kInsTile / 32) * sizeof(u32)));
-    KH_TRY(ensure(t, t->tile_counts, ntiles * sizeof(u32)));
-    KH_TRY(ensure(t, t->tile_offs, ntiles * sizeof(u64)));
-    KH_TRY(ensure(t, t->scan_blocks, ((std::max(ntiles, n_starts_max + 1) + kScanTile - 1) / kScanTile + 2) * sizeof(u64)));
-    KH_TRY(ensure(t, t->grouped, (n_local_max + 1) * sizeof(V)));
-    KH_TRY(ensure(t, t->owner_ctr, 3 * kMaxRanks * sizeof(u64)));
-    KH_TRY(ensure(t, t->owner_byte, n_local_max + 1));
-    KH_TRY(ensure(t, t->changed_flag, 16));
-    Peers& pe = t->peers;
-    memset(&pe, 0, sizeof(pe));
-    pe.world = world; pe.rank = rank;
-    pe.table[rank] = t->table; pe.nbuckets[rank] = t->nbuckets;
-    pe.link[rank] = static_cast<u64*>(t->link.p); pe.seglen[rank] = static_cast<unsigned char*>(t->seglen.p);
-    pe.contig_pre[rank] = static_cast<u32*>(t->contig_pre.p); pe.contig_off[rank] = static_cast<u64*>(t->contig_off.p);
-    pe.out[rank] = static_cast<char*>(t->out.p); pe.out_cap[rank] = t->shard_out_cap;
-    t->shard_on = true;
+    t->nbuckets = nb_alloc;
+    c.caps.nbuckets_alloc = nb_alloc;
+    // staging: one buffer per (local region, source rank)
+    const double share = (double)std::max<u64>(n_local_max, 1) * (double)(1u << shift) / ((double)world * (double)C);
+    u64 cap_rs = (u64)((share * 1.10 + 24.0 * std::sqrt(share + 1.0) + 64.0) * t->debug_cap_pct / 100.0);
+    cap_rs = std::max<u64>(8, (cap_rs + 7) & ~7ull);
+    if (cap_rs >= 0xFFFFFFF0ull) return fail(t, KH_ERR_ARG, "staging buffer too large");
+    c.caps.cap_rs = (u32)cap_rs;
+    c.caps.extra_cap = (u32)std::min<u64>(0x7FFFFFF0ull, t->debug_cap_pct < 100 ? n_local_max * (u64)world + 65536 : n_exp / 16 + 65536);
+    const u64 hcap = sharded ? std::min<u64>(std::max<u64>(n_starts_max, 1), n_local_max + 1) : 0;     // plain handles size it at seal
+    c.caps.hcap = (u32)hcap;
+    const u64 seg_cap = hcap + n_exp + 64;
+    if (seg_cap >= (u64)kLocalMask - 16 && sharded) return fail(t, KH_ERR_ARG, "too many segments per GPU for 28-bit local ids");
+    c.caps.seg_cap = (u32)std::min<u64>(seg_cap, 0xFFFFFF00ull);
+    c.caps.pool_cap = n_exp + 16 * C + 64;
+    c.caps.inbox_cap = world > 1 ? (u32)std::min<u64>(0x7FFFFFF0ull, ((n_exp / 2 + hcap) / world) * 5 / 4 + 4096) : 1;
+    c.out_cap = n_total + std::max<u64>(n_starts_max, 1) * (u64)(t->k + 1) + 64;
+    c.bprs = (u32)((cap_rs + kSubTile - 1) / kSubTile);
+    const u64 nreg_local = R * (u64)world;
+    KH_TRY(ensure(t, c.stage_vals, nreg_local * cap_rs * sizeof(V)));
+    KH_TRY(ensure(t, c.stage_tags, nreg_local * cap_rs * sizeof(unsigned short)));
+    KH_TRY(ensure(t, c.stage_cnt, nreg_local * sizeof(u32)));
+    KH_TRY(ensure(t, c.reg_cursor, kCtMaxRegions * sizeof(u32)));
+    KH_TRY(ensure(t, c.extra_vals, (u64)c.caps.extra_cap * sizeof(V)));
+    KH_TRY(ensure(t, c.extra_chunk, (u64)c.caps.extra_cap * sizeof(u32)));
+    KH_TRY(ensure(t, c.extra_cnt, 16));
+    KH_TRY(ensure(t, c.fine, C * (u64)slots_max * sizeof(V)));
+    KH_TRY(ensure(t, c.chunk_cursor, (C + 1) * sizeof(u32)));
+    KH_TRY(ensure(t, c.chunk_base, (C + 2) * sizeof(u32)));
+    KH_TRY(ensure(t, c.pool_off, (C + 2) * sizeof(u32)));
+    KH_TRY(ensure(t, c.seg_base, (C + 1) * sizeof(u32)));
+    KH_TRY(ensure(t, c.pool, c.caps.pool_cap + 64));
+    KH_TRY(ensure(t, c.inbox, (u64)world * c.caps.inbox_cap * sizeof(CtReq<W>)));
+    KH_TRY(ensure(t, c.inbox_cnt, kMaxRanks * sizeof(u32)));
+    KH_TRY(ensure(t, c.out_cursor, kMaxRanks * sizeof(u32)));
+    KH_TRY(ensure(t, c.flags, 2 * kMaxRanks * sizeof(u32)));
+    if (sharded) {
+        KH_TRY(ensure(t, t->link, seg_cap * sizeof(u64)));
+        KH_TRY(ensure(t, c.meta, seg_cap * sizeof(u64)));
+        KH_TRY(ensure(t, c.ext_key, seg_cap * sizeof(V)));
+        KH_TRY(ensure(t, t->contig_len, (hcap + 2) * sizeof(u32)));
+        KH_TRY(ensure(t, t->contig_pre, (hcap + 2) * sizeof(u32)));
+        KH_TRY(ensure(t, t->contig_off, (hcap + 2) * sizeof(u64)));
+        KH_TRY(ensure(t, t->out, c.out_cap));
+        KH_TRY(ensure(t, t->starts, (hcap + 1) * sizeof(V)));
+        const u64 ntiles = (n_local_max + kInsTile - 1) / kInsTile + 1;
+        KH_TRY(ensure(t, t->mask, (ntiles + 1) * (kInsTile / 32) * sizeof(u32)));
+        KH_TRY(ensure(t, t->tile_counts, (ntiles + 1) * sizeof(u32)));
+        KH_TRY(ensure(t, t->tile_offs, (ntiles + 1) * sizeof(u64)));
+        KH_TRY(ensure(t, t->scan_blocks, ((std::max(ntiles, hcap + 2) + kScanTile - 1) / kScanTile + 2) * sizeof(u64)));
+    }
+    KH_CUDA(t, cudaMemsetAsync(c.reg_cursor.p, 0, kCtMaxRegions * sizeof(u32), t->stream));
+    KH_CUDA(t, cudaMemsetAsync(c.extra_cnt.p, 0, 16, t->stream));
+    KH_CUDA(t, cudaMemsetAsync(c.stage_cnt.p, 0, nreg_local * sizeof(u32), t->stream));
+    KH_CUDA(t, cudaMemsetAsync(c.inbox_cnt.p, 0, kMaxRanks * sizeof(u32), t->stream));
+    KH_CUDA(t, cudaMemsetAsync(c.flags.p, 0, 2 * kMaxRanks * sizeof(u32), t->stream));
+    KH_CUDA(t, cudaStreamSynchronize(t->stream));
+    if (!c.attr_set) {
+        KH_CUDA(t, cudaFuncSetAttribute(ct_build_kernel<W>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)CtBuild<W>::kSmem));
+        KH_CUDA(t, cudaFuncSetAttribute(ct_stage_kernel<W>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)ct_stage_smem(W, kCtMaxRegions, 18)));
+        c.attr_set = true;
+    }
+    memset(&c.pe, 0, sizeof(c.pe));
+    c.pe.world = world; c.pe.rank = rank;
+    c.epoch = 0;
+    ct_set_self(t);
+    c.on = true; c.sealed = false;
     return KH_OK;
 }
 
+int ct_barrier(kh_table* t, int round = -1) {
+    auto& c = t->ct;
+    if (c.pe.world <= 1) return KH_OK;
+    ++c.epoch;
+    ct_barrier_kernel<<<1, 32, 0, t->stream>>>(c.pe, c.epoch & 0x7FFFFFFFu, t->d_ctr, round);
+    ++t->n_launches;
+    KH_CUDA(t, cudaGetLastError());
+    return KH_OK;
+}
+
+// K2+K3 on a chunk table: stage the records in their owners' memory, register the start nodes in input order
 template <int W>
-int shard_owner_partition_impl(kh_table* t, const unsigned char* recs, u64 n, const void** slots_out, u64* counts_out) {
+int ct_stage(kh_table* t, const unsigned char* recs, u64 n) {
     typedef typename Slot<W>::value_t V;
-    const int world = t->peers.world;
-    if (n > t->shard_n_local_max) return fail(t, KH_ERR_ARG, "more records than kh_shard_init reserved (n_local_max)");
-    u64* octr = static_cast<u64*>(t->owner_ctr.p);
-    for (int w = 0; w < kMaxRanks; ++w) counts_out[w] = 0;
-    *slots_out = t->grouped.p;
+    auto& c = t->ct;
     if (n == 0) return KH_OK;
+    if (n >= 0xFFF00000ull) return fail(t, KH_ERR_ARG, "at most 2^32-2^20 records per insert call; split the batch");
     const u64 ntiles = (n + kInsTile - 1) / kInsTile;
-    KH_CUDA(t, cudaEventRecord(t->ev[EV_INS0], t->stream));
-    KH_CUDA(t, cudaMemsetAsync(octr, 0, 3 * kMaxRanks * sizeof(u64), t->stream));
-    owner_count_kernel<W><<<(unsigned)ntiles, kInsThreads, (size_t)kInsTile * t->pb + kStageSlack, t->stream>>>(
-        recs, n, t->k, t->olen, world, static_cast<u32*>(t->mask.p), static_cast<u32*>(t->tile_counts.p), octr,
-        static_cast<unsigned char*>(t->owner_byte.p), t->d_ctr);
+    if (!c.sharded) {
+        KH_TRY(ensure(t, t->mask, (ntiles + 1) * (kInsTile / 32) * sizeof(u32)));
+        KH_TRY(ensure(t, t->tile_counts, (ntiles + 1) * sizeof(u32)));
+        KH_TRY(ensure(t, t->tile_offs, (ntiles + 1) * sizeof(u64)));
+        KH_TRY(ensure(t, t->scan_blocks, ((ntiles + kScanTile - 1) / kScanTile + 2) * sizeof(u64)));
+        // the start list may have to hold every record of this call
+        KH_TRY(ensure(t, t->starts, (c.n_starts_host + n + 1) * sizeof(V), /*keep=*/true));
+        c.caps.hcap = (u32)std::min<u64>(0xFFFFFF00ull, c.n_starts_host + n + 1);        // bound for this call's start scatter only
+    } else if (n > c.n_local_max) {
+        return fail(t, KH_ERR_ARG, "more records than kh_shard_init reserved (n_local_max)");
+    }
+    const u32 nreg = c.g.regions_per_rank * (u32)c.g.world;
+    ct_stage_kernel<W><<<(unsigned)((n + kPartTile - 1) / kPartTile), kPartThreads, ct_stage_smem(W, nreg, t->pb), t->stream>>>(
+        recs, n, c.g, c.pe, c.caps, static_cast<u32*>(c.reg_cursor.p), static_cast<u32*>(t->mask.p),
+        static_cast<u32*>(t->tile_counts.p), t->d_ctr);
     KH_CUDA(t, cudaGetLastError());
     KH_TRY(device_scan(t, static_cast<u32*>(t->tile_counts.p), ntiles, static_cast<u64*>(t->tile_offs.p), &t->d_ctr->scan_total));
-    u64 host_counts[kMaxRanks];
-    KH_CUDA(t, cudaMemcpyAsync(host_counts, octr, sizeof(host_counts), cudaMemcpyDeviceToHost, t->stream));
+    ct_scatter_starts_kernel<W><<<(unsigned)((ntiles * 32 + 255) / 256), 256, 0, t->stream>>>(
+        recs, n, t->k, static_cast<u32*>(t->mask.p), static_cast<u64*>(t->tile_offs.p), ntiles, static_cast<V*>(t->starts.p),
+        t->d_ctr, c.caps.hcap);
+    ct_bump_starts_kernel<<<1, 1, 0, t->stream>>>(t->d_ctr, c.caps.hcap);
+    KH_CUDA(t, cudaGetLastError());
+    t->n_launches += 3;
+    KH_CUDA(t, cudaEventRecord(t->ev[EV_STAGE1], t->stream));
+    t->have_stage = true;
+    c.sealed = false; c.assembled = false;
+    t->table_dirty = true;
+    return KH_OK;
+}
+
+__global__ void ct_init_seal_kernel(Counters* c, u32 hcap) {
+    c->next_seg = hcap;
+    c->n_inserted = 0;
+    c->n_duplicates = 0;
+}
+__global__ void ct_init_assemble_kernel(Counters* c) {
+    c->n_nodes = 0;
+    c->contig_bytes = 0;
+    c->rank_rounds = 0;
+    c->rank_done = 0;
+    for (int i = 0; i < 40; ++i) c->flags[i] = 0;
+}
+
+// seal, part 0: publish the staging fill to the owners (then a barrier); part 1: group by chunk, lay out, build + contract
+template <int W>
+int ct_seal_publish(kh_table* t) {
+    auto& c = t->ct;
+    ct_publish_stage_kernel<<<4, 256, 0, t->stream>>>(c.g, c.pe, c.caps, static_cast<const u32*>(c.reg_cursor.p));
+    ++t->n_launches;
+    KH_CUDA(t, cudaGetLastError());
+    return ct_barrier(t);
+}
+template <int W>
+int ct_seal_build(kh_table* t) {
+    typedef typename Slot<W>::value_t V;
+    auto& c = t->ct;
+    const u32 C = c.g.chunks_per_rank, R = c.g.regions_per_rank;
+    if (!c.sharded) {                 // plain handle: the host knows the start count (every insert call synchronises)
+        const u64 hcap = c.n_starts_host + 1;
+        const u64 seg_cap = hcap + std::max<u64>(t->n_expected, 1) + 64;
+        if (seg_cap >= 0xFFFFFF00ull) return fail(t, KH_ERR_ARG, "too many segments for 32-bit ids");
+        c.caps.hcap = (u32)hcap; c.caps.seg_cap = (u32)seg_cap;
+        KH_TRY(ensure(t, t->link, seg_cap * sizeof(u64)));
+        KH_TRY(ensure(t, c.meta, seg_cap * sizeof(u64)));
+        KH_TRY(ensure(t, c.ext_key, seg_cap * sizeof(V)));
+        ct_set_self(t);
+    }
+    KH_CUDA(t, cudaMemsetAsync(c.chunk_cursor.p, 0, (C + 1) * sizeof(u32), t->stream));
+    ct_init_seal_kernel<<<1, 1, 0, t->stream>>>(t->d_ctr, c.caps.hcap);
+    ct_scatter_kernel<W><<<R * (u32)c.g.world * c.bprs, kSubThreads, 8u << c.g.cpr_shift, t->stream>>>(
+        static_cast<const V*>(c.stage_vals.p), static_cast<const unsigned short*>(c.stage_tags.p), static_cast<const u32*>(c.stage_cnt.p),
+        c.g, c.caps, c.bprs, static_cast<u32*>(c.chunk_cursor.p), static_cast<V*>(c.fine.p), t->d_ctr);
+    ct_extra_kernel<W><<<64, 256, 0, t->stream>>>(static_cast<const V*>(c.extra_vals.p), static_cast<const u32*>(c.extra_chunk.p),
+                                                  static_cast<const u32*>(c.extra_cnt.p), c.caps, static_cast<u32*>(c.chunk_cursor.p),
+                                                  static_cast<V*>(c.fine.p), t->d_ctr);
+    ct_layout_kernel<<<1, 1024, 0, t->stream>>>(static_cast<const u32*>(c.chunk_cursor.p), C, c.g, c.caps, (u32)Slot<W>::kPerBucket,
+                                                CtBuild<W>::kMaxSlots, static_cast<u32*>(c.chunk_base.p), static_cast<u32*>(c.pool_off.p), t->d_ctr);
+    t->n_launches += 5;
+    KH_CUDA(t, cudaEventRecord(t->ev[EV_BUILD0], t->stream));
+    ct_build_kernel<W><<<C, kCtBuildThreads, CtBuild<W>::kSmem, t->stream>>>(
+        static_cast<const V*>(c.fine.p), static_cast<const u32*>(c.chunk_cursor.p), static_cast<const u32*>(c.chunk_base.p),
+        static_cast<const u32*>(c.pool_off.p), static_cast<V*>(t->table), static_cast<u32*>(c.seg_base.p),
+        static_cast<u64*>(t->link.p), static_cast<u64*>(c.meta.p), static_cast<V*>(c.ext_key.p),
+        static_cast<unsigned char*>(c.pool.p), c.g, c.caps, t->d_ctr);
+    KH_CUDA(t, cudaGetLastError());
+    KH_CUDA(t, cudaEventRecord(t->ev[EV_BUILD1], t->stream));
+    t->have_build = true;
+    c.sealed = true;
+    return KH_OK;
+}
+
+// The traverse, in parts that each end with a barrier across the ranks (kh_shard_assemble runs them all; a host that
+// emulates several ranks on ONE device enqueues part p for every rank before part p + 1, see kh_capi.h):
+//   0  publish staging fill | barrier
+//   1  seal (if not sealed) + head stubs + resolve the pending links (local lookups; requests to the owners) | barrier
+//   2  answer the requests that arrived (peer store into the sender's link) | barrier
+//   3 .. 3+R-1  one pointer-jumping round each | barrier that also agrees on "nobody moved" (then the rest return at once)
+//   3+R  contig lengths, claims, offsets | barrier
+//   4+R  emit | barrier
+constexpr int kCtMaxRounds = 24;            // chains of up to 2^24 segments
+constexpr int kCtParts = 5 + kCtMaxRounds;
+
+template <int W>
+int ct_assemble_part(kh_table* t, int part) {
+    typedef typename Slot<W>::value_t V;
+    auto& c = t->ct;
+    const unsigned gb = (unsigned)t->sm_count * 8;
+    u64* link = static_cast<u64*>(t->link.p);
+    switch (part) {
+    case 0:
+        if (c.assembled) { c.sealed = false; c.assembled = false; }      // claims and jumped links of the last traverse: rebuild
+        KH_CUDA(t, cudaEventRecord(t->ev[EV_AS0], t->stream));
+        if (!c.sealed) return ct_seal_publish<W>(t);
+        return ct_barrier(t);
+    case 1: {
+        if (!c.sealed) { KH_TRY(ct_seal_build<W>(t)); KH_CUDA(t, cudaEventRecord(t->ev[EV_INS1], t->stream)); t->have_ins = true; }
+        if (!c.sharded) {
+            const u64 hc = c.n_starts_host;
+            KH_TRY(ensure(t, t->contig_len, (hc + 3) * sizeof(u32)));
+            KH_TRY(ensure(t, t->contig_pre, (hc + 3) * sizeof(u32)));
+            KH_TRY(ensure(t, t->contig_off, (hc + 3) * sizeof(u64)));
+            c.out_cap = t->h_ctr->n_inserted + c.n_starts_host * (u64)(t->k + 1) + 64;       // n_inserted: refreshed by the seal's sync below
+            ct_set_self(t);
+        }
+        c.assembled = true;
+        ct_init_assemble_kernel<<<1, 1, 0, t->stream>>>(t->d_ctr);
+        KH_CUDA(t, cudaMemsetAsync(c.out_cursor.p, 0, kMaxRanks * sizeof(u32), t->stream));
+        ct_stub_kernel<W><<<std::max(1u, std::min(gb, (c.caps.hcap + 255u) / 256u)), 256, 0, t->stream>>>(
+            static_cast<const V*>(t->starts.p), t->d_ctr, c.caps.hcap, link, static_cast<u64*>(c.meta.p), static_cast<V*>(c.ext_key.p));
+        ct_resolve_kernel<W><<<gb, 256, 0, t->stream>>>(static_cast<const V*>(t->table), static_cast<const u32*>(c.chunk_base.p),
+                                                        static_cast<const u32*>(c.seg_base.p), link, static_cast<const V*>(c.ext_key.p),
+                                                        c.g, c.pe, c.caps, static_cast<u32*>(c.out_cursor.p), t->d_ctr);
+        if (c.pe.world > 1) { ct_publish_inbox_kernel<<<1, 32, 0, t->stream>>>(c.pe, c.caps, static_cast<const u32*>(c.out_cursor.p)); ++t->n_launches; }
+        t->n_launches += 3;
+        KH_CUDA(t, cudaGetLastError());
+        return ct_barrier(t);
+    }
+    case 2:
+        if (c.pe.world > 1) {
+            ct_answer_kernel<W><<<gb, 256, 0, t->stream>>>(static_cast<const V*>(t->table), static_cast<const u32*>(c.chunk_base.p),
+                                                           static_cast<const u32*>(c.seg_base.p), static_cast<const CtReq<W>*>(c.inbox.p),
+                                                           static_cast<const u32*>(c.inbox_cnt.p), c.g, c.pe, c.caps);
+            KH_CUDA(t, cudaGetLastError());
+            ++t->n_launches;
+        }
+        KH_CUDA(t, cudaEventRecord(t->ev[EV_WALK], t->stream));
+        return ct_barrier(t);
+    case 3 + kCtMaxRounds: {
+        ct_lengths_kernel<<<gb, 256, 0, t->stream>>>(c.pe, link, c.caps, t->k, static_cast<u32*>(t->contig_len.p),
+                                                     static_cast<u32*>(t->contig_pre.p), t->d_ctr);
+        ct_claim_kernel<<<gb, 256, 0, t->stream>>>(c.pe, link, c.caps, static_cast<const u32*>(t->contig_len.p), t->d_ctr);
+        KH_CUDA(t, cudaGetLastError());
+        t->n_launches += 2;
+        KH_TRY(device_scan(t, static_cast<u32*>(t->contig_len.p), (u64)c.caps.hcap + 1, static_cast<u64*>(t->contig_off.p), &t->d_ctr->contig_bytes));
+        KH_CUDA(t, cudaEventRecord(t->ev[EV_RANK], t->stream));
+        return ct_barrier(t);
+    }
+    case 4 + kCtMaxRounds:
+        ct_emit_kernel<<<gb, 256, 0, t->stream>>>(c.pe, link, static_cast<const u64*>(c.meta.p), static_cast<const unsigned char*>(c.pool.p),
+                                                  c.caps, t->d_ctr, t->k);
+        ct_emit_heads_kernel<W><<<gb, 256, 0, t->stream>>>(static_cast<const V*>(t->starts.p), c.caps, t->k, static_cast<const u32*>(t->contig_len.p),
+                                                          static_cast<const u64*>(t->contig_off.p), t->d_ctr, c.out_cap, static_cast<char*>(t->out.p));
+        KH_CUDA(t, cudaGetLastError());
+        t->n_launches += 2;
+        KH_CUDA(t, cudaEventRecord(t->ev[EV_AS1], t->stream));
+        t->have_as = true;
+        return ct_barrier(t);
+    default: {
+        if (part < 3 || part >= 3 + kCtMaxRounds) return fail(t, KH_ERR_ARG, "unknown assemble part");
+        const int r = part - 3;
+        ct_rank_round_kernel<<<gb, 256, 0, t->stream>>>(c.pe, link, c.caps, t->d_ctr, t->d_ctr->flags, r);
+        KH_CUDA(t, cudaGetLastError());
+        ++t->n_launches;
+        return ct_barrier(t, r);
+    }
+    }
+}
+
+// wait for the step, collect counters; *bits_out = device error bits (0 = fine)
+int ct_finish(kh_table* t, u32* bits_out) {
+    auto& c = t->ct;
+    KH_TRY(read_counters(t));
+    const Counters& h = *t->h_ctr;
+    const u64 n_starts = std::min<u64>(h.n_starts_dev, c.caps.hcap);
+    t->n_starts = n_starts;
+    t->stats.n_contigs = n_starts;
+    t->stats.n_nodes = h.n_nodes;
+    t->stats.contig_bytes = h.contig_bytes;
+    t->stats.n_segments = (h.next_seg > c.caps.hcap ? h.next_seg - c.caps.hcap : 0) + n_starts;
+    u32 rounds = 0;
+    for (int i = 0; i < kCtMaxRounds; ++i) rounds += h.flags[i] ? 1u : 0u;
+    t->stats.rank_rounds = rounds + 1;
+    t->last_contig_bytes = h.contig_bytes;
+    t->last_n_contigs = n_starts;
+    u32 e = h.errors;
+    if (e == 0 && h.contig_bytes > c.out_cap) e = kErrConverge;
+    if (bits_out) *bits_out = e;
+    if (h.errors) clear_error_bits(t);
+    return KH_OK;
+}
+
+// plain-handle wrappers -----------------------------------------------------------------------------------------
+template <int W>
+int ct_insert_plain(kh_table* t, const unsigned char* recs, u64 n, bool record_start) {
+    auto& c = t->ct;
+    if (record_start) KH_CUDA(t, cudaEventRecord(t->ev[EV_INS0], t->stream));
+    KH_TRY(ct_stage<W>(t, recs, n));
+    KH_TRY(read_counters(t));                 // start count (sizes the start list of the next call) + input errors
+    c.n_starts_host = std::min<u64>(t->h_ctr->n_starts_dev, 0xFFFFFF00ull);
+    t->n_starts = c.n_starts_host;
+    KH_CUDA(t, cudaEventRecord(t->ev[EV_INS1], t->stream));
+    t->have_ins = true;
+    const u32 e = t->h_ctr->errors;
+    if (e) { clear_error_bits(t); return status_from_errors(t, e); }
+    return KH_OK;
+}
+
+template <int W>
+int ct_seal_plain(kh_table* t) {
+    auto& c = t->ct;
+    if (c.sealed) return KH_OK;
+    KH_TRY(ct_seal_publish<W>(t));
+    KH_TRY(ct_seal_build<W>(t));
+    KH_CUDA(t, cudaEventRecord(t->ev[EV_INS1], t->stream));
     KH_TRY(read_counters(t));
     const u32 e = t->h_ctr->errors;
     if (e) { clear_error_bits(t); return status_from_errors(t, e); }
-    u64 base[kMaxRanks], run = 0;
-    for (int w = 0; w < kMaxRanks; ++w) { base[w] = run; run += host_counts[w]; counts_out[w] = host_counts[w]; }
-    KH_CUDA(t, cudaMemcpyAsync(octr + kMaxRanks, base, sizeof(base), cudaMemcpyHostToDevice, t->stream));
-    owner_scatter_kernel<W><<<(unsigned)ntiles, kInsThreads, (size_t)kInsTile * t->pb + kStageSlack, t->stream>>>(
-        recs, n, t->k, static_cast<const unsigned char*>(t->owner_byte.p), world, octr + kMaxRanks, octr + 2 * kMaxRanks,
-        static_cast<V*>(t->grouped.p));
-    const u64 fresh = t->h_ctr->scan_total;
-    if (t->n_starts + fresh > t->shard_n_starts_max) return fail(t, KH_ERR_ARG, "more start nodes than kh_shard_init reserved (n_starts_max)");
-    if (fresh) {
-        scatter_starts_kernel<W><<<(unsigned)((ntiles * 32 + 255) / 256), 256, 0, t->stream>>>(
-            recs, n, t->k, static_cast<u32*>(t->mask.p), static_cast<u64*>(t->tile_offs.p), ntiles,
-            static_cast<V*>(t->starts.p), t->n_starts);
-        t->n_starts += fresh;
-    }
-    KH_CUDA(t, cudaGetLastError());
-    KH_CUDA(t, cudaStreamSynchronize(t->stream));    // base[] lives on this stack frame
     return KH_OK;
 }
 
 template <int W>
-int insert_slots_impl(kh_table* t, const void* slots, u64 n) {
-    typedef typename Slot<W>::value_t V;
-    if (n == 0) return KH_OK;
-    const unsigned blocks = (unsigned)((n + kInsTile - 1) / kInsTile);
-    // A whole shard arriving into a clean table larger than L2 is built chunk by chunk in shared memory (kernels.cuh,
-    // chunked build): two grouping passes over the received values, no global atomics, boundary starts registered
-    // in a dense sweep of every finished chunk.  Anything else takes the atomic insert below.
-    const bool chunked = t->shard_on && t->shard_migrate && t->shard_build && !t->table_dirty && n < 0xFFF00000ull &&
-                         (t->shard_build == 2 ||       // 2 = always (tests: small tables take the same path)
-                          (t->table_bytes > (64ull << 20) && n * 8 >= t->nbuckets * (u64)t->per_bucket));
-    if (chunked) {
-        u32 part_shift = kChunkShift + 7;                               // 128 chunks (8 MB of table) per region
-        while (((t->nbuckets - 1) >> part_shift) + 1 > (u64)kMaxParts) ++part_shift;
-        if (part_shift - kChunkShift > 10) return fail(t, KH_ERR_ARG, "table too large for the chunked build");
-        const u32 nparts = (u32)(((t->nbuckets - 1) >> part_shift) + 1);
-        const double share = (double)n * (double)std::min<u64>(t->nbuckets, 1ull << part_shift) / (double)t->nbuckets;
-        u64 part_cap = (u64)(share + 24.0 * std::sqrt(share + 1.0) + 64.0) * t->debug_cap_pct / 100;
-        part_cap = (part_cap + kInsTile - 1) / kInsTile * kInsTile;
-        const u64 nchunks = (t->nbuckets + kChunkBuckets - 1) >> kChunkShift;
-        const double share2 = (double)n * (double)std::min<u64>(t->nbuckets, kChunkBuckets) / (double)t->nbuckets;
-        u32 chunk_cap = (u32)((u64)(share2 + 24.0 * std::sqrt(share2 + 1.0) + 32.0) * t->debug_cap_pct / 100);
-        chunk_cap = std::max(4u, (chunk_cap + 3u) & ~3u);
-        const u32 overflow_cap = (u32)std::min<u64>(0x7FFFFFFFull, t->debug_cap_pct < 100 ? n + 65536 : n / 32 + 65536);
-        const u32 bpp2 = (u32)((part_cap + kSubTile - 1) / kSubTile);
-        const u32 nsub = 1u << (part_shift - kChunkShift);
-        KH_TRY(ensure(t, t->part_cursor, kMaxParts * sizeof(u32)));
-        KH_TRY(ensure(t, t->shard_parts, (u64)nparts * part_cap * sizeof(V)));
-        KH_TRY(ensure(t, t->fine, nchunks * (u64)chunk_cap * sizeof(V)));
-        KH_TRY(ensure(t, t->chunk_cursor, nchunks * sizeof(u32)));
-        KH_TRY(ensure(t, t->overflow, (u64)overflow_cap * sizeof(V)));
-        if (!t->chunk_attr_set) {
-            KH_CUDA(t, cudaFuncSetAttribute(build_chunks_kernel<W, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(kChunkBuckets * 32)));
-            KH_CUDA(t, cudaFuncSetAttribute(build_chunks_kernel<W, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(kChunkBuckets * 32)));
-            t->chunk_attr_set = true;
-        }
-        KH_CUDA(t, cudaMemsetAsync(t->part_cursor.p, 0, kMaxParts * sizeof(u32), t->stream));
-        KH_CUDA(t, cudaMemsetAsync(t->chunk_cursor.p, 0, nchunks * sizeof(u32), t->stream));
-        KH_CUDA(t, cudaMemsetAsync(&t->d_ctr->n_outbox, 0, sizeof(u32), t->stream));
-        V* parts = static_cast<V*>(t->shard_parts.p);
-        V* over = static_cast<V*>(t->overflow.p);
-        const unsigned l1_blocks = (unsigned)((n + kSubTile - 1) / kSubTile);
-        subpartition_kernel<W><<<l1_blocks, kSubThreads, 8 * (size_t)nparts + 16, t->stream>>>(      // level 1: by 8 MB region
-            static_cast<const V*>(slots), nullptr, n, 0, l1_blocks, part_shift, nparts, t->k, t->mlen, t->nbuckets,
-            (u32)part_cap, static_cast<u32*>(t->part_cursor.p), parts, over, overflow_cap, t->d_ctr);
-        subpartition_kernel<W><<<nparts * bpp2, kSubThreads, 8 * (size_t)nsub + 16, t->stream>>>(    // level 2: by 64 KB chunk
-            parts, static_cast<const u32*>(t->part_cursor.p), 0, part_cap, bpp2, kChunkShift, nsub, t->k, t->mlen, t->nbuckets,
-            chunk_cap, static_cast<u32*>(t->chunk_cursor.p), static_cast<V*>(t->fine.p), over, overflow_cap, t->d_ctr);
-        BoundaryReg br;
-        br.seg_of_slot = static_cast<u32*>(t->seg_of_slot.p); br.boundary_list = t->boundary_list.p; br.bcap = t->lay.bcap;
-        br.rank = t->peers.rank; br.world = t->peers.world; br.mo = t->olen;
-        build_chunks_kernel<W, true><<<(unsigned)nchunks, kBuildThreads, kChunkBuckets * 32, t->stream>>>(
-            static_cast<const V*>(t->fine.p), static_cast<const u32*>(t->chunk_cursor.p), chunk_cap, static_cast<V*>(t->table),
-            t->nbuckets, t->k, t->mlen, 0, over, overflow_cap, t->d_ctr, br);
-        insert_overflow_shard_kernel<W><<<64, 256, 0, t->stream>>>(
-            over, overflow_cap, t->k, t->mlen, t->olen, t->peers.rank, t->peers.world, static_cast<V*>(t->table), t->nbuckets,
-            static_cast<u32*>(t->seg_of_slot.p), static_cast<V*>(t->boundary_list.p), t->lay.bcap, t->d_ctr);
-    } else if (t->shard_on && t->shard_migrate)
-        insert_slots_shard_kernel<W><<<blocks, kInsThreads, 0, t->stream>>>(
-            static_cast<const V*>(slots), n, t->k, t->mlen, t->olen, t->peers.rank, t->peers.world, static_cast<V*>(t->table),
-            t->nbuckets, static_cast<u32*>(t->seg_of_slot.p), static_cast<V*>(t->boundary_list.p), t->lay.bcap, t->d_ctr);
-    else
-        insert_slots_direct_kernel<W><<<blocks, kInsThreads, 0, t->stream>>>(
-            static_cast<const V*>(slots), n, t->k, t->mlen, static_cast<V*>(t->table), t->nbuckets, t->d_ctr);
-    KH_CUDA(t, cudaGetLastError());
-    t->table_dirty = true;
-    KH_CUDA(t, cudaEventRecord(t->ev[EV_INS1], t->stream));
-    t->have_ins = true;
+int ct_assemble_plain(kh_table* t) {
+    auto& c = t->ct;
+    if (c.assembled) { c.sealed = false; c.assembled = false; }
+    KH_TRY(ct_seal_plain<W>(t));              // also refreshes n_inserted on the host (sizes the output)
+    KH_TRY(ensure(t, t->out, t->h_ctr->n_inserted + c.n_starts_host * (u64)(t->k + 1) + 64));
+    for (int part = 0; part < kCtParts; ++part) KH_TRY(ct_assemble_part<W>(t, part));
+    u32 bits = 0;
+    KH_TRY(ct_finish(t, &bits));
+    if (bits) return status_from_errors(t, bits);
     return KH_OK;
 }
 
-// walk phase: returns the pending cross-GPU links grouped by destination (migrating mode)
-template <int W>
-int shard_walk_impl(kh_table* t, const void** entries_out, u64* counts_out) {
-    typedef typename Slot<W>::value_t V;
-    for (int w = 0; w < kMaxRanks; ++w) counts_out[w] = 0;
-    *entries_out = t->outbox_grouped.p;
-    const u32 n_starts = (u32)t->n_starts;
-    KH_CUDA(t, cudaEventRecord(t->ev[EV_AS0], t->stream));
-    KH_CUDA(t, cudaMemsetAsync(static_cast<u32*>(t->contig_len.p) + n_starts, 0, sizeof(u32), t->stream));
-    t->stats.rank_rounds = 0;
-    if (!t->shard_migrate) {
-        int dummy;
-        return shard_phase_impl<W>(t, 0, &dummy);
-    }
-    const MigLayout lay = t->lay;
-    init_mig_kernel<<<1, 1, 0, t->stream>>>(t->d_ctr, lay.n_split + lay.bcap);
-    if (n_starts)
-        head_stub_kernel<W><<<(n_starts + 255) / 256, 256, 0, t->stream>>>(
-            static_cast<const V*>(t->starts.p), n_starts, t->k, t->olen, t->peers.rank, t->peers.world, lay,
-            static_cast<u64*>(t->link.p), static_cast<unsigned char*>(t->seglen.p), static_cast<OutEntry<W>*>(t->outbox.p), t->d_ctr);
-    MigWalkParams wp;
-    wp.table = t->table; wp.nbuckets = t->nbuckets; wp.boundary_list = t->boundary_list.p;
-    wp.link = static_cast<u64*>(t->link.p); wp.seglen = static_cast<unsigned char*>(t->seglen.p);
-    wp.tmp = static_cast<unsigned char*>(t->tmp.p); wp.outbox = t->outbox.p; wp.ctr = t->d_ctr; wp.lay = lay;
-    wp.split_shift = t->split_shift; wp.seg_chars = t->seg_chars; wp.k = t->k; wp.m = t->mlen; wp.mo = t->olen;
-    wp.rank = t->peers.rank; wp.world = t->peers.world;
-    walk_mig_kernel<W><<<t->shard_walk_blocks, kWalkThreads, 0, t->stream>>>(wp);
-    KH_CUDA(t, cudaGetLastError());
-    KH_CUDA(t, cudaEventRecord(t->ev[EV_WALK], t->stream));
-    u64* octr = static_cast<u64*>(t->owner_ctr.p);
-    KH_CUDA(t, cudaMemsetAsync(octr, 0, 3 * kMaxRanks * sizeof(u64), t->stream));
-    const unsigned gb = (unsigned)t->sm_count * 4;
-    outbox_count_kernel<W><<<gb, 256, 0, t->stream>>>(static_cast<OutEntry<W>*>(t->outbox.p), t->d_ctr, lay.outbox_cap, t->k, t->olen,
-                                                     t->peers.rank, t->peers.world, octr);
-    u64 host_counts[kMaxRanks];
-    KH_CUDA(t, cudaMemcpyAsync(host_counts, octr, sizeof(host_counts), cudaMemcpyDeviceToHost, t->stream));
-    KH_CUDA(t, cudaStreamSynchronize(t->stream));
-    u64 base[kMaxRanks], run = 0;
-    for (int w = 0; w < kMaxRanks; ++w) { base[w] = run; run += host_counts[w]; counts_out[w] = host_counts[w]; }
-    KH_CUDA(t, cudaMemcpyAsync(octr + kMaxRanks, base, sizeof(base), cudaMemcpyHostToDevice, t->stream));
-    outbox_scatter_kernel<W><<<gb, 256, 0, t->stream>>>(static_cast<const OutEntry<W>*>(t->outbox.p), t->d_ctr, lay.outbox_cap,
-                                                       octr + kMaxRanks, octr + 2 * kMaxRanks, static_cast<OutEntry<W>*>(t->outbox_grouped.p));
-    KH_CUDA(t, cudaGetLastError());
-    KH_CUDA(t, cudaStreamSynchronize(t->stream));    // base[] is on this frame
-    return KH_OK;
-}
-
-template <int W>
-int shard_resolve_impl(kh_table* t, const void* inbox, u64 n) {
-    typedef typename Slot<W>::value_t V;
-    if (!t->shard_migrate || n == 0) return KH_OK;
-    resolve_links_kernel<W><<<(unsigned)((n + 255) / 256), 256, 0, t->stream>>>(
-        t->peers, static_cast<const OutEntry<W>*>(inbox), n, static_cast<const V*>(t->table), t->nbuckets, t->k, t->mlen,
-        static_cast<const u32*>(t->seg_of_slot.p), static_cast<const V*>(t->boundary_list.p), t->lay, t->d_ctr);
-    KH_CUDA(t, cudaGetLastError());
-    return KH_OK;
-}
-
-template <int W>
-int shard_phase_impl(kh_table* t, int phase, int* flag_out) {
-    typedef typename Slot<W>::value_t V;
-    const Peers& pe = t->peers;
-    const u32 n_starts = (u32)t->n_starts, n_split = t->shard_n_split;
-    const unsigned gb = (unsigned)t->sm_count * 8;
-    const u32 head_base = t->shard_migrate ? t->lay.walk_cap : n_split;     // local id of contig 0's head segment
-    if (flag_out) *flag_out = 0;
-    switch (phase) {
-    case 0: {   // walk
-        KH_CUDA(t, cudaEventRecord(t->ev[EV_AS0], t->stream));
-        init_assemble_kernel<<<1, 1, 0, t->stream>>>(t->d_ctr, n_split + n_starts);
-        KH_CUDA(t, cudaMemsetAsync(static_cast<u32*>(t->contig_len.p) + n_starts, 0, sizeof(u32), t->stream));
-        ShardWalkParams wp;
-        wp.peers = pe; wp.starts = t->starts.p;
-        wp.link = static_cast<u64*>(t->link.p); wp.seglen = static_cast<unsigned char*>(t->seglen.p);
-        wp.tmp = static_cast<unsigned char*>(t->tmp.p); wp.ctr = t->d_ctr;
-        wp.n_starts = n_starts; wp.n_split = n_split; wp.split_shift = t->split_shift;
-        wp.seg_chars = t->seg_chars; wp.seg_cap = (u32)t->shard_seg_cap; wp.k = t->k; wp.m = t->mlen; wp.mo = t->olen;
-        const u64 walkers = (u64)n_starts + n_split;
-        const unsigned blocks = (unsigned)std::max<u64>(1, std::min<u64>(t->shard_walk_blocks, (walkers + kWalkThreads - 1) / kWalkThreads));
-        walk_sharded_kernel<W><<<blocks, kWalkThreads, 0, t->stream>>>(wp);
-        KH_CUDA(t, cudaGetLastError());
-        KH_CUDA(t, cudaEventRecord(t->ev[EV_WALK], t->stream));
-        return KH_OK;
-    }
-    case 1: {   // a batch of pointer-jumping rounds; stale peer reads are valid, so no barrier between them
-        u32* flag = static_cast<u32*>(t->changed_flag.p);
-        // chains of ~100 segments need 7 doubling rounds plus one that sees nothing move: the first batch is 8,
-        // so the common case costs ONE host round trip; longer chains add batches of 4
-        const int batch = t->stats.rank_rounds == 0 ? 8 : 4;
-        for (int r = 0; r < batch; ++r) {
-            KH_CUDA(t, cudaMemsetAsync(flag, 0, sizeof(u32), t->stream));
-            if (t->shard_migrate)
-                rank_round_mig_kernel<<<gb, 256, 0, t->stream>>>(pe, static_cast<u64*>(t->link.p), t->lay, n_starts, t->d_ctr, flag);
-            else
-                rank_round_sharded_kernel<<<gb, 256, 0, t->stream>>>(pe, static_cast<u64*>(t->link.p), (u32)t->shard_seg_cap, t->d_ctr, flag);
-        }
-        KH_CUDA(t, cudaGetLastError());
-        u32 h = 0;
-        KH_CUDA(t, cudaMemcpyAsync(&h, flag, sizeof(u32), cudaMemcpyDeviceToHost, t->stream));
-        KH_CUDA(t, cudaStreamSynchronize(t->stream));
-        if (flag_out) *flag_out = (int)h;          // did the LAST round of the batch still move something?
-        t->stats.rank_rounds += batch;
-        return KH_OK;
-    }
-    case 2:     // contig lengths
-        contig_lengths_sharded_kernel<<<gb, 256, 0, t->stream>>>(pe, static_cast<u64*>(t->link.p), head_base, n_starts, t->k,
-            static_cast<u32*>(t->contig_len.p), static_cast<u32*>(t->contig_pre.p), t->d_ctr);
-        KH_CUDA(t, cudaGetLastError());
-        return KH_OK;
-    case 3:     // claim tails
-        claim_tails_sharded_kernel<<<gb, 256, 0, t->stream>>>(pe, static_cast<u64*>(t->link.p), head_base, n_starts,
-            static_cast<u32*>(t->contig_len.p), t->d_ctr);
-        KH_CUDA(t, cudaGetLastError());
-        return KH_OK;
-    case 4:     // offsets of the local contigs
-        KH_TRY(device_scan(t, static_cast<u32*>(t->contig_len.p), (u64)n_starts + 1, static_cast<u64*>(t->contig_off.p), &t->d_ctr->contig_bytes));
-        KH_CUDA(t, cudaEventRecord(t->ev[EV_RANK], t->stream));
-        return KH_OK;
-    case 5: {   // emit
-        if (t->shard_migrate)
-            emit_segments_mig_kernel<<<(unsigned)(((u64)t->lay.walk_cap + 255) / 256), 256, 0, t->stream>>>(
-                pe, static_cast<u64*>(t->link.p), static_cast<unsigned char*>(t->seglen.p), static_cast<unsigned char*>(t->tmp.p),
-                t->seg_chars, t->lay, t->d_ctr, t->k);
-        else
-            emit_segments_sharded_kernel<<<(unsigned)((t->shard_seg_cap + 255) / 256), 256, 0, t->stream>>>(
-                pe, static_cast<u64*>(t->link.p), static_cast<unsigned char*>(t->seglen.p), static_cast<unsigned char*>(t->tmp.p),
-                t->seg_chars, (u32)t->shard_seg_cap, t->d_ctr, t->k);
-        if (n_starts) {
-            const u64 head_threads = (u64)n_starts * (u64)(t->k + 1);
-            emit_heads_kernel<W><<<(unsigned)((head_threads + 255) / 256), 256, 0, t->stream>>>(
-                static_cast<const V*>(t->starts.p), n_starts, t->k, static_cast<u32*>(t->contig_len.p),
-                static_cast<u64*>(t->contig_off.p), t->d_ctr, t->shard_out_cap, static_cast<char*>(t->out.p));
-        }
-        KH_CUDA(t, cudaGetLastError());
-        KH_CUDA(t, cudaEventRecord(t->ev[EV_AS1], t->stream));
-        t->have_as = true;
-        return KH_OK;
-    }
-    case 6: {   // collect counters (after the final barrier)
-        KH_TRY(read_counters(t));
-        t->stats.n_contigs = n_starts;
-        t->stats.n_nodes = t->h_ctr->n_nodes;
-        t->stats.contig_bytes = t->h_ctr->contig_bytes;
-        t->stats.n_segments = std::min<u64>(t->h_ctr->next_seg, t->shard_seg_cap);
-        if (flag_out) *flag_out = (int)t->h_ctr->errors;
-        if (t->h_ctr->errors) clear_error_bits(t);
-        return KH_OK;
-    }
-    default:
-        return fail(t, KH_ERR_ARG, "unknown shard phase");
-    }
-}
+}  // namespace
 
 // ============================================================================ C ABI ======
 extern "C" {
 
-int kh_abi_version(void) { return 1; }
+int kh_abi_version(void) { return 2; }
 
 int kh_device_count(void) {
     int n = 0;
@@ -832,7 +898,11 @@ int kh_create(int k, uint64_t n_expected, double load_factor, int device, kh_tab
     auto bail = [&](int rc) { kh_destroy(t); return rc; };
     t->k = k; t->device = device; t->lf = load_factor; t->n_expected = n_expected;
     t->pl = (k + 3) / 4; t->pb = t->pl + 2;
-    t->W = (2 * k + 6 <= 64) ? 1 : 2;
+    // Large tables (and every sharded handle, kh_shard_init) are chunk tables (ctable.cuh); small ones, and K outside
+    // 17..54, stay plain open-addressing tables built with global atomics.  KH_CT: 0 never, 1 auto, 2 always.
+    t->ct_env = env_int("KH_CT", 1);
+    const bool use_ct = ct_supported(k) && (t->ct_env == 2 || (t->ct_env != 0 && n_expected >= (1ull << 20)));
+    t->W = use_ct ? ct_slot_words(k) : ((2 * k + 6 <= 64) ? 1 : 2);
     t->slot_bytes = t->W == 1 ? 8 : 16;
     t->per_bucket = 32 / t->slot_bytes;
     if (cudaSetDevice(device) != cudaSuccess) return bail(KH_ERR_CUDA);
@@ -847,20 +917,20 @@ int kh_create(int k, uint64_t n_expected, double load_factor, int device, kh_tab
     const long double slots = (long double)std::max<uint64_t>(n_expected, 1) / (long double)load_factor;
     t->nbuckets = std::max<u64>(16, (u64)(slots / t->per_bucket) + 1);
     t->nbuckets = (t->nbuckets + 15) / 16 * 16;       // whole placement regions (slot.cuh RegionOf)
-    t->table_bytes = (size_t)t->nbuckets * 32;
+    t->table_bytes = use_ct ? 0 : (size_t)t->nbuckets * 32;       // a chunk table is allocated by ct_setup
     int rc = KH_OK;
     auto ck = [&](cudaError_t e) { if (e != cudaSuccess && rc == KH_OK) { rc = e == cudaErrorMemoryAllocation ? KH_ERR_NOMEM : KH_ERR_CUDA; t->err = cudaGetErrorString(e); } };
     ck(cudaStreamCreateWithFlags(&t->own_stream, cudaStreamNonBlocking));
     ck(cudaStreamCreateWithFlags(&t->copy_stream, cudaStreamNonBlocking));
     t->stream = t->own_stream;
-    ck(cudaMalloc(&t->table, t->table_bytes));
+    if (!use_ct) ck(cudaMalloc(&t->table, t->table_bytes));
     ck(cudaMalloc((void**)&t->d_ctr, sizeof(Counters)));
     ck(cudaHostAlloc((void**)&t->h_ctr, sizeof(Counters), cudaHostAllocDefault));
     for (auto& e : t->ev) ck(cudaEventCreate(&e));
     for (auto& e : t->ev_copied) ck(cudaEventCreateWithFlags(&e, cudaEventDisableTiming));
     for (auto& e : t->ev_consumed) ck(cudaEventCreateWithFlags(&e, cudaEventDisableTiming));
     if (rc != KH_OK) { fprintf(stderr, "libkh_b200: kh_create: %s\n", t->err.c_str()); return bail(rc); }
-    ck(cudaMemsetAsync(t->table, 0, t->table_bytes, t->stream));
+    if (!use_ct) ck(cudaMemsetAsync(t->table, 0, t->table_bytes, t->stream));
     ck(cudaMemsetAsync(t->d_ctr, 0, sizeof(Counters), t->stream));
     ck(cudaStreamSynchronize(t->stream));
     if (rc != KH_OK) return bail(rc);
@@ -874,7 +944,6 @@ int kh_create(int k, uint64_t n_expected, double load_factor, int device, kh_tab
     // measured: the shared-memory build wins for 64-bit slots (2.85 vs 3.03 ms) and loses for 128-bit slots
     // (4.6 vs 4.1 ms: twice the bytes through the two grouping passes), so it is the default only for K <= 29
     t->build_mode = env_int("KH_BUILD", t->W == 1 ? 1 : 0);
-    t->shard_build = env_int("KH_SHARD_BUILD", 1);
     t->debug_cap_pct = std::max(1, env_int("KH_DEBUG_CAP_PCT", 100));
     t->ins_mode = env_int("KH_INS_MODE", 1);
     t->warm_ahead = env_int("KH_WARM_AHEAD", 1);
@@ -882,6 +951,11 @@ int kh_create(int k, uint64_t n_expected, double load_factor, int device, kh_tab
     if (v > 0) t->part_bytes = (u64)v << 20;
     v = env_int("KH_SEG_CHARS", 0);
     if (v > 0 && set_option(t, "seg_chars", v) != KH_OK) fprintf(stderr, "libkh_b200: ignoring KH_SEG_CHARS=%d\n", v);
+    if (use_ct) {
+        rc = t->W == 1 ? ct_setup<1>(t, 0, 1, n_expected, n_expected, n_expected, false)
+                       : ct_setup<2>(t, 0, 1, n_expected, n_expected, n_expected, false);
+        if (rc != KH_OK) { fprintf(stderr, "libkh_b200: kh_create: %s\n", t->err.c_str()); return bail(rc); }
+    }
     t->err.clear();
     *out = t;
     return KH_OK;
@@ -895,10 +969,14 @@ int kh_destroy(kh_table* t) {
                       &t->tmp, &t->part_cursor, &t->grouped, &t->fine, &t->chunk_cursor, &t->overflow, &t->contig_len, &t->contig_pre, &t->contig_off, &t->out, &t->stage[0], &t->stage[1],
                       &t->text_stage, &t->scratch_a, &t->scratch_b, &t->scratch_c};
     for (DevBuf* b : bufs) if (b->p) cudaFree(b->p);
-    for (auto& row : t->ipc_opened) for (void* q : row) if (q) cudaIpcCloseMemHandle(q);
-    if (t->owner_ctr.p) cudaFree(t->owner_ctr.p);
-    for (DevBuf* b : {&t->seg_of_slot, &t->boundary_list, &t->outbox, &t->outbox_grouped, &t->owner_byte, &t->shard_parts}) if (b->p) cudaFree(b->p);
-    if (t->changed_flag.p) cudaFree(t->changed_flag.p);
+    for (auto& row : t->ct.ipc_opened) for (void* q : row) if (q) cudaIpcCloseMemHandle(q);
+    {
+        auto& c = t->ct;
+        for (DevBuf* b : {&c.stage_vals, &c.stage_tags, &c.stage_cnt, &c.reg_cursor, &c.extra_vals, &c.extra_chunk, &c.extra_cnt, &c.fine,
+                          &c.chunk_cursor, &c.chunk_base, &c.pool_off, &c.seg_base, &c.ext_key, &c.meta, &c.pool, &c.inbox, &c.inbox_cnt,
+                          &c.out_cursor, &c.flags})
+            if (b->p) cudaFree(b->p);
+    }
     if (t->table) cudaFree(t->table);
     if (t->d_ctr) cudaFree(t->d_ctr);
     if (t->h_ctr) cudaFreeHost(t->h_ctr);
@@ -918,7 +996,14 @@ int kh_clear(kh_table* t) {
     if (!t) return KH_ERR_ARG;
     KH_CUDA(t, cudaSetDevice(t->device));
     KH_CUDA(t, cudaEventRecord(t->ev[EV_CLR0], t->stream));
-    KH_CUDA(t, cudaMemsetAsync(t->table, 0, t->table_bytes, t->stream));
+    if (t->ct.on) {              // a chunk table is rewritten chunk by chunk at the next seal: only the staging cursors go back to zero
+        KH_CUDA(t, cudaMemsetAsync(t->ct.reg_cursor.p, 0, kCtMaxRegions * sizeof(u32), t->stream));
+        KH_CUDA(t, cudaMemsetAsync(t->ct.extra_cnt.p, 0, 16, t->stream));
+        t->ct.sealed = false; t->ct.assembled = false;
+        t->ct.n_starts_host = 0;
+    } else {
+        KH_CUDA(t, cudaMemsetAsync(t->table, 0, t->table_bytes, t->stream));
+    }
     KH_CUDA(t, cudaMemsetAsync(t->d_ctr, 0, sizeof(Counters), t->stream));
     KH_CUDA(t, cudaEventRecord(t->ev[EV_CLR1], t->stream));
     t->have_clr = true;
@@ -1048,6 +1133,18 @@ int kh_find_device(kh_table* t, const void* pkmers_dev, uint64_t n, void* pairs_
     if (n == 0) return KH_OK;
     KH_CUDA(t, cudaSetDevice(t->device));
     const unsigned blocks = (unsigned)((n + 255) / 256);
+    if (t->ct.on) {
+        if (t->ct.pe.world > 1) return fail(t, KH_ERR_ARG, "kh_find on a sharded handle is not supported");
+        KH_TRY(t->W == 1 ? ct_seal_plain<1>(t) : ct_seal_plain<2>(t));
+        if (t->W == 1)
+            ct_find_kernel<1><<<blocks, 256, 0, t->stream>>>(static_cast<const u64*>(t->table), static_cast<const u32*>(t->ct.chunk_base.p), t->ct.g,
+                static_cast<const unsigned char*>(pkmers_dev), n, static_cast<unsigned char*>(pairs_dev_out), found_dev_out);
+        else
+            ct_find_kernel<2><<<blocks, 256, 0, t->stream>>>(static_cast<const u128*>(t->table), static_cast<const u32*>(t->ct.chunk_base.p), t->ct.g,
+                static_cast<const unsigned char*>(pkmers_dev), n, static_cast<unsigned char*>(pairs_dev_out), found_dev_out);
+        KH_CUDA(t, cudaGetLastError());
+        return KH_OK;
+    }
     if (t->W == 1)
         find_kernel<1><<<blocks, 256, 0, t->stream>>>(static_cast<const u64*>(t->table), t->nbuckets, t->k, t->mlen,
             static_cast<const unsigned char*>(pkmers_dev), n, static_cast<unsigned char*>(pairs_dev_out), found_dev_out);
@@ -1102,6 +1199,10 @@ int kh_assemble(kh_table* t, const char** contigs_host, const uint64_t** offsets
     if (offsets_host) *offsets_host = static_cast<const uint64_t*>(t->h_off);
     if (rc != KH_OK) return rc;
     const u64 bytes = t->stats.contig_bytes;
+    KH_TRY(ensure_pinned(t, t->h_out, t->h_out_cap, bytes));                    // a chunk table learns its size at the seal
+    KH_TRY(ensure_pinned(t, t->h_off, t->h_off_cap, (t->n_starts + 1) * sizeof(u64)));
+    if (contigs_host) *contigs_host = static_cast<const char*>(t->h_out);
+    if (offsets_host) *offsets_host = static_cast<const uint64_t*>(t->h_off);
     if (bytes) KH_CUDA(t, cudaMemcpyAsync(t->h_out, t->out.p, bytes, cudaMemcpyDeviceToHost, t->stream));
     KH_CUDA(t, cudaMemcpyAsync(t->h_off, t->contig_off.p, (t->n_starts + 1) * sizeof(u64), cudaMemcpyDeviceToHost, t->stream));
     KH_CUDA(t, cudaStreamSynchronize(t->stream));
@@ -1112,6 +1213,7 @@ int kh_assemble(kh_table* t, const char** contigs_host, const uint64_t** offsets
 int kh_get_stats(kh_table* t, kh_stats* out) {
     if (!t || !out) return KH_ERR_ARG;
     KH_CUDA(t, cudaSetDevice(t->device));
+    if (t->ct.on && !t->ct.sharded && !t->ct.sealed && t->table_dirty) KH_TRY(t->W == 1 ? ct_seal_plain<1>(t) : ct_seal_plain<2>(t));
     KH_CUDA(t, cudaStreamSynchronize(t->stream));
     kh_stats& s = t->stats;
     s.n_buckets = t->nbuckets;
@@ -1120,6 +1222,7 @@ int kh_get_stats(kh_table* t, kh_stats* out) {
     s.n_duplicates = t->h_ctr->n_duplicates;
     s.n_starts = t->n_starts;
     s.slot_bits = t->W == 1 ? 64 : 128;
+    if (t->ct.on) s.n_starts = std::min<u64>(t->h_ctr->n_starts_dev, 0xFFFFFFFFull);
     if (t->have_ins) s.ms_insert = elapsed(t->ev[EV_INS0], t->ev[EV_INS1]);
     if (t->have_as) {
         s.ms_assemble = elapsed(t->ev[EV_AS0], t->ev[EV_AS1]);
@@ -1129,6 +1232,9 @@ int kh_get_stats(kh_table* t, kh_stats* out) {
     }
     if (t->have_pack) s.ms_pack = elapsed(t->ev[EV_PACK0], t->ev[EV_PACK1]);
     if (t->have_clr) s.ms_clear = elapsed(t->ev[EV_CLR0], t->ev[EV_CLR1]);
+    if (t->have_build) s.ms_build = elapsed(t->ev[EV_BUILD0], t->ev[EV_BUILD1]);
+    if (t->have_stage && t->have_ins) s.ms_stage = elapsed(t->ev[EV_INS0], t->ev[EV_STAGE1]);
+    s.n_launches = t->n_launches;
     *out = s;
     return KH_OK;
 }
@@ -1179,36 +1285,55 @@ int kh_measure_random_sector_rate(int device, uint64_t footprint_bytes, uint64_t
 // ---------------------------------------------------------------- sharded (multi-GPU) ------
 int kh_shard_init(kh_table* t, int rank, int world, uint64_t n_local_max, uint64_t n_total, uint64_t n_starts_max) {
     if (!t) return KH_ERR_ARG;
+    if (world < 1 || world > kMaxRanks || rank < 0 || rank >= world) return fail(t, KH_ERR_ARG, "1 <= world <= 8 and 0 <= rank < world");
+    if (!ct_supported(t->k)) return fail(t, KH_ERR_ARG, "the sharded path supports 17 <= K <= 54");
+    if (t->ct.connected) return fail(t, KH_ERR_ARG, "kh_shard_init after kh_shard_connect: set options, init, then export and connect");
     KH_CUDA(t, cudaSetDevice(t->device));
-    return t->W == 1 ? shard_init_impl<1>(t, rank, world, n_local_max, n_total, n_starts_max)
-                     : shard_init_impl<2>(t, rank, world, n_local_max, n_total, n_starts_max);
+    const int W = ct_slot_words(t->k);
+    if (W != t->W) {                       // created as a plain table with narrower slots: it is empty, switch
+        t->W = W; t->slot_bytes = W == 1 ? 8 : 16; t->per_bucket = 32 / t->slot_bytes;
+    }
+    return t->W == 1 ? ct_setup<1>(t, rank, world, n_local_max, n_total, n_starts_max, /*sharded=*/true)
+                     : ct_setup<2>(t, rank, world, n_local_max, n_total, n_starts_max, /*sharded=*/true);
 }
 
-int kh_shard_walk(kh_table* t, const void** links_dev_out, uint64_t* counts_out, uint64_t* link_bytes_out) {
-    if (!t || !links_dev_out || !counts_out) return KH_ERR_ARG;
-    KH_TRY(shard_require(t));
-    KH_CUDA(t, cudaSetDevice(t->device));
-    if (link_bytes_out) *link_bytes_out = t->W == 1 ? sizeof(OutEntry<1>) : sizeof(OutEntry<2>);
-    return t->W == 1 ? shard_walk_impl<1>(t, links_dev_out, reinterpret_cast<u64*>(counts_out))
-                     : shard_walk_impl<2>(t, links_dev_out, reinterpret_cast<u64*>(counts_out));
+static int shard_require(kh_table* t) {
+    if (!t->ct.on || !t->ct.sharded) return fail(t, KH_ERR_ARG, "handle is not in sharded mode (call kh_shard_init first)");
+    return KH_OK;
 }
 
-int kh_shard_resolve(kh_table* t, const void* links_dev, uint64_t n) {
-    if (!t || (n && !links_dev)) return KH_ERR_ARG;
-    KH_TRY(shard_require(t));
-    KH_CUDA(t, cudaSetDevice(t->device));
-    return t->W == 1 ? shard_resolve_impl<1>(t, links_dev, n) : shard_resolve_impl<2>(t, links_dev, n);
+int kh_shard_export_count(void) { return CTX_NBUF; }
+
+static void ct_export_list(kh_table* t, void* (&bufs)[CTX_NBUF]) {
+    auto& c = t->ct;
+    bufs[CTX_STAGE_VALS] = c.stage_vals.p; bufs[CTX_STAGE_TAGS] = c.stage_tags.p; bufs[CTX_STAGE_CNT] = c.stage_cnt.p;
+    bufs[CTX_EXTRA_VALS] = c.extra_vals.p; bufs[CTX_EXTRA_CHUNK] = c.extra_chunk.p; bufs[CTX_EXTRA_CNT] = c.extra_cnt.p;
+    bufs[CTX_LINK] = t->link.p; bufs[CTX_META] = c.meta.p; bufs[CTX_INBOX] = c.inbox.p; bufs[CTX_INBOX_CNT] = c.inbox_cnt.p;
+    bufs[CTX_PRE] = t->contig_pre.p; bufs[CTX_OFF] = t->contig_off.p; bufs[CTX_OUT] = t->out.p; bufs[CTX_FLAGS] = c.flags.p;
+}
+static void ct_import_list(kh_table* t, int r, void* const (&p)[CTX_NBUF], u64 out_cap) {
+    CtPeers& pe = t->ct.pe;
+    pe.stage_vals[r] = p[CTX_STAGE_VALS]; pe.stage_tags[r] = static_cast<unsigned short*>(p[CTX_STAGE_TAGS]);
+    pe.stage_cnt[r] = static_cast<u32*>(p[CTX_STAGE_CNT]);
+    pe.extra_vals[r] = p[CTX_EXTRA_VALS]; pe.extra_chunk[r] = static_cast<u32*>(p[CTX_EXTRA_CHUNK]);
+    pe.extra_cnt[r] = static_cast<u32*>(p[CTX_EXTRA_CNT]);
+    pe.link[r] = static_cast<u64*>(p[CTX_LINK]); pe.meta[r] = static_cast<u64*>(p[CTX_META]);
+    pe.inbox[r] = p[CTX_INBOX]; pe.inbox_cnt[r] = static_cast<u32*>(p[CTX_INBOX_CNT]);
+    pe.contig_pre[r] = static_cast<u32*>(p[CTX_PRE]); pe.contig_off[r] = static_cast<u64*>(p[CTX_OFF]);
+    pe.out[r] = static_cast<char*>(p[CTX_OUT]); pe.out_cap[r] = out_cap;
+    pe.flags[r] = static_cast<u32*>(p[CTX_FLAGS]);
 }
 
 int kh_shard_export(kh_table* t, void* handles_out, uint64_t* meta_out) {
     if (!t || !handles_out || !meta_out) return KH_ERR_ARG;
     KH_TRY(shard_require(t));
     KH_CUDA(t, cudaSetDevice(t->device));
-    void* bufs[SH_NBUF] = {t->table, t->link.p, t->seglen.p, t->contig_pre.p, t->contig_off.p, t->out.p};
+    void* bufs[CTX_NBUF];
+    ct_export_list(t, bufs);
     cudaIpcMemHandle_t* h = static_cast<cudaIpcMemHandle_t*>(handles_out);
-    for (int i = 0; i < SH_NBUF; ++i) KH_CUDA(t, cudaIpcGetMemHandle(&h[i], bufs[i]));
-    meta_out[0] = t->nbuckets;
-    meta_out[1] = t->shard_out_cap;
+    for (int i = 0; i < CTX_NBUF; ++i) KH_CUDA(t, cudaIpcGetMemHandle(&h[i], bufs[i]));
+    meta_out[0] = t->ct.g.chunks_per_rank;
+    meta_out[1] = t->ct.out_cap;
     return KH_OK;
 }
 
@@ -1216,33 +1341,33 @@ int kh_shard_connect(kh_table* t, const void* all_handles, const uint64_t* all_m
     if (!t || !all_handles || !all_meta) return KH_ERR_ARG;
     KH_TRY(shard_require(t));
     KH_CUDA(t, cudaSetDevice(t->device));
-    Peers& pe = t->peers;
+    auto& c = t->ct;
     const cudaIpcMemHandle_t* h = static_cast<const cudaIpcMemHandle_t*>(all_handles);
-    for (int r = 0; r < pe.world; ++r) {
-        if (r == pe.rank) continue;
-        void* p[SH_NBUF];
-        for (int i = 0; i < SH_NBUF; ++i) {
-            KH_CUDA(t, cudaIpcOpenMemHandle(&p[i], h[r * SH_NBUF + i], cudaIpcMemLazyEnablePeerAccess));
-            t->ipc_opened[r][i] = p[i];
+    for (int r = 0; r < c.pe.world; ++r) {
+        if (r == c.pe.rank) continue;
+        if (all_meta[2 * r] != c.g.chunks_per_rank) return fail(t, KH_ERR_ARG, "ranks disagree on the table geometry (same n_total, load factor and K everywhere)");
+        void* p[CTX_NBUF];
+        for (int i = 0; i < CTX_NBUF; ++i) {
+            KH_CUDA(t, cudaIpcOpenMemHandle(&p[i], h[r * CTX_NBUF + i], cudaIpcMemLazyEnablePeerAccess));
+            c.ipc_opened[r][i] = p[i];
         }
-        pe.table[r] = p[SH_TABLE]; pe.nbuckets[r] = all_meta[2 * r];
-        pe.link[r] = static_cast<u64*>(p[SH_LINK]); pe.seglen[r] = static_cast<unsigned char*>(p[SH_SEGLEN]);
-        pe.contig_pre[r] = static_cast<u32*>(p[SH_PRE]); pe.contig_off[r] = static_cast<u64*>(p[SH_OFF]);
-        pe.out[r] = static_cast<char*>(p[SH_OUT]); pe.out_cap[r] = all_meta[2 * r + 1];
+        ct_import_list(t, r, p, all_meta[2 * r + 1]);
     }
+    c.connected = true;
     return KH_OK;
 }
 
-// All ranks live in this process (tests on one GPU, or one process driving several GPUs with peer
-// access enabled): wire the peers up from their handles directly.
+// All ranks live in this process (one host thread per GPU, or several ranks emulated on one GPU in the tests)
 int kh_shard_connect_local(kh_table* t, kh_table* const* peers, int world) {
     if (!t || !peers) return KH_ERR_ARG;
     KH_TRY(shard_require(t));
-    if (world != t->peers.world) return fail(t, KH_ERR_ARG, "world does not match kh_shard_init");
-    Peers& pe = t->peers;
+    auto& c = t->ct;
+    if (world != c.pe.world) return fail(t, KH_ERR_ARG, "world does not match kh_shard_init");
     for (int r = 0; r < world; ++r) {
-        const kh_table* q = peers[r];
-        if (!q || !q->shard_on || q->k != t->k) return fail(t, KH_ERR_ARG, "peer handle is not an initialised shard of the same K");
+        kh_table* q = peers[r];
+        if (!q || !q->ct.on || !q->ct.sharded || q->k != t->k || q->ct.pe.rank != r || q->ct.g.chunks_per_rank != c.g.chunks_per_rank)
+            return fail(t, KH_ERR_ARG, "peer handle is not shard r of the same table (same K, n_total, load factor)");
+        if (q == t) continue;
         if (q->device != t->device) {
             int can = 0;
             cudaDeviceCanAccessPeer(&can, t->device, q->device);
@@ -1252,33 +1377,53 @@ int kh_shard_connect_local(kh_table* t, kh_table* const* peers, int world) {
             if (e != cudaSuccess && e != cudaErrorPeerAccessAlreadyEnabled) return fail(t, KH_ERR_CUDA, cudaGetErrorString(e));
             cudaGetLastError();
         }
-        pe.table[r] = q->table; pe.nbuckets[r] = q->nbuckets;
-        pe.link[r] = static_cast<u64*>(q->link.p); pe.seglen[r] = static_cast<unsigned char*>(q->seglen.p);
-        pe.contig_pre[r] = static_cast<u32*>(q->contig_pre.p); pe.contig_off[r] = static_cast<u64*>(q->contig_off.p);
-        pe.out[r] = static_cast<char*>(q->out.p); pe.out_cap[r] = q->shard_out_cap;
+        void* p[CTX_NBUF];
+        ct_export_list(q, p);
+        ct_import_list(t, r, p, q->ct.out_cap);
     }
+    c.connected = true;
     return KH_OK;
 }
 
-int kh_shard_owner_partition(kh_table* t, const void* pairs_dev, uint64_t n, const void** slots_dev_out, uint64_t* counts_out) {
-    if (!t || !slots_dev_out || !counts_out || (n && !pairs_dev)) return KH_ERR_ARG;
+// empty table + barrier: no rank may start writing into a peer before that peer has reset its counters
+int kh_shard_begin(kh_table* t) {
+    if (!t) return KH_ERR_ARG;
+    KH_TRY(shard_require(t));
+    KH_TRY(kh_clear(t));
+    return ct_barrier(t);
+}
+
+int kh_shard_insert(kh_table* t, const void* pairs_dev, uint64_t n) {
+    if (!t || (n && !pairs_dev)) return KH_ERR_ARG;
     KH_TRY(shard_require(t));
     KH_CUDA(t, cudaSetDevice(t->device));
-    return t->W == 1 ? shard_owner_partition_impl<1>(t, static_cast<const unsigned char*>(pairs_dev), n, slots_dev_out, reinterpret_cast<u64*>(counts_out))
-                     : shard_owner_partition_impl<2>(t, static_cast<const unsigned char*>(pairs_dev), n, slots_dev_out, reinterpret_cast<u64*>(counts_out));
+    if (!t->have_ins || t->ct.sealed || !t->table_dirty) KH_CUDA(t, cudaEventRecord(t->ev[EV_INS0], t->stream));
+    return t->W == 1 ? ct_stage<1>(t, static_cast<const unsigned char*>(pairs_dev), n)
+                     : ct_stage<2>(t, static_cast<const unsigned char*>(pairs_dev), n);
 }
 
-int kh_insert_slots_device(kh_table* t, const void* slots_dev, uint64_t n) {
-    if (!t || (n && !slots_dev)) return KH_ERR_ARG;
-    KH_CUDA(t, cudaSetDevice(t->device));
-    return t->W == 1 ? insert_slots_impl<1>(t, slots_dev, n) : insert_slots_impl<2>(t, slots_dev, n);
-}
+int kh_shard_assemble_parts(void) { return kCtParts; }
 
-int kh_shard_phase(kh_table* t, int phase, int* flag_out) {
+int kh_shard_assemble_part(kh_table* t, int part) {
     if (!t) return KH_ERR_ARG;
     KH_TRY(shard_require(t));
     KH_CUDA(t, cudaSetDevice(t->device));
-    return t->W == 1 ? shard_phase_impl<1>(t, phase, flag_out) : shard_phase_impl<2>(t, phase, flag_out);
+    return t->W == 1 ? ct_assemble_part<1>(t, part) : ct_assemble_part<2>(t, part);
+}
+
+int kh_shard_assemble(kh_table* t) {
+    for (int part = 0; part < kCtParts; ++part) KH_TRY(kh_shard_assemble_part(t, part));
+    return KH_OK;
+}
+
+int kh_shard_finish(kh_table* t, int* error_bits_out) {
+    if (!t) return KH_ERR_ARG;
+    KH_TRY(shard_require(t));
+    KH_CUDA(t, cudaSetDevice(t->device));
+    u32 bits = 0;
+    KH_TRY(ct_finish(t, &bits));
+    if (error_bits_out) *error_bits_out = (int)bits;
+    return KH_OK;
 }
 
 int kh_shard_result(kh_table* t, const char** contigs_dev, const uint64_t** offsets_dev,
@@ -1293,7 +1438,29 @@ int kh_shard_result(kh_table* t, const char** contigs_dev, const uint64_t** offs
     return KH_OK;
 }
 
-uint64_t kh_slot_bytes(int k) { return (2 * k + 6 <= 64) ? 8 : 16; }
+// introspection for tests and debugging: device pointer and size of an internal buffer of a chunk table
+int kh_debug_buffer(kh_table* t, const char* name, void** ptr_out, uint64_t* bytes_out) {
+    if (!t || !name || !ptr_out || !bytes_out) return KH_ERR_ARG;
+    auto& c = t->ct;
+    const std::string n(name);
+    const DevBuf* b = nullptr;
+    if (n == "link") b = &t->link; else if (n == "meta") b = &c.meta; else if (n == "ext_key") b = &c.ext_key;
+    else if (n == "chunk_base") b = &c.chunk_base; else if (n == "seg_base") b = &c.seg_base; else if (n == "chunk_cursor") b = &c.chunk_cursor;
+    else if (n == "inbox_cnt") b = &c.inbox_cnt; else if (n == "out_cursor") b = &c.out_cursor; else if (n == "stage_cnt") b = &c.stage_cnt;
+    else if (n == "contig_len") b = &t->contig_len; else if (n == "pool") b = &c.pool;
+    else if (n == "counters") { *ptr_out = t->d_ctr; *bytes_out = sizeof(Counters); return KH_OK; }
+    else if (n == "caps") {          // host-side numbers: hcap, seg_cap, inbox_cap, cap_rs, chunks_per_rank, regions_per_rank
+        static thread_local uint64_t v[8];
+        v[0] = c.caps.hcap; v[1] = c.caps.seg_cap; v[2] = c.caps.inbox_cap; v[3] = c.caps.cap_rs; v[4] = c.g.chunks_per_rank; v[5] = c.g.regions_per_rank;
+        v[6] = c.epoch; v[7] = c.g.cpr_shift;
+        *ptr_out = v; *bytes_out = sizeof(v); return KH_OK;
+    }
+    if (!b) return fail(t, KH_ERR_ARG, "unknown buffer " + n);
+    *ptr_out = b->p; *bytes_out = b->cap;
+    return KH_OK;
+}
+
+uint64_t kh_slot_bytes(int k) { return (ct_supported(k) ? ct_slot_words(k) : ((2 * k + 6 <= 64) ? 1 : 2)) * 8; }
 
 // device -> host copy on the handle's stream, synchronous (tests / result collection)
 int kh_copy_to_host(kh_table* t, void* dst_host, const void* src_dev, uint64_t bytes) {

@@ -36,7 +36,6 @@
 //   meta[seg]  = (offset of the segment's characters in the rank's character pool << 24) | number of characters
 #pragma once
 #include "kernels.cuh"
-#include "sharded.cuh"
 
 namespace kh {
 
@@ -73,7 +72,7 @@ struct CtPeers {
     u64* contig_off[kMaxRanks];
     char* out[kMaxRanks];
     u64 out_cap[kMaxRanks];
-    u32* flags[kMaxRanks];                // barrier: flags[r][s] = last epoch rank s signalled to rank r
+    u32* flags[kMaxRanks];                // barrier: flags[r][2 * s + parity] = (epoch << 1 | payload bit) rank s signalled to rank r
 };
 
 struct CtCaps {
@@ -86,24 +85,35 @@ struct CtCaps {
 // the previous kernels of this stream wrote -- including stores into peer memory -- is complete when this kernel
 // starts, and the release/acquire pair orders the flag against them.  A peer that never arrives (it failed) ends
 // the wait after ~4 s with kErrInternal instead of hanging the GPU.
-__global__ void ct_barrier_kernel(const CtPeers pe, u32 epoch, Counters* ctr) {
+// The flag carries one payload bit next to the epoch.  The barriers between pointer-jumping rounds (round >= 0)
+// use it for "this rank moved a link in this round": every rank sees the same bits, so all of them agree when
+// nobody moved -- they set rank_done and the remaining round and barrier kernels of the step return at once.
+__global__ void ct_barrier_kernel(const CtPeers pe, u32 epoch, Counters* ctr, int round) {
     const int r = (int)threadIdx.x;
-    if (r >= pe.world) return;
-    __threadfence_system();
-    u32* dst = pe.flags[r] + pe.rank;
-    asm volatile("st.release.sys.global.u32 [%0], %1;" ::"l"(dst), "r"(epoch) : "memory");
-    const u32* src = pe.flags[pe.rank] + r;
-    unsigned long long t0, t1;
-    asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t0));
-    for (;;) {
-        u32 seen;
-        asm volatile("ld.acquire.sys.global.u32 %0, [%1];" : "=r"(seen) : "l"(src) : "memory");
-        if ((int)(seen - epoch) >= 0) break;
-        asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t1));
-        if (t1 - t0 > 4000000000ull) { atomicOr(&ctr->errors, kErrInternal); break; }
-        __nanosleep(200);
+    if (round >= 0 && ctr->rank_done) return;                    // agreed on by all ranks: nobody waits here any more
+    const u32 bit = round >= 0 ? (ctr->flags[round] ? 1u : 0u) : 0u;
+    u32 peer_bit = 0;
+    if (r < pe.world) {
+        __threadfence_system();
+        u32* dst = pe.flags[r] + 2 * pe.rank + (epoch & 1u);           // two slots per peer, by epoch parity: a peer that is already
+        asm volatile("st.release.sys.global.u32 [%0], %1;" ::"l"(dst), "r"((epoch << 1) | bit) : "memory");
+        const u32* src = pe.flags[pe.rank] + 2 * r + (epoch & 1u);      // one barrier ahead cannot overwrite the value we still have to read
+        unsigned long long t0, t1;
+        asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t0));
+        for (;;) {
+            u32 seen;
+            asm volatile("ld.acquire.sys.global.u32 %0, [%1];" : "=r"(seen) : "l"(src) : "memory");
+            if ((int)((seen >> 1) - epoch) >= 0) { peer_bit = ((seen >> 1) == epoch) ? (seen & 1u) : 1u; break; }
+            asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t1));
+            if (t1 - t0 > 4000000000ull) { atomicOr(&ctr->errors, kErrInternal); peer_bit = 1; break; }
+            __nanosleep(200);
+        }
+        __threadfence_system();
     }
-    __threadfence_system();
+    if (round >= 0) {
+        const u32 any = __ballot_sync(kFullMask, peer_bit != 0);
+        if (r == 0 && any == 0) ctr->rank_done = 1;
+    }
 }
 
 // ---- pass A: stage records, grouped by table region, in the owner's memory --------------------------------
@@ -725,14 +735,16 @@ ct_answer_kernel(const typename Slot<W>::value_t* __restrict__ table, const u32*
 
 // ---- pointer jumping over segment lists that span GPUs --------------------------------------------------------------
 // A link is FINAL (top bit of the distance word) once its pointer is the chain's last segment (high word a marker);
-// a link that is not final always moves when it is visited, so "nothing moved here" means this rank is done for good
-// and needs no agreement with the others: round r returns at once if round r-1 moved nothing on this rank.
+// a link that is not final always moves when it is visited, so "nothing moved here" means this rank's links are final
+// for good and it only keeps the others company at the barriers.  The rounds of all ranks run in lockstep (a barrier
+// after each, ct_barrier_kernel): jumping over a peer's link doubles the distance only if the peer jumps too --
+// ranks that ran their rounds on their own would walk a chain one remote segment per round.
 __device__ __forceinline__ u64* ct_peer_link(const CtPeers& pe, u32 gid) { return pe.link[gid >> kRankShift] + (gid & kLocalMask); }
 __device__ __forceinline__ bool ct_is_end_marker(u32 hi) { return hi == kLinkTail || hi == kLinkClaimed || hi == kLinkMissing || hi == kLinkConverge; }
 
 __global__ void __launch_bounds__(256)
 ct_rank_round_kernel(const CtPeers pe, u64* __restrict__ link, const CtCaps caps, Counters* ctr, u32* __restrict__ moved, int round) {
-    if (round > 0 && moved[round - 1] == 0) return;
+    if (ctr->rank_done || (round > 0 && moved[round - 1] == 0)) return;     // everybody / this rank has only final links
     const u32 nseg = min(ctr->next_seg, caps.seg_cap);
     bool any = false;
     for (u64 i = (u64)blockIdx.x * blockDim.x + threadIdx.x; i < nseg; i += (u64)gridDim.x * blockDim.x) {

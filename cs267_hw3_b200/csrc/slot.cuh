@@ -227,6 +227,9 @@ template <> struct Slot<2> {
         if (s == 0) return v;
         return u128{(v.lo >> s) | (v.hi << (64 - s)), v.hi >> s};
     }
+    static __host__ __device__ __forceinline__ value_t shr_any(value_t v, int s) {   // 0 <= s < 128
+        return s >= 64 ? u128{v.hi >> (s - 64), 0ull} : shr(v, s);
+    }
     static __host__ __device__ __forceinline__ value_t be_bytes(const unsigned char* p, int pl) {
         u128 x{0ull, 0ull};
         for (int i = 0; i < pl; ++i) {
@@ -246,7 +249,7 @@ template <> struct Slot<2> {
     static __device__ __forceinline__ value_t from_record_staged(const unsigned char* rec, int k, int pl, bool& ok) {
         u64 hi, lo;
         lds_be128(rec, hi, lo);
-        u128 v = shr(u128{lo, hi}, 122 - 2 * k);        // key << 6; 0 <= 122 - 2K <= 62 for 30 <= K <= 61
+        u128 v = shr_any(u128{lo, hi}, 122 - 2 * k);    // key << 6; 122 - 2K is 0..62 for K >= 30 and up to 88 for the short K a chunk table keeps in 128-bit slots
         const u32 b = ext_code(rec[pl]), f = ext_code(rec[pl + 1]);
         ok = (b != kExtBad) && (f != kExtBad);
         v.lo = (v.lo & ~63ull) | ((u64)(b & 7u) << 3) | (u64)((f + 1u) & 7u);
@@ -268,8 +271,9 @@ template <> struct Slot<2> {
     static __host__ __device__ __forceinline__ value_t next_key(value_t v, int k) {
         u128 n = shl(u128{v.lo & ~63ull, v.hi}, 2);
         n.lo |= (u64)fwd(v) << 6;
-        const int bits = 2 * k + 6;            // 66..128 for K in 30..61
-        if (bits < 128) n.hi &= (1ull << (bits - 64)) - 1ull;
+        const int bits = 2 * k + 6;            // 66..128 for K in 30..61; below 64 for the short K a chunk table keeps in 128-bit slots
+        if (bits <= 64) { n.hi = 0ull; if (bits < 64) n.lo &= (1ull << bits) - 1ull; }
+        else if (bits < 128) n.hi &= (1ull << (bits - 64)) - 1ull;
         return n;
     }
     static __host__ __device__ __forceinline__ u32 base_at(value_t v, int k, int i) {
@@ -488,6 +492,14 @@ __host__ __device__ __forceinline__ void ct_place(u32 minhash, const CtGeom& g, 
 #endif
 }
 
+// multi-GPU: global segment id = (rank << kRankShift) | local id
+constexpr int kMaxRanks = 8;
+constexpr u32 kRankShift = 28;
+constexpr u32 kLocalMask = (1u << kRankShift) - 1u;
+// pointer jumping: a link whose pointer already is its chain's last segment is flagged in the top bit of the distance
+// word, so later rounds do not pay a (possibly remote) read for it
+constexpr u32 kLinkFinalBit = 0x80000000u;
+constexpr u32 kLinkDistMask = 0x7FFFFFFFu;
 constexpr u32 kLinkMissing = 0xFFFFFFFBu;   // ctable: the successor k-mer is in no table (raised only if a start-rooted contig ends here)
 constexpr u32 kLinkConverge = 0xFFFFFFFAu;  // ctable: the successor k-mer sits in the middle of another segment (it has two predecessors)
 constexpr u32 kLinkCtFirstMarker = kLinkConverge;
@@ -517,6 +529,8 @@ struct Counters {
     u32 n_boundary;       // sharded: nodes of this shard whose predecessor lives on another GPU (walker starts)
     u32 n_outbox;         // sharded: pending links produced by the local walk
     u32 flags[40];
+    u32 rank_done;        // ctable: no rank moved a link in the last pointer-jumping round (agreed on by all ranks)
+    u32 pad0;
     u64 n_starts_dev;     // ctable: start nodes registered so far (kept on the device: no host round trip per insert)
 };
 

@@ -1,22 +1,26 @@
 """Multi-GPU (hash-sharded) insert + traverse: host-side orchestration over the C ABI.
 
-Replaces what the reference does with UPC++: the table is sharded by
-``owner = hash(key) % ranks`` (hash_map.hpp:28-30); every rank groups its block of records by owner
-(K7), the groups cross ranks in ONE all-to-all (NCCL over NVLink through torch.distributed; the
-reference issues one blocking RPC per destination, hash_map.hpp:64-77), each rank inserts what it
-received (K2).  During the walk a successor lookup reads the owner's table directly through its
-NVLink peer mapping (K8) -- the one-sided analogue of the reference's per-lookup RPC round trip
-(hash_map.hpp:93-100) -- and the segment lists are stitched by pointer jumping across GPUs.
-Rank r emits the contigs whose start node lies in its block of input lines, in input order
-(kmer_hash.cpp:27-31, read_kmers.hpp:55-58), exactly like the reference's ``<prefix>_<r>.dat``.
+Replaces what the reference does with UPC++: the table is sharded by owner rank
+(hash_map.hpp:28-30); inserts travel as one batch per destination (hash_map.hpp:64-77), finds are RPC round
+trips (hash_map.hpp:93-100).  Here a rank owns a contiguous range of table CHUNKS (csrc/ctable.cuh) and the
+owner of a k-mer follows from its minimizer, so consecutive k-mers of a contig live on one GPU.  A step is
+SPMD and stream-ordered, exactly as in include/kh_capi.h:
 
-Two communicators:
-  * TorchComm  -- one process per GPU (torchrun), NCCL for the exchange and the barriers, CUDA IPC for
-                  the peer mappings.  This is the product path.
-  * LocalComm  -- all ranks in one process (even on ONE GPU): the same kernels and phases with the
-                  exchange done by device copies.  Used by the tests on single-GPU boxes.
-The pure-host pieces (owner function mirror, exchange plan, ``exchange_bytes``) run on CPU tensors
-with the gloo backend (tests/test_sharded_host.py).
+    kh_shard_begin -> kh_shard_insert -> kh_shard_assemble -> kh_shard_finish
+
+The records reach their owner GPU through NVLink peer stores inside the grouping kernel (no separate all-to-all
+step), chain links that leave a GPU and their answers travel the same way, phases are separated by an in-stream
+barrier kernel; the host only waits in kh_shard_finish.  Rank r emits the contigs whose start node lies in its
+block of input lines, in input order (kmer_hash.cpp:27-31, read_kmers.hpp:55-58) -- the reference's
+``<prefix>_<r>.dat``.
+
+Two ways to host the ranks:
+  * TorchComm  -- one process per GPU (torchrun): torch.distributed moves the CUDA IPC handles once at start-up
+                  and reduces the error bits at the end; nothing else crosses the host.  This is what bench.py runs.
+  * LocalComm  -- all ranks in this process (even on ONE GPU): the same calls, enqueued part by part for all
+                  ranks in turn (kh_shard_assemble_part) so that barrier kernels of ranks that share a device
+                  cannot block each other's queued work.  Used by the tests on single-GPU boxes.
+The C++ twin (one host thread per GPU) is include/kh/sharded_host.hpp.
 """
 from __future__ import annotations
 
@@ -27,6 +31,7 @@ import numpy as np
 
 MAX_RANKS = 8
 _M64 = (1 << 64) - 1
+_M32 = (1 << 32) - 1
 
 
 # ---------------------------------------------------------------------------- host mirrors ----
@@ -50,43 +55,29 @@ def slot_from_pair(pair: bytes, k: int) -> int:
     return (key << 6) | (ext_code(pair[pl]) << 3) | (ext_code(pair[pl + 1]) + 1)
 
 
-def minimizer_len(k: int) -> int:
-    return k if k <= 14 else (11 if k <= 18 else (13 if k <= 29 else (21 if k <= 40 else 31)))
+def ct_minimizer_len(k: int) -> int:
+    return 15 if k >= 31 else (13 if k >= 23 else (k - 6 if k >= 17 else k))
 
 
-def owner_minimizer_len(k: int) -> int:
-    return k if k <= 14 else 7
+def ct_window(k: int) -> int:
+    return min(32, k - ct_minimizer_len(k) + 1)
 
 
-def minimizer_value(slot: int, k: int, m: int) -> int:
-    """The m-mer of the k-mer with the smallest order value, leftmost on ties (csrc/slot.cuh)."""
-    key, mask = slot >> 6, (1 << (2 * m)) - 1
-    best, bx = 1 << 32, 0
-    for s in range(2 * (k - m), -1, -2):
-        x = (key >> s) & mask
-        g = ((x * 0x9E3779B97F4A7C15) & _M64) >> 32
-        if g < best:
-            best, bx = g, x
-    return bx
+def ct_min_hash(slot: int, k: int) -> int:
+    """Mirror of ct_min_hash<W>() (csrc/slot.cuh): min over the `win` rightmost m-mers of (x ^ seed) * odd mod 2^32."""
+    key, m, win = slot >> 6, ct_minimizer_len(k), ct_window(k)
+    mask = (1 << (2 * m)) - 1
+    return min((((key >> (2 * j)) & mask) ^ 0x5BD1E995) * 0x9E3779B1 & _M32 for j in range(win))
 
 
-def owner_of_slot(slot: int, k: int, world: int, locality: bool = True) -> int:
-    """Mirror of owner_of<W>() in csrc/sharded.cuh (tests compare it with the GPU's grouping).
-
-    locality=True: the owner is a hash of the k-mer's minimizer, so the successor of a k-mer usually has the
-    same owner; False: plain hash of the key (KH_LOCALITY=0)."""
-    if locality:
-        h = _fmix64((minimizer_value(slot, k, owner_minimizer_len(k)) + 0x632BE59BD9B4E019) & _M64)
-    elif 2 * k + 6 <= 64:
-        h = _fmix64((slot >> 6) ^ 0x9E3779B97F4A7C15)
-    else:
-        lo, hi = slot & _M64, slot >> 64
-        h = _fmix64(((lo >> 6) + 0xD6E8FEB86659FD93 + _fmix64(hi ^ 0xA0761D6478BD642F)) & _M64)
+def owner_of_slot(slot: int, k: int, world: int) -> int:
+    """Mirror of ct_place() (csrc/slot.cuh): the rank that owns a k-mer (tests compare it with where the GPU put it)."""
+    h = _fmix64((ct_min_hash(slot, k) + 0x632BE59BD9B4E019) & _M64)
     return (h * world) >> 64
 
 
 def slot_bytes(k: int) -> int:
-    return 8 if 2 * k + 6 <= 64 else 16
+    return 8 if (17 <= k <= 54 and 2 * k + 6 + 14 <= 64) or (not 17 <= k <= 54 and 2 * k + 6 <= 64) else 16
 
 
 def block_of_rank(n: int, world: int, rank: int) -> tuple[int, int]:
@@ -97,32 +88,10 @@ def block_of_rank(n: int, world: int, rank: int) -> tuple[int, int]:
 
 
 def shard_capacity(n_total: int, world: int) -> int:
-    """k-mers a shard must be able to hold: its expected share plus slack.  With minimizer-keyed ownership whole
-    supermers (runs of ~4-16 k-mers) move together, so the spread is a few times the binomial one."""
+    """k-mers a shard must be able to hold: its expected share plus slack.  Ownership follows the minimizer, so whole
+    supermers (runs of ~4-16 k-mers) move together and the spread is a few times the binomial one."""
     share = n_total / world
-    return int(share * 1.005 + 40.0 * math.sqrt(share + 1.0)) + 1024
-
-
-def exchange_bytes(send, send_counts, elem_bytes, group=None):
-    """All-to-all of variable-size groups of `elem_bytes`-byte elements (torch tensors, any backend).
-
-    send        uint8 tensor: the groups for rank 0, 1, ... back to back
-    send_counts elements per destination
-    returns (recv uint8 tensor, recv_counts list)
-    """
-    import torch
-    import torch.distributed as dist
-
-    world = dist.get_world_size(group)
-    sc = torch.tensor(list(send_counts[:world]), dtype=torch.int64, device=send.device)
-    rc = torch.empty_like(sc)
-    dist.all_to_all_single(rc, sc, group=group)
-    recv_counts = [int(x) for x in rc.tolist()]
-    recv = torch.empty(sum(recv_counts) * elem_bytes, dtype=torch.uint8, device=send.device)
-    dist.all_to_all_single(recv, send[: sum(send_counts[:world]) * elem_bytes],
-                           output_split_sizes=[x * elem_bytes for x in recv_counts],
-                           input_split_sizes=[int(x) * elem_bytes for x in send_counts[:world]], group=group)
-    return recv, recv_counts
+    return int(share * 1.02 + 64.0 * math.sqrt(share + 1.0)) + 4096
 
 
 # ---------------------------------------------------------------------------- shard object ----
@@ -133,7 +102,7 @@ class Shard:
                  load_factor: float = 0.5, device: int = 0, n_starts_max: int | None = None):
         import cs267_hw3_b200 as kh
 
-        self.kh, self.k, self.rank, self.world = kh, k, rank, world
+        self.kh, self.k, self.rank, self.world, self.device = kh, k, rank, world, device
         self.n_local_max, self.n_total = n_local_max, n_total
         self.n_starts_max = n_local_max if n_starts_max is None else n_starts_max
         self.tab = kh.KmerHashTable(k, shard_capacity(n_total, world), load_factor, device)
@@ -142,7 +111,7 @@ class Shard:
         self.reinit()
 
     def reinit(self) -> None:
-        """(Re)compute the fixed capacities, e.g. after changing split_buckets / seg_chars."""
+        """Fix the capacities (after setting options, before connecting the peers)."""
         self.tab._check(self.kh.lib().kh_shard_init(self.tab._h, self.rank, self.world, self.n_local_max, self.n_total,
                                                     self.n_starts_max))
 
@@ -152,48 +121,42 @@ class Shard:
             return
         vp, u64, i32 = C.c_void_p, C.c_uint64, C.c_int
         L.kh_shard_init.argtypes = [vp, i32, i32, u64, u64, u64]
-        L.kh_shard_walk.argtypes = [vp, C.POINTER(vp), C.POINTER(u64), C.POINTER(u64)]
-        L.kh_shard_resolve.argtypes = [vp, vp, u64]
+        L.kh_shard_export_count.restype = i32
         L.kh_shard_export.argtypes = [vp, vp, C.POINTER(u64)]
         L.kh_shard_connect.argtypes = [vp, vp, C.POINTER(u64)]
         L.kh_shard_connect_local.argtypes = [vp, C.POINTER(vp), i32]
-        L.kh_shard_owner_partition.argtypes = [vp, vp, u64, C.POINTER(vp), C.POINTER(u64)]
-        L.kh_insert_slots_device.argtypes = [vp, vp, u64]
-        L.kh_shard_phase.argtypes = [vp, i32, C.POINTER(i32)]
+        L.kh_shard_begin.argtypes = [vp]
+        L.kh_shard_insert.argtypes = [vp, vp, u64]
+        L.kh_shard_assemble.argtypes = [vp]
+        L.kh_shard_assemble_parts.restype = i32
+        L.kh_shard_assemble_part.argtypes = [vp, i32]
+        L.kh_shard_finish.argtypes = [vp, C.POINTER(i32)]
         L.kh_shard_result.argtypes = [vp, C.POINTER(vp), C.POINTER(vp), C.POINTER(u64), C.POINTER(u64), C.POINTER(u64)]
         L.kh_slot_bytes.argtypes = [i32]
         L.kh_slot_bytes.restype = u64
         L.kh_device_alloc.argtypes = [C.POINTER(vp), u64]
+        L.kh_device_alloc_on.argtypes = [i32, C.POINTER(vp), u64]
         L.kh_device_free.argtypes = [vp]
         L.kh_copy_to_host.argtypes = [vp, vp, vp, u64]
         L.kh_copy_device.argtypes = [vp, vp, vp, u64]
         L._shard_declared = True
 
-    # -- K7 --
-    def owner_partition(self, pairs_dev: int, n: int) -> tuple[int, list[int]]:
-        L = self.kh.lib()
-        out = C.c_void_p()
-        counts = (C.c_uint64 * MAX_RANKS)()
-        self.tab._check(L.kh_shard_owner_partition(self.tab._h, pairs_dev, n, C.byref(out), counts))
-        return out.value or 0, [int(x) for x in counts][: self.world]
+    def begin(self) -> None:
+        self.tab._check(self.kh.lib().kh_shard_begin(self.tab._h))
 
-    def insert_slots(self, slots_dev: int, n: int) -> None:
-        self.tab._check(self.kh.lib().kh_insert_slots_device(self.tab._h, slots_dev, n))
+    def insert(self, pairs_dev: int, n: int) -> None:
+        self.tab._check(self.kh.lib().kh_shard_insert(self.tab._h, pairs_dev, n))
 
-    def walk(self) -> tuple[int, list[int], int]:
-        """K8: local walk; returns (device ptr of pending links grouped by destination, counts, bytes per link)."""
-        out, nb = C.c_void_p(), C.c_uint64()
-        counts = (C.c_uint64 * MAX_RANKS)()
-        self.tab._check(self.kh.lib().kh_shard_walk(self.tab._h, C.byref(out), counts, C.byref(nb)))
-        return out.value or 0, [int(x) for x in counts][: self.world], int(nb.value)
+    def assemble(self) -> None:
+        self.tab._check(self.kh.lib().kh_shard_assemble(self.tab._h))
 
-    def resolve(self, links_dev: int, n: int) -> None:
-        self.tab._check(self.kh.lib().kh_shard_resolve(self.tab._h, links_dev, n))
+    def assemble_part(self, part: int) -> None:
+        self.tab._check(self.kh.lib().kh_shard_assemble_part(self.tab._h, part))
 
-    def phase(self, which: int) -> int:
-        flag = C.c_int()
-        self.tab._check(self.kh.lib().kh_shard_phase(self.tab._h, which, C.byref(flag)))
-        return flag.value
+    def finish(self) -> int:
+        bits = C.c_int()
+        self.tab._check(self.kh.lib().kh_shard_finish(self.tab._h, C.byref(bits)))
+        return bits.value
 
     def result(self):
         cp, op = C.c_void_p(), C.c_void_p()
@@ -208,7 +171,7 @@ class Shard:
         return buf, nc, nn
 
     def export(self) -> tuple[bytes, tuple[int, int]]:
-        handles = (C.c_uint8 * (6 * 64))()
+        handles = (C.c_uint8 * (self.kh.lib().kh_shard_export_count() * 64))()
         meta = (C.c_uint64 * 2)()
         self.tab._check(self.kh.lib().kh_shard_export(self.tab._h, handles, meta))
         return bytes(handles), (int(meta[0]), int(meta[1]))
@@ -229,7 +192,7 @@ class Shard:
 
 ERR_BITS = {1: ("KH_ERR_NOT_FOUND", "Error: k-mer not found in Distributed HashMap."), 2: ("KH_ERR_TABLE_FULL", "hash table full"),
             4: ("KH_ERR_CYCLE", "chain never terminates (cycle)"), 8: ("KH_ERR_BAD_INPUT", "malformed input"),
-            16: ("KH_ERR_CONVERGE", "chains are not linear"), 32: ("KH_ERR_CUDA", "internal segment bookkeeping overflow")}
+            16: ("KH_ERR_CONVERGE", "chains are not linear"), 32: ("KH_ERR_CUDA", "internal: a capacity was exceeded or a peer never reached a barrier")}
 
 
 class ShardedError(RuntimeError):
@@ -239,76 +202,65 @@ class ShardedError(RuntimeError):
         self.bits = bits
 
 
-# ---------------------------------------------------------------------------- communicators ----
+# ---------------------------------------------------------------------------- hosting the ranks ----
 class LocalComm:
-    """All ranks in this process; shards[i] is rank i."""
+    """All ranks in this process; shards[i] is rank i.  Calls that contain a barrier are enqueued for every rank
+    before the next one (see the module docstring)."""
 
     def __init__(self, shards: list[Shard]):
         self.shards = shards
-        self._recv = [None] * len(shards)
 
     def connect(self):
         for s in self.shards:
             s.connect_local(self.shards)
 
-    def barrier(self):
+    def sync(self):
         for s in self.shards:
             s.tab.sync()
 
-    def any(self, flags: list[int]) -> bool:
-        return any(flags)
+    def begin(self):
+        for s in self.shards:
+            s.begin()
 
-    def any_after_barrier(self, flags: list[int]) -> bool:
-        self.barrier()
-        return any(flags)
+    def assemble(self):
+        parts = self.shards[0].kh.lib().kh_shard_assemble_parts()
+        for p in range(parts):
+            for s in self.shards:
+                s.assemble_part(p)
 
-    def bits_or(self, bits: list[int]) -> int:
-        out = 0
-        for b in bits:
-            out |= b
-        return out
-
-    def exchange(self, sends: list[tuple[int, list[int]]], elem: int) -> list[tuple[int, int]]:
-        """sends[src] = (device ptr of groups in owner order, counts per dest) -> [(recv ptr, n)] per dest."""
-        L = self.shards[0].kh.lib()
-        world = len(self.shards)
-        out = []
-        for d in range(world):
-            n_recv = sum(sends[s][1][d] for s in range(world))
-            if self._recv[d] is None or self._recv[d][1] < n_recv * elem:
-                if self._recv[d] is not None:
-                    L.kh_device_free(self._recv[d][0])
-                p = C.c_void_p()
-                assert L.kh_device_alloc(C.byref(p), max(n_recv * elem, 256) * 5 // 4) == 0
-                self._recv[d] = (p, max(n_recv * elem, 256) * 5 // 4)
-            base = self._recv[d][0].value
-            off = 0
-            for s in range(world):
-                cnt = sends[s][1][d]
-                src = sends[s][0] + sum(sends[s][1][:d]) * elem
-                self.shards[d].tab._check(L.kh_copy_device(self.shards[d].tab._h, base + off, src, cnt * elem))
-                off += cnt * elem
-            out.append((base, n_recv))
-        self.barrier()
-        return out
+    def finish(self) -> int:
+        bits = 0
+        for s in self.shards:
+            bits |= s.finish()
+        return bits
 
     def close(self):
-        L = self.shards[0].kh.lib()
-        for r in self._recv:
-            if r is not None:
-                L.kh_device_free(r[0])
-        self._recv = []
+        pass
 
 
-class _DevView:
-    """Expose a raw device pointer to torch through __cuda_array_interface__."""
+def gather_peer_handles(handles: bytes, meta: tuple[int, int], dist, world: int):
+    """Every rank's CUDA IPC handle blob and metadata, in rank order (any torch.distributed backend)."""
+    gathered = [None] * world
+    dist.all_gather_object(gathered, (handles, meta))
+    return [g[0] for g in gathered], [tuple(g[1]) for g in gathered]
 
-    def __init__(self, ptr: int, nbytes: int):
-        self.__cuda_array_interface__ = {"shape": (nbytes,), "typestr": "|u1", "data": (ptr, False), "version": 2}
+
+def reduce_error_bits(bits: int, dist, device="cpu") -> int:
+    """OR of the per-rank error bits (kh_shard_finish) over all ranks."""
+    import torch
+
+    t = torch.tensor([bits], dtype=torch.int32, device=device)
+    gathered = [torch.zeros_like(t) for _ in range(dist.get_world_size())]
+    dist.all_gather(gathered, t)
+    out = 0
+    for g in gathered:
+        out |= int(g.item())
+    return out
 
 
 class TorchComm:
-    """One rank per process (torchrun); NCCL on the current CUDA stream."""
+    """One rank per process (torchrun).  torch.distributed carries the CUDA IPC handles at start-up and the error
+    bits at the end of a step; the data path never touches it."""
 
     def __init__(self, shard: Shard):
         import torch
@@ -316,108 +268,50 @@ class TorchComm:
 
         self.torch, self.dist = torch, dist
         self.shards = [shard]
-        self.dev = torch.device("cuda", torch.cuda.current_device())
-        self._keep = None
 
     def connect(self):
         s = self.shards[0]
         h, m = s.export()
-        gathered = [None] * s.world
-        self.dist.all_gather_object(gathered, (h, m))
-        s.connect([g[0] for g in gathered], [g[1] for g in gathered])
-        self.barrier()
+        hs, ms = gather_peer_handles(h, m, self.dist, s.world)
+        s.connect(hs, ms)
+        self.dist.barrier()
 
-    def barrier(self):
-        t = self.torch.zeros(1, device=self.dev)
-        self.dist.all_reduce(t)
-        self.torch.cuda.current_stream().synchronize()
+    def sync(self):
+        self.shards[0].tab.sync()
 
-    def any(self, flags: list[int]) -> bool:
-        t = self.torch.tensor([1.0 if any(flags) else 0.0], device=self.dev)
-        self.dist.all_reduce(t, op=self.dist.ReduceOp.MAX)
-        return bool(t.item() > 0)
+    def begin(self):
+        self.shards[0].begin()
 
-    def any_after_barrier(self, flags: list[int]) -> bool:
-        # the all-reduce is enqueued behind this rank's kernels and completes only when every rank has reached
-        # it in its own stream: it IS the barrier, no second collective needed
-        return self.any(flags)
+    def assemble(self):
+        self.shards[0].assemble()
 
-    def bits_or(self, bits: list[int]) -> int:
-        b = bits[0]
-        t = self.torch.tensor([float((b >> i) & 1) for i in range(8)], device=self.dev)
-        self.dist.all_reduce(t, op=self.dist.ReduceOp.MAX)
-        return sum(1 << i for i, v in enumerate(t.tolist()) if v > 0)
-
-    def exchange(self, sends, elem):
-        ptr, counts = sends[0]
-        n_send = sum(counts)
-        send = self.torch.as_tensor(_DevView(ptr, max(n_send * elem, 1)), device=self.dev) if ptr else \
-            self.torch.empty(0, dtype=self.torch.uint8, device=self.dev)
-        recv, rc = exchange_bytes(send, counts, elem)
-        self._keep = recv                      # alive until the insert kernel has consumed it
-        return [(recv.data_ptr(), sum(rc))]
+    def finish(self) -> int:
+        bits = self.shards[0].finish()
+        dev = self.torch.device("cuda", self.torch.cuda.current_device()) if self.dist.get_backend() == "nccl" else "cpu"
+        return reduce_error_bits(bits, self.dist, dev)
 
     def close(self):
-        self._keep = None
+        pass
 
 
 # ---------------------------------------------------------------------------- the algorithm ----
 def sharded_insert(comm, blocks: list[tuple[int, int]]) -> None:
     """blocks[i] = (device ptr of this rank's kmer_pair records, count) for comm.shards[i].
-
-    initialize_kmers (kmer_hash.cpp:21-33) across ranks: group by owner, ONE all-to-all, insert."""
-    shards = comm.shards
-    elem = slot_bytes(shards[0].k)
-    sends = [s.owner_partition(ptr, n) for s, (ptr, n) in zip(shards, blocks)]
-    recvs = comm.exchange(sends, elem)
-    for s, (ptr, n) in zip(shards, recvs):
-        s.insert_slots(ptr, n)
-    comm.barrier()                                        # hash_map.hpp:79: every insert is visible before any find
+    initialize_kmers (kmer_hash.cpp:21-33) across ranks; only enqueues."""
+    for s, (ptr, n) in zip(comm.shards, blocks):
+        s.insert(ptr, n)
 
 
-def sharded_assemble(comm, max_rounds: int = 40, timings: dict | None = None) -> int:
-    """assemble_contigs (kmer_hash.cpp:38-55) across ranks.  Returns the number of pointer-jumping rounds.
-    Raises ShardedError if any rank flagged an error.  `timings` (optional) receives host wall-clock
-    milliseconds per phase (each phase ends with a barrier that drains the stream)."""
-    import time
-
-    shards = comm.shards
-    t0 = time.perf_counter()
-
-    def lap(name):
-        nonlocal t0
-        if timings is not None:
-            t1 = time.perf_counter()
-            timings[name] = timings.get(name, 0.0) + (t1 - t0) * 1e3
-            t0 = t1
-
-    walked = [s.walk() for s in shards]                   # every GPU walks the k-mers it owns
-    lap("walk")
-    recvs = comm.exchange([(w[0], w[1]) for w in walked], walked[0][2])     # links that leave the GPU: one all-to-all
-    for s, (ptr, n) in zip(shards, recvs):
-        s.resolve(ptr, n)                                 # local lookup + one peer store into the sender's link
-    comm.barrier()
-    lap("links")
-    for _ in range(max_rounds):
-        moved = [s.phase(1) for s in shards]              # a batch of rounds (8, then 4), no barrier needed inside it
-        if not comm.any_after_barrier(moved):
-            break
-    rounds = shards[0].tab.stats()["rank_rounds"]
-    lap("rank_rounds")
-    for ph in (2, 3, 4):                                  # lengths, tail claims, offsets: no barrier needed in between
-        for s in shards:                                  # (lengths accepts tails another rank has already claimed)
-            s.phase(ph)
-    comm.barrier()
-    lap("lengths_claims_offsets")
-    for s in shards:
-        s.phase(5)                                        # emit: every GPU copies its segments into the owner rank's buffer
-    comm.barrier()
-    lap("emit")
-    bits = comm.bits_or([s.phase(6) for s in shards])
-    lap("collect")
+def sharded_assemble(comm, finish: bool = True) -> int:
+    """assemble_contigs (kmer_hash.cpp:38-55) across ranks.  Returns the number of pointer-jumping rounds of rank 0's
+    shard.  Raises ShardedError if any rank flagged an error."""
+    comm.assemble()
+    if not finish:
+        return 0
+    bits = comm.finish()
     if bits:
         raise ShardedError(bits)
-    return rounds
+    return comm.shards[0].tab.stats()["rank_rounds"]
 
 
 # ---------------------------------------------------------------------------- bench (N > 1) ----

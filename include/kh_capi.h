@@ -13,7 +13,7 @@
  *                            of byte 0, tail padded with A (packing.hpp:50-92)
  *   1 byte backward ext, 1 byte forward ext, ASCII in {A,C,G,T,F} (kmer_t.hpp:43-45)
  * i.e. 7 / 10 / 15 bytes for K = 19 / 31 / 51, alignment 1.  The device-side slot
- * format is private.  Supported K: 2..61 (64-bit slots up to K=29, 128-bit above).
+ * format is private.  Supported K: 2..61 (64-bit or 128-bit slots, chosen by the library).
  *
  * There is no CPU fallback: every entry point that computes needs a CUDA device and
  * returns KH_ERR_CUDA without one.
@@ -71,6 +71,9 @@ typedef struct kh_stats {
     float ms_walk, ms_rank, ms_emit;
     float ms_pack;             /* last kh_pack_lines* call                                  */
     float ms_clear;            /* last kh_clear                                             */
+    float ms_build;            /* chunk table: the build + contract kernel of the last seal  */
+    float ms_stage;            /* chunk table: first insert call .. end of the last staging  */
+    uint64_t n_launches;       /* kernels this handle has launched since kh_create          */
 } kh_stats;
 
 int kh_abi_version(void);                 /* bumps when this header changes incompatibly */
@@ -140,39 +143,53 @@ int kh_measure_random_sector_rate(int device, uint64_t footprint_bytes, uint64_t
 
 /* ---------------------------------------------------------------------------------------------
  * Sharded (multi-GPU) path -- replaces the UPC++ side of DistributedHashMap: owner-rank selection
- * (hash_map.hpp:28-30), batched remote inserts (hash_map.hpp:38-46, 64-77) and remote finds
- * (hash_map.hpp:93-100).  One handle per GPU / per rank.  The caller moves the per-owner batches
- * between ranks (NCCL all-to-all through torch.distributed in cs267_hw3_b200/sharded.py) and
- * separates the phases with barriers; lookups during the walk read the owner's table directly
- * over NVLink peer mappings (CUDA IPC between processes, or kh_shard_connect_local in one process).
+ * (hash_map.hpp:28-30), batched remote inserts (hash_map.hpp:38-46, 64-77), remote finds
+ * (hash_map.hpp:93-100) and the barriers (hash_map.hpp:79, kmer_hash.cpp:32, 126, 136).
+ * SPMD like the reference: one handle per rank (GPU), every rank makes the same calls in the same
+ * order -- from one process per GPU (cs267_hw3_b200/sharded.py under torchrun, CUDA IPC peer mappings)
+ * or from one host thread per GPU in one process (include/kh/sharded_host.hpp).  A step is
+ *     kh_shard_begin;  kh_shard_insert (any number of times);  kh_shard_assemble;  kh_shard_finish
+ * and everything before kh_shard_finish only ENQUEUES work on the handle's stream: the records reach their
+ * owner GPU through NVLink peer stores inside the grouping kernel, chain links that leave a GPU and their
+ * answers travel the same way, phases are separated by an in-stream barrier kernel.  Nothing in a step
+ * allocates or synchronises with the host, so kh_shard_init reserves every buffer.
+ * Supported K: 17..54.  Options (kh_set_option / KH_* environment) must be set before kh_shard_init,
+ * and kh_shard_init must precede kh_shard_export / kh_shard_connect*.
  * ------------------------------------------------------------------------------------------- */
-uint64_t kh_slot_bytes(int k);            /* bytes of one exchanged slot value: 8 (K<=29) or 16 */
+uint64_t kh_slot_bytes(int k);            /* bytes of one table slot: 8 or 16 */
 /* Fix all capacities for this rank: at most n_local_max records (n_starts_max of them start nodes) parsed
- * here, n_total records over all ranks. */
+ * here, n_total records over all ranks.  kh_create's n_expected is the number of k-mers THIS shard must be
+ * able to hold (its share of n_total plus slack, see kh_sharded::shard_capacity). */
 int kh_shard_init(kh_table* t, int rank, int world, uint64_t n_local_max, uint64_t n_total, uint64_t n_starts_max);
-/* 6 CUDA IPC handles (64 bytes each) + 2 uint64 of metadata for this rank; gather them from all ranks */
+/* kh_shard_export_count() CUDA IPC handles (64 bytes each) + 2 uint64 of metadata for this rank; gather them
+ * from all ranks (rank order) and hand the lot to kh_shard_connect. */
+int kh_shard_export_count(void);
 int kh_shard_export(kh_table* t, void* handles_out, uint64_t* meta_out);
 int kh_shard_connect(kh_table* t, const void* all_handles, const uint64_t* all_meta);
+/* all ranks in this process: wire them up directly (peer access is enabled between their devices) */
 int kh_shard_connect_local(kh_table* t, kh_table* const* peers, int world);
-/* K7: group this rank's records by owning rank (slot values, owner order) and register its start
- * nodes in input order (kmer_hash.cpp:27-31).  counts_out has 8 entries. */
-int kh_shard_owner_partition(kh_table* t, const void* pairs_dev, uint64_t n, const void** slots_dev_out, uint64_t* counts_out);
-/* K2 on slot values received from the other ranks */
-int kh_insert_slots_device(kh_table* t, const void* slots_dev, uint64_t n);
-/* K8, the walk: every GPU follows successors only through k-mers it owns; where a chain leaves the GPU the
- * segment ends with a pending link.  Returns those links grouped by destination rank (counts_out has 8
- * entries, *link_bytes_out is the size of one link record); the caller moves them with one all-to-all
- * and hands what it received to kh_shard_resolve, which looks the k-mers up locally and patches the
- * senders' links through the peer mapping.  Barrier after each. */
-int kh_shard_walk(kh_table* t, const void** links_dev_out, uint64_t* counts_out, uint64_t* link_bytes_out);
-int kh_shard_resolve(kh_table* t, const void* links_dev, uint64_t n);
-/* remaining phases, each followed by a barrier across ranks: 1 a batch of pointer-jumping rounds
- * (flag_out = "the last one still moved something"; repeat until no rank reports movement),
- * 2 contig lengths, 3 claim tails, 4 offsets (2-4 need no barrier between them, one after 4), 5 emit, barrier,
- * 6 collect (flag_out = device error bits) */
-int kh_shard_phase(kh_table* t, int phase, int* flag_out);
+/* A fresh DistributedHashMap on this rank (kh_clear) + barrier: no rank writes into a peer that has not reset yet. */
+int kh_shard_begin(kh_table* t);
+/* initialize_kmers (kmer_hash.cpp:21-33) for this rank's block of records (device memory, kmer_pair bytes):
+ * stage every record in its owner's memory, register this rank's start nodes in input order. */
+int kh_shard_insert(kh_table* t, const void* pairs_dev, uint64_t n);
+/* assemble_contigs (kmer_hash.cpp:38-55): build the shard, chain the segments across GPUs, rank, emit.
+ * kh_shard_assemble = parts 0 .. kh_shard_assemble_parts()-1 in order; every part ends with the barrier.  A host
+ * that drives several ranks on ONE device must enqueue part p for all of them before part p+1 (their streams
+ * may share a hardware queue, where a waiting barrier would block the peer's work behind it). */
+int kh_shard_assemble(kh_table* t);
+int kh_shard_assemble_parts(void);
+int kh_shard_assemble_part(kh_table* t, int part);
+/* wait for the step; *error_bits_out: 1 k-mer not found, 2 table full, 4 cycle, 8 bad input, 16 converge,
+ * 32 internal (a capacity was exceeded / a peer never reached a barrier).  OR the bits of all ranks. */
+int kh_shard_finish(kh_table* t, int* error_bits_out);
+/* this rank's `<prefix>_<rank>.dat`: the contigs whose start node lies in its block, in input order */
 int kh_shard_result(kh_table* t, const char** contigs_dev, const uint64_t** offsets_dev,
                     uint64_t* n_contigs, uint64_t* contig_bytes, uint64_t* n_nodes);
+
+/* Introspection for tests and debugging: device pointer and capacity of an internal buffer of a chunk table
+ * ("link", "meta", "chunk_base", "seg_base", "chunk_cursor", "counters", ...; "caps" returns HOST numbers). */
+int kh_debug_buffer(kh_table* t, const char* name, void** ptr_out, uint64_t* bytes_out);
 
 /* small device-memory helpers for hosts without their own CUDA binding */
 int kh_device_alloc(void** ptr, uint64_t bytes);                 /* on the current device */

@@ -123,7 +123,8 @@ int main(int argc, char** argv) {
             must(kh_copy_device(cluster.table(r), dev[r], blocks[r].data(), counts[r] * sizeof(kmer_pair)), cluster.table(r), "H2D");
             cdev[r] = dev[r];
         }
-        cluster.insert(cdev, counts);                              // initialize_kmers
+        cluster.begin();
+        cluster.insert(cdev, counts);                              // initialize_kmers (enqueued; the build completes inside assemble)
         const auto insert_time = clock::now();
         std::vector<kh_sharded::RankOutput> outs = cluster.assemble();   // assemble_contigs
         const auto end_time = clock::now();
