@@ -315,17 +315,30 @@ def sharded_assemble(comm, finish: bool = True) -> int:
 
 
 # ---------------------------------------------------------------------------- bench (N > 1) ----
-def bench(args, k, n_total, c_total, longn, workload, rank, world, local_rank):
-    """Strong scaling of the N=1 workload: the same synthetic file, block-partitioned over the ranks
-    (read_kmers.hpp:55-58), table hash-sharded over the GPUs."""
+def shutdown():
+    import torch.distributed as dist
+
+    dist.barrier()
+    dist.destroy_process_group()
+
+
+def bench(args, workload, rank, world, local_rank, steps, warmup):
+    """One workload on `world` GPUs, one process per GPU (torchrun).  Strong scaling: the same synthetic file as at
+    N=1, block-partitioned over the ranks (read_kmers.hpp:55-58), table sharded by chunk range.  A step is enqueued
+    without any host synchronisation; the host waits once per step (kh_shard_finish) to read the error bits."""
     import time
 
     import torch
     import torch.distributed as dist
 
     import cs267_hw3_b200 as kh
+    from bench import METRIC, UNIT, WORKLOADS, ClockSampler, alg_bytes_per_kmer, measured_peak_gbs
     from tools import kmergen
 
+    k, n_total, c_total, longn = WORKLOADS[workload]
+    if args.n:
+        c_total = max(1, int(round(args.n * c_total / n_total)))
+        n_total = args.n
     t_gen = time.time()
     weak = getattr(args, "scaling", "strong") == "weak"
     if weak:
@@ -335,7 +348,6 @@ def bench(args, k, n_total, c_total, longn, workload, rank, world, local_rank):
             raise ValueError("--scaling weak needs K >= 31 (independent per-rank files must not share k-mers)")
         data = kmergen.Dataset(k, n_total, c_total, seed=267 + 1000 * rank, long_nodes=longn)
         n_local, lo = n_total, 0
-        n_per_rank, c_per_rank = n_total, c_total
         n_total, c_total = n_total * world, c_total * world
         exp_buf, exp_nc = data.expected_array(1, 0)
     else:
@@ -359,107 +371,125 @@ def bench(args, k, n_total, c_total, longn, workload, rank, world, local_rank):
     dev.copy_(torch.from_numpy(host.array))
     torch.cuda.synchronize()
 
-    phase_ms: dict = {}
-
     def step():
-        shard.tab.clear()
-        comm.barrier()
+        comm.begin()                                   # fresh table + barrier: the ranks start the step together
         e0, e1, e2 = (torch.cuda.Event(enable_timing=True) for _ in range(3))
         e0.record(stream)
         sharded_insert(comm, [(dev.data_ptr(), n_local)])
         e1.record(stream)
-        rounds = sharded_assemble(comm, timings=phase_ms)
+        comm.assemble()
         e2.record(stream)
-        return e0, e1, e2, rounds
+        bits = shard.finish()                          # the step's only host wait
+        if bits:
+            raise ShardedError(bits)
+        return e0, e1, e2
 
-    from bench import ClockSampler
     sampler = ClockSampler(local_rank)        # warm-up + timed steps
     sampler.start()
-    for _ in range(args.warmup):
+    for _ in range(warmup):
         step()
-    phase_ms.clear()
     dist.barrier()
     torch.cuda.synchronize()
-    evs = []
+    launches0 = shard.tab.stats()["n_launches"]
+    evs, stage = [], {"ms_stage": [], "ms_build": [], "ms_walk": [], "ms_rank": [], "ms_emit": []}
     wall0 = time.perf_counter()
-    for _ in range(args.steps):
+    for _ in range(steps):
         evs.append(step())
+        st = shard.tab.stats()
+        for key in stage:
+            stage[key].append(st[key])
     dist.barrier()
     torch.cuda.synchronize()
     wall = time.perf_counter() - wall0
+    st_last = shard.tab.stats()
+    launches = st_last["n_launches"] - launches0
     clocks = sampler.stop()
-    ms_total = float(np.mean([a.elapsed_time(c) for a, b, c, r in evs]))
-    ms_ins = float(np.mean([a.elapsed_time(b) for a, b, c, r in evs]))
-    t = torch.tensor([ms_total, ms_ins], device="cuda", dtype=torch.float64)
-    dist.all_reduce(t, op=dist.ReduceOp.MAX)                       # slowest rank defines the step
-    ms_total, ms_ins = t.tolist()
+    ms_total = float(np.mean([a.elapsed_time(c) for a, b, c in evs]))
+    ms_ins = float(np.mean([a.elapsed_time(b) for a, b, c in evs]))
+    tm = torch.tensor([ms_total, ms_ins] + [float(np.mean(v)) for v in stage.values()], device="cuda", dtype=torch.float64)
+    dist.all_reduce(tm, op=dist.ReduceOp.MAX)                      # slowest rank defines the step
+    ms_total, ms_ins = tm[:2].tolist()
+    stage_max = dict(zip(stage.keys(), tm[2:].tolist()))
 
     got, nc, nn = shard.result_host()
     ok = bool(nc == exp_nc and got.size == exp_buf.size and np.array_equal(got, exp_buf))
 
     # end to end: this rank's records start in pinned HOST memory, its contigs end in host memory
-    host_t = torch.from_numpy(host.array)
-    e2e_ms = []
-    for i in range(3):
-        shard.tab.clear()
-        comm.barrier()
-        a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-        a.record(stream)
-        dev.copy_(host_t, non_blocking=True)                      # H2D of the step's input
-        sharded_insert(comm, [(dev.data_ptr(), n_local)])
-        sharded_assemble(comm)
-        out_host, _, _ = shard.result_host()                        # D2H of the step's result
-        b.record(stream)
-        torch.cuda.synchronize()
-        if i:
-            e2e_ms.append(a.elapsed_time(b))
-    te = torch.tensor([float(np.mean(e2e_ms))], device="cuda", dtype=torch.float64)
-    dist.all_reduce(te, op=dist.ReduceOp.MAX)
-    e2e_ms_max = float(te.item())
-    ok = ok and bool(np.array_equal(out_host, exp_buf))
-    tot = torch.tensor([float(nn), 1.0 if ok else 0.0, float(got.size)], device="cuda", dtype=torch.float64)
+    e2e_ms_max, out_host = None, got
+    if not args.no_e2e:
+        host_t = torch.from_numpy(host.array)
+        e2e_ms = []
+        for i in range(3):
+            comm.begin()
+            a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            a.record(stream)
+            dev.copy_(host_t, non_blocking=True)                      # H2D of the step's input
+            sharded_insert(comm, [(dev.data_ptr(), n_local)])
+            comm.assemble()
+            if shard.finish():
+                raise ShardedError(1 << 5)
+            out_host, _, _ = shard.result_host()                        # D2H of the step's result
+            b.record(stream)
+            torch.cuda.synchronize()
+            if i:
+                e2e_ms.append(a.elapsed_time(b))
+        te = torch.tensor([float(np.mean(e2e_ms))], device="cuda", dtype=torch.float64)
+        dist.all_reduce(te, op=dist.ReduceOp.MAX)
+        e2e_ms_max = float(te.item())
+        ok = ok and bool(np.array_equal(out_host, exp_buf))
+    tot = torch.tensor([float(nn), 1.0 if ok else 0.0, float(got.size), float(st_last["n_segments"])], device="cuda", dtype=torch.float64)
     dist.all_reduce(tot, op=dist.ReduceOp.SUM)
-    nodes_all, ok_all, bytes_all = tot.tolist()
+    nodes_all, ok_all, bytes_all, segs_all = tot.tolist()
     verified = bool(int(nodes_all) == n_total and int(ok_all) == world)
     line = None
     if rank == 0:
-        from bench import METRIC, UNIT, alg_bytes_per_kmer, measured_peak_gbs
         peak, peak_src = measured_peak_gbs()
         alg = alg_bytes_per_kmer(k)
         path_gbs = n_total * alg["total"] / (ms_total * 1e-3) / 1e9
-        sb = slot_bytes(k)
+        sb = int(st_last["slot_bits"]) // 8
+        build_ms = stage_max["ms_build"]
+        build_bytes = (n_total / world) * (alg["insert"] + alg["lookup"] + alg["output"])
         line = {
             "metric": METRIC, "value": n_total / (ms_total * 1e-3), "unit": UNIT, "n_gpus": world,
-            "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms_total, "higher_is_better": True,
-            "scaling": "weak" if weak else "strong", "vs_baseline": None, "dtype": "u64" if k <= 29 else "u128", "data": "synthetic",
+            "steps": steps, "warmup": warmup, "ms_per_step": ms_total, "higher_is_better": True,
+            "scaling": "weak" if weak else "strong", "vs_baseline": None, "dtype": "u64" if sb == 8 else "u128", "data": "synthetic",
             "config": {"workload": workload, "k": k, "n_kmers": n_total, "n_contigs": c_total, "load_factor": args.load_factor,
-                       "seed": 267, "per_gpu_kmers": n_local,
-                       "sharding": f"table sharded over {world} GPUs by minimizer hash; input lines block-partitioned "
-                       "(read_kmers.hpp:55-58); one NCCL all-to-all of slot values for the inserts; every GPU walks the "
-                       "k-mers it owns, chain hand-overs travel in one all-to-all and are patched in through NVLink peer "
-                       "mappings; pointer jumping and contig text across GPUs over peer mappings",
-                       "timing": "CUDA events on the launching stream per step, max over ranks, mean of steps",
-                       "l2": "per-GPU table and records larger than L2; table re-zeroed between steps (outside the event pair)"},
-            "stages_ms": {"ms_insert_incl_all_to_all": ms_ins, "ms_traverse": ms_total - ms_ins,
-                          "traverse_phases_host_ms_rank0": {k2: v / args.steps for k2, v in phase_ms.items()}},
-            "rank_rounds": evs[-1][3], "assembly_time_s": ms_total * 1e-3, "wall_s_timed_loop": wall, "gen_s": t_gen,
-            "verified": verified,
-            "roofline": {"bound": "hbm", "kernel": "whole path (walk_mig_kernel + build_chunks_kernel dominate on each GPU)",
-                         "achieved": path_gbs, "peak": peak * world, "unit": "GB/s", "frac": path_gbs / (peak * world),
-                         "traffic": None, "peak_source": peak_src + f" x {world} GPUs", "alg_bytes_per_kmer": alg,
-                         "nvlink_bytes_per_step": int(n_total * (world - 1) / world * sb),
-                         "nvlink_note": "(P-1)/P of the slot values cross in the insert all-to-all; lookups never leave "
-                                        "the owner GPU (migrating walk) -- chain hand-overs (one 16/32-byte entry per "
-                                        "supermer boundary), pointer jumping and the contig text cross in addition"},
-            "e2e": {"value": n_total / (e2e_ms_max * 1e-3), "unit": UNIT, "ms_per_step": e2e_ms_max,
-                    "h2d_bytes_per_step": int(n_total * pb), "d2h_bytes_per_step": int(bytes_all),
-                    "note": "each rank copies its block of records from pinned host memory and its contigs back"},
-            "gpu_launches": (23 + evs[-1][3]) * args.steps,      # per rank: 10 insert, 6 walk + links, rounds, 7 finish
+                       "seed": 267, "per_gpu_kmers": n_local, "slot_bytes": sb,
+                       "sharding": f"chunk table sharded over {world} GPUs (a rank owns a contiguous range of chunks; the chunk, and "
+                       "so the owner, follows from the k-mer's minimizer); input lines block-partitioned (read_kmers.hpp:55-58); "
+                       "slot values reach the owner through NVLink peer stores inside the grouping kernel; one lookup per "
+                       "segment chains the segments, requests to other GPUs and their answers are peer stores; pointer "
+                       "jumping and the contig text across GPUs over peer mappings; in-stream flag barriers, one host wait per step",
+                       "timing": "CUDA events on the launching stream per step (after the step's opening barrier .. after its "
+                                 "closing barrier), max over ranks, mean of steps",
+                       "l2": "per-GPU staging buffers and table larger than L2; every step starts from an empty table"},
+            "stages_ms": {"ms_insert_staging_incl_peer_stores": ms_ins, "ms_seal_and_traverse": ms_total - ms_ins,
+                          "max_over_ranks": stage_max},
+            "n_segments": int(segs_all), "rank_rounds": int(st_last["rank_rounds"]), "assembly_time_s": ms_total * 1e-3,
+            "wall_s_timed_loop": wall, "gen_s": t_gen, "verified": verified,
+            "roofline": {"bound": "hbm", "kernel": "ct_build_kernel (per GPU, slowest rank)", "achieved": build_bytes / (build_ms * 1e-3) / 1e9 if build_ms else None,
+                         "peak": peak, "unit": "GB/s", "frac": build_bytes / (build_ms * 1e-3) / 1e9 / peak if build_ms else None,
+                         "traffic": None, "peak_source": peak_src, "kernel_ms": build_ms,
+                         "units_per_launch": n_total // world, "alg_bytes_per_unit": alg["insert"] + alg["lookup"] + alg["output"],
+                         "alg_bytes_per_kmer": alg,
+                         "path": {"achieved": path_gbs, "peak": peak * world, "frac": path_gbs / (peak * world),
+                                  "note": "N x B_alg / t(insert+traverse) against the measured HBM peak x GPUs"},
+                         "nvlink_bytes_per_step": int(n_total * (world - 1) / world * (sb + 2)),
+                         "nvlink_note": "(P-1)/P of the slot values (+ 2-byte chunk tags) cross in the staging pass; per segment "
+                                        "that continues on another GPU one 16/32-byte request and a 4-byte answer; per round one "
+                                        "8-byte read per open link; the contig characters of segments whose contig lives elsewhere"},
+            "e2e": ({"value": n_total / (e2e_ms_max * 1e-3), "unit": UNIT, "ms_per_step": e2e_ms_max,
+                     "h2d_bytes_per_step": int(n_total * pb), "d2h_bytes_per_step": int(bytes_all),
+                     "note": "each rank copies its block of records from pinned host memory and its contigs back"}
+                    if e2e_ms_max else None),
+            "gpu_launches": int(launches),
+            "gpu_launches_note": "kernels launched by rank 0 in the timed steps (counted by the library)",
             "clocks": clocks,
         }
     comm.close()
     shard.close()
     host.free()
+    del dev
+    torch.cuda.empty_cache()
     dist.barrier()
-    dist.destroy_process_group()
     return line

@@ -28,7 +28,11 @@ static void run(int k, int world) {
         S::to_record(v, k, pl, back);
         const bool rt = memcmp(rec, back, pb) == 0;
         print128(v);
-        printf(" %u ", ok ? owner_of<W>(v, world, k, owner_minimizer_len(k)) : 99u);
+        CtGeom g = {};
+        g.k = k; g.m = ct_minimizer_len(k); g.win = ct_window(k); g.world = world; g.chunks_per_rank = 1;
+        u32 owner = 99u, chunk = 0;
+        if (ok) ct_place(ct_min_hash<W>(S::key_only(v), g.m, g.win), g, owner, chunk);      // the rank that stores the k-mer (hash_map.hpp:28-30)
+        printf(" %u ", owner);
         print128(S::next_key(v, k));
         printf(" ");
         print128(S::back(v) < 4 ? S::prev_key(v, k) : S::zero());

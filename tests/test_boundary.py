@@ -46,7 +46,7 @@ def test_library_is_sm100a_and_uses_wide_sector_ops():
 def test_pure_helpers_need_no_gpu():
     import cs267_hw3_b200 as kh
     L = kh.lib()
-    assert L.kh_abi_version() == 1
+    assert L.kh_abi_version() == 2
     assert [L.kh_pair_bytes(k) for k in (19, 31, 51)] == [7, 10, 15]
     assert [L.kh_packed_bytes(k) for k in (19, 31, 51)] == [5, 8, 13]
     assert b"k-mer not found in Distributed HashMap" in L.kh_status_string(kh.KH_ERR_NOT_FOUND)

@@ -96,3 +96,36 @@ def test_cli_streamed_ingest_writes_the_same_bytes(bins, tmp_path, chunk_lines):
     env = dict(os.environ, KH_STREAM="1", KH_STREAM_CHUNK_LINES=chunk_lines)
     subprocess.run([bins[k], str(inp), "test", "st"], cwd=tmp_path, check=True, capture_output=True, env=env)
     assert (tmp_path / "st_0.dat").read_bytes() == d.expected()[0]
+
+
+@pytest.mark.parametrize("case,k", [("k19_a", 19), ("k51_a", 51)])
+def test_unmodified_reference_main_over_the_drop_in_headers(tmp_path, case, k):
+    """the reference's kmer_hash.cpp, compiled UNMODIFIED against include/ (hash_map.hpp,
+    kmer_t.hpp, read_kmers.hpp, butil.hpp and the one-process upcxx/upcxx.hpp) and libkh_b200.so -- built where the
+    reference tree exists (oracle/Makefile `dropin`), shipped as oracle/_ref/kmer_hash_dropin_<K>.  Its own
+    assemble_contigs loop (one DistributedHashMap::find per step, kmer_hash.cpp:38-55) over the GPU table must write the
+    bytes the reference wrote with its own hash map (tests/golden/<case>.dat)."""
+    exe = os.path.join(ROOT, "oracle", "_ref", f"kmer_hash_dropin_{k}")
+    if not os.path.exists(exe):
+        pytest.skip("oracle/_ref/kmer_hash_dropin_* is built only where /root/reference exists (make -C oracle dropin)")
+    inp = os.path.join(ROOT, "tests", "golden", case + ".txt")
+    r = subprocess.run([exe, inp, "test", "dd"], cwd=tmp_path, capture_output=True, text=True, timeout=600)
+    assert r.returncode == 0, r.stdout + r.stderr
+    with open(os.path.join(ROOT, "tests", "golden", case + ".dat"), "rb") as f:
+        assert (tmp_path / "dd_0.dat").read_bytes() == f.read()
+    assert re.search(r"Rank 0 reconstructed \d+ contigs with \d+ nodes from 0 start nodes\.", r.stdout)
+    r = subprocess.run([exe, inp], cwd=tmp_path, capture_output=True, text=True, timeout=600)
+    assert r.returncode == 0 and "Finished inserting in" in r.stdout and "Assembled in" in r.stdout
+
+
+@pytest.mark.parametrize("k,case", [(19, "k19_a"), (31, "k31_a"), (51, "k51_a")])
+def test_header_api_find_and_hashmap(tmp_path, k, case):
+    """hash_map.hpp:50-55, 83 and README.md:95-99 through the drop-in headers: insert_all(vector), find(std::string),
+    the reference's own one-find-per-step walk, HashMap::insert / find(pkmer_t) -- tests/native/hash_map_check.cpp."""
+    exe = tmp_path / "hm_check"
+    pkg = os.path.join(ROOT, "cs267_hw3_b200")
+    subprocess.run(["g++", "-O2", "-std=c++17", "-pthread", f"-DKMER_LEN={k}", "-I" + os.path.join(ROOT, "include"),
+                    os.path.join(ROOT, "tests", "native", "hash_map_check.cpp"), "-L" + pkg, "-lkh_b200", "-Wl,-rpath," + pkg,
+                    "-o", str(exe)], check=True, capture_output=True)
+    r = subprocess.run([str(exe), os.path.join(ROOT, "tests", "golden", case + ".txt")], capture_output=True, text=True, timeout=600)
+    assert r.returncode == 0 and r.stdout.startswith("OK"), r.stdout + r.stderr

@@ -1,0 +1,49 @@
+"""GPU, more than one device: the sharded path with one PROCESS per GPU (torchrun, CUDA IPC peer mappings, NVLink
+peer stores, in-stream barriers) -- the transport bench.py --gpus N measures -- and with one THREAD per GPU in one
+process (the C++ cluster behind `KH_RANKS=N ./kmer_hash_<K>`).  Skipped on boxes with a single GPU, where
+tests/test_gpu_sharded.py runs the same kernels and entry points with all ranks on one device."""
+import os
+import subprocess
+import sys
+
+import pytest
+
+from tools import kmergen
+
+pytestmark = pytest.mark.gpu
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+def _ngpu():
+    try:
+        import torch
+        return torch.cuda.device_count()
+    except Exception:
+        return 0
+
+
+@pytest.mark.parametrize("world", [2, 4, 8])
+def test_one_process_per_gpu_matches_the_reference_per_rank_files(world):
+    if _ngpu() < world:
+        pytest.skip(f"needs {world} GPUs")
+    r = subprocess.run([sys.executable, "-m", "torch.distributed.run", "--nnodes=1", f"--nproc-per-node={world}",
+                        "--master-addr", "127.0.0.1", "--master-port", str(29611 + world),
+                        os.path.join(ROOT, "tests", "multi_gpu_worker.py")], capture_output=True, text=True, timeout=900)
+    assert r.returncode == 0, r.stdout[-4000:] + r.stderr[-4000:]
+    assert r.stdout.count("OK") == 3 * world and "MISMATCH" not in r.stdout
+
+
+@pytest.mark.parametrize("world,k", [(2, 51), (2, 19), (4, 31), (8, 51)])
+def test_one_thread_per_gpu_cli(tmp_path, world, k):
+    if _ngpu() < world:
+        pytest.skip(f"needs {world} GPUs")
+    from cs267_hw3_b200 import build as b
+    exe = dict(zip((19, 31, 51), b.build_cli()))[k]
+    d = kmergen.Dataset(k, 500_000, 4_000, seed=70 + world)
+    inp = tmp_path / "in.txt"
+    d.text().tofile(inp)
+    env = dict(os.environ, KH_RANKS=str(world))
+    r = subprocess.run([exe, str(inp), "test", "mg"], cwd=tmp_path, capture_output=True, text=True, env=env, timeout=600)
+    assert r.returncode == 0, r.stdout + r.stderr
+    for rank in range(world):
+        assert (tmp_path / f"mg_{rank}.dat").read_bytes() == d.expected(world, rank)[0]
