@@ -540,7 +540,9 @@ int ct_setup(kh_table* t, int rank, int world, u64 n_local_max, u64 n_total, u64
     if (seg_cap >= (u64)kLocalMask - 16 && sharded) return fail(t, KH_ERR_ARG, "too many segments per GPU for 28-bit local ids");
     c.caps.seg_cap = (u32)std::min<u64>(seg_cap, 0xFFFFFF00ull);
     c.caps.pool_cap = n_exp + 16 * C + 64;
-    c.caps.inbox_cap = world > 1 ? (u32)std::min<u64>(0x7FFFFFF0ull, ((n_exp / 2 + hcap) / world) * 5 / 4 + 4096) : 1;
+    // every rank must arrive at the SAME capacities for the buffers its peers index (staging, extras, inbox): they
+    // may depend on n_total, n_local_max, the load factor and K only -- never on this rank's own start-node count
+    c.caps.inbox_cap = world > 1 ? (u32)std::min<u64>(0x7FFFFFF0ull, ((n_exp + n_local_max) / world) * 9 / 8 + 4096) : 1;
     c.out_cap = n_total + std::max<u64>(n_starts_max, 1) * (u64)(t->k + 1) + 64;
     c.bprs = (u32)((cap_rs + kSubTile - 1) / kSubTile);
     const u64 nreg_local = R * (u64)world;
@@ -810,7 +812,16 @@ int ct_finish(kh_table* t, u32* bits_out) {
     u32 e = h.errors;
     if (e == 0 && h.contig_bytes > c.out_cap) e = kErrConverge;
     if (bits_out) *bits_out = e;
-    if (h.errors) clear_error_bits(t);
+    if (e & kErrInternal) {             // say which capacity or wait it was (rare path: a message on stderr is worth more than silence)
+        char msg[512];
+        snprintf(msg, sizeof msg, "rank %d/%d internal error, site bits 0x%x (1 barrier wait, 2 start list, 4 segment ids, 8 link inbox, "
+                 "16 unresolved head stub, 32 output buffer): starts %llu/%u, segments %u/%u, contig bytes %llu/%llu, epoch %u",
+                 c.pe.rank, c.pe.world, h.err_where, (unsigned long long)h.n_starts_dev, c.caps.hcap, h.next_seg, c.caps.seg_cap,
+                 (unsigned long long)h.contig_bytes, (unsigned long long)c.out_cap, c.epoch);
+        t->err = msg;
+        fprintf(stderr, "libkh_b200: %s\n", msg);
+    }
+    if (h.errors) { clear_error_bits(t); KH_CUDA(t, cudaMemsetAsync(&t->d_ctr->err_where, 0, sizeof(u32), t->stream)); }
     return KH_OK;
 }
 
@@ -1304,6 +1315,14 @@ static int shard_require(kh_table* t) {
 
 int kh_shard_export_count(void) { return CTX_NBUF; }
 
+// everything two ranks must agree on to index each other's buffers
+static uint64_t ct_geometry_signature(kh_table* t) {
+    const auto& c = t->ct;
+    u64 h = fmix64((u64)c.g.chunks_per_rank + 0x9E3779B97F4A7C15ull * (u64)c.g.cpr_shift);
+    h = fmix64(h ^ c.caps.cap_rs); h = fmix64(h ^ c.caps.extra_cap); h = fmix64(h ^ c.caps.inbox_cap);
+    return fmix64(h ^ (u64)c.pe.world);
+}
+
 static void ct_export_list(kh_table* t, void* (&bufs)[CTX_NBUF]) {
     auto& c = t->ct;
     bufs[CTX_STAGE_VALS] = c.stage_vals.p; bufs[CTX_STAGE_TAGS] = c.stage_tags.p; bufs[CTX_STAGE_CNT] = c.stage_cnt.p;
@@ -1332,7 +1351,7 @@ int kh_shard_export(kh_table* t, void* handles_out, uint64_t* meta_out) {
     ct_export_list(t, bufs);
     cudaIpcMemHandle_t* h = static_cast<cudaIpcMemHandle_t*>(handles_out);
     for (int i = 0; i < CTX_NBUF; ++i) KH_CUDA(t, cudaIpcGetMemHandle(&h[i], bufs[i]));
-    meta_out[0] = t->ct.g.chunks_per_rank;
+    meta_out[0] = ct_geometry_signature(t);
     meta_out[1] = t->ct.out_cap;
     return KH_OK;
 }
@@ -1345,7 +1364,7 @@ int kh_shard_connect(kh_table* t, const void* all_handles, const uint64_t* all_m
     const cudaIpcMemHandle_t* h = static_cast<const cudaIpcMemHandle_t*>(all_handles);
     for (int r = 0; r < c.pe.world; ++r) {
         if (r == c.pe.rank) continue;
-        if (all_meta[2 * r] != c.g.chunks_per_rank) return fail(t, KH_ERR_ARG, "ranks disagree on the table geometry (same n_total, load factor and K everywhere)");
+        if (all_meta[2 * r] != ct_geometry_signature(t)) return fail(t, KH_ERR_ARG, "ranks disagree on the table geometry (same n_total, n_local_max, load factor and K everywhere)");
         void* p[CTX_NBUF];
         for (int i = 0; i < CTX_NBUF; ++i) {
             KH_CUDA(t, cudaIpcOpenMemHandle(&p[i], h[r * CTX_NBUF + i], cudaIpcMemLazyEnablePeerAccess));
@@ -1365,7 +1384,7 @@ int kh_shard_connect_local(kh_table* t, kh_table* const* peers, int world) {
     if (world != c.pe.world) return fail(t, KH_ERR_ARG, "world does not match kh_shard_init");
     for (int r = 0; r < world; ++r) {
         kh_table* q = peers[r];
-        if (!q || !q->ct.on || !q->ct.sharded || q->k != t->k || q->ct.pe.rank != r || q->ct.g.chunks_per_rank != c.g.chunks_per_rank)
+        if (!q || !q->ct.on || !q->ct.sharded || q->k != t->k || q->ct.pe.rank != r || ct_geometry_signature(q) != ct_geometry_signature(t))
             return fail(t, KH_ERR_ARG, "peer handle is not shard r of the same table (same K, n_total, load factor)");
         if (q == t) continue;
         if (q->device != t->device) {

@@ -80,6 +80,11 @@ struct CtCaps {
     u64 nbuckets_alloc, pool_cap;
 };
 
+__device__ __forceinline__ void ct_internal(Counters* ctr, u32 site) {
+    atomicOr(&ctr->errors, kErrInternal);
+    atomicOr(&ctr->err_where, site);
+}
+
 // ---- in-stream barrier across the GPUs of one step -------------------------------------------------------
 // One warp; lane r signals rank r (a store into ITS flag array) and waits for rank r's signal in ours.  Everything
 // the previous kernels of this stream wrote -- including stores into peer memory -- is complete when this kernel
@@ -105,7 +110,7 @@ __global__ void ct_barrier_kernel(const CtPeers pe, u32 epoch, Counters* ctr, in
             asm volatile("ld.acquire.sys.global.u32 %0, [%1];" : "=r"(seen) : "l"(src) : "memory");
             if ((int)((seen >> 1) - epoch) >= 0) { peer_bit = ((seen >> 1) == epoch) ? (seen & 1u) : 1u; break; }
             asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t1));
-            if (t1 - t0 > 4000000000ull) { atomicOr(&ctr->errors, kErrInternal); peer_bit = 1; break; }
+            if (t1 - t0 > 4000000000ull) { ct_internal(ctr, kSiteBarrier); peer_bit = 1; break; }
             __nanosleep(200);
         }
         __threadfence_system();
@@ -247,7 +252,7 @@ ct_publish_stage_kernel(const CtGeom g, const CtPeers pe, const CtCaps caps, con
 // start nodes seen so far live on the device (no host round trip per insert call in the sharded path)
 __global__ void ct_bump_starts_kernel(Counters* ctr, u32 hcap) {
     const u64 total = ctr->n_starts_dev + ctr->scan_total;
-    if (total > hcap) { atomicOr(&ctr->errors, kErrInternal); ctr->n_starts_dev = hcap; }
+    if (total > hcap) { ct_internal(ctr, kSiteStarts); ctr->n_starts_dev = hcap; }
     else ctr->n_starts_dev = total;
 }
 
@@ -518,7 +523,7 @@ ct_build_kernel(const typename Slot<W>::value_t* __restrict__ fine, const u32* _
     const u32 nheads = s_nheads;
     if (threadIdx.x == 0) {
         u32 seg0 = nheads ? atomicAdd(&ctr->next_seg, nheads) : 0u;
-        if (seg0 + nheads > caps.seg_cap) { atomicOr(&s_err, kErrInternal); seg0 = caps.seg_cap; }
+        if (seg0 + nheads > caps.seg_cap) { ct_internal(ctr, kSiteSegCap); seg0 = caps.seg_cap; }
         s_seg0 = seg0;
         seg_base[c] = seg0;
     }
@@ -703,7 +708,7 @@ ct_resolve_kernel(const typename Slot<W>::value_t* __restrict__ table, const u32
             if (dest[r] == 0xFFFFFFFFu) continue;
             const u32 at = s_base[dest[r]] + rk[r];
             if (at < caps.inbox_cap) static_cast<CtReq<W>*>(pe.inbox[dest[r]])[(u64)g.rank * caps.inbox_cap + at] = e[r];
-            else atomicOr(&ctr->errors, kErrInternal);
+            else ct_internal(ctr, kSiteInbox);
         }
         __syncthreads();
     }
@@ -776,7 +781,7 @@ ct_lengths_kernel(const CtPeers pe, const u64* __restrict__ link, const CtCaps c
         u32 e = 0, tail_hi = 0, chars = 0, pre = 0;
         if (pc == kLinkMissing) e = kErrNotFound;
         else if (pc == kLinkConverge) e = kErrConverge;
-        else if (pc >= kLinkCtFirstMarker) e = kErrInternal;                     // a stub is never a tail, and nobody may leave it pending
+        else if (pc >= kLinkCtFirstMarker) { e = kErrInternal; atomicOr(&ctr->err_where, kSiteStubOpen); }                     // a stub is never a tail, and nobody may leave it pending
         else if (!((u32)lc & kLinkFinalBit)) e = kErrCycle;                      // still moving after the last round: kmer_hash.cpp:44 never exits
         else {
             tail_hi = (u32)(__ldcg(ct_peer_link(pe, pc)) >> 32);
@@ -844,7 +849,7 @@ ct_emit_kernel(const CtPeers pe, const u64* __restrict__ link, const u64* __rest
                 if (ok) {
                     const u64 off = pe.contig_off[r][c] + (u64)k + (is_tail ? pre : pre - dist);
                     len = (u32)(mt & 0xFFFFFFu);
-                    if (off + len > pe.out_cap[r]) { atomicOr(&ctr->errors, kErrInternal); len = 0; }
+                    if (off + len > pe.out_cap[r]) { ct_internal(ctr, kSiteOutCap); len = 0; }
                     dst = pe.out[r] + off;
                     src = pool + (mt >> 24);
                 }

@@ -516,6 +516,9 @@ constexpr u32 kLinkClaimed = 0xFFFFFFFDu;   // tail claimed by a contig; low wor
 constexpr u32 kLinkPending = 0xFFFFFFFCu;   // sharded walk: successor lives on another GPU, link not resolved yet
 constexpr u32 kLinkFirstMarker = kLinkPending;
 
+// where a kErrInternal came from (Counters::err_where)
+enum : u32 { kSiteBarrier = 1u, kSiteStarts = 2u, kSiteSegCap = 4u, kSiteInbox = 8u, kSiteStubOpen = 16u, kSiteOutCap = 32u };
+
 struct Counters {
     u32 next_walker;
     u32 next_seg;
@@ -530,7 +533,7 @@ struct Counters {
     u32 n_outbox;         // sharded: pending links produced by the local walk
     u32 flags[40];
     u32 rank_done;        // ctable: no rank moved a link in the last pointer-jumping round (agreed on by all ranks)
-    u32 pad0;
+    u32 err_where;        // ctable: which capacity / wait raised kErrInternal (CtSite bits), for the error message
     u64 n_starts_dev;     // ctable: start nodes registered so far (kept on the device: no host round trip per insert)
 };
 
