@@ -79,8 +79,7 @@ struct kh_table {
         u32 epoch = 0;                    // barriers passed (all ranks call them in lockstep)
         u64 n_local_max = 0, n_total = 0, n_starts_max = 0, out_cap = 0;
         u64 n_starts_host = 0;            // non-sharded handles learn it at every insert (they sync anyway)
-        u32 bprs = 1;                     // scatter blocks per (region, source) buffer
-        DevBuf stage_vals, stage_tags, stage_cnt, reg_cursor, extra_vals, extra_chunk, extra_cnt, fine, chunk_cursor,
+        DevBuf xin_vals, xin_chunk, xin_cnt, xin_done, xout_cursor, extra_vals, extra_chunk, extra_cnt, fine, chunk_cursor,
                chunk_base, pool_off, seg_base, ext_key, meta, pool, inbox, inbox_cnt, out_cursor, flags;
         void* ipc_opened[kMaxRanks][16] = {};
     } ct;
@@ -473,20 +472,19 @@ int set_option(kh_table* t, const std::string& name, int64_t value) {
 // same code with itself as its only peer.
 namespace {
 
-enum { CTX_STAGE_VALS, CTX_STAGE_TAGS, CTX_STAGE_CNT, CTX_EXTRA_VALS, CTX_EXTRA_CHUNK, CTX_EXTRA_CNT, CTX_LINK, CTX_META,
+enum { CTX_XIN_VALS, CTX_XIN_CHUNK, CTX_XIN_CNT, CTX_EXTRA_VALS, CTX_EXTRA_CHUNK, CTX_EXTRA_CNT, CTX_LINK, CTX_META,
        CTX_INBOX, CTX_INBOX_CNT, CTX_PRE, CTX_OFF, CTX_OUT, CTX_FLAGS, CTX_NBUF };
 
-size_t ct_stage_smem(int W, u32 nreg, int pb) {
-    const size_t un = std::max<size_t>((size_t)kPartTile * (W == 1 ? 8 : 16), (size_t)kPartTile * pb) + kStageSlack;
-    return ((12 * (size_t)nreg + 4 * kPartTile + 15) & ~(size_t)15) + un;
+size_t ct_stage_smem(int W, int world) {       // multi-GPU: the remote values of a tile sorted by owner + their chunk ids
+    return world > 1 ? (size_t)kStgTile * ((W == 1 ? 8 : 16) + 4) : 0;
 }
 
 void ct_set_self(kh_table* t) {
     auto& c = t->ct;
     CtPeers& pe = c.pe;
     const int r = pe.rank;
-    pe.stage_vals[r] = c.stage_vals.p; pe.stage_tags[r] = static_cast<unsigned short*>(c.stage_tags.p);
-    pe.stage_cnt[r] = static_cast<u32*>(c.stage_cnt.p);
+    pe.xin_vals[r] = c.xin_vals.p; pe.xin_chunk[r] = static_cast<u32*>(c.xin_chunk.p);
+    pe.xin_cnt[r] = static_cast<u32*>(c.xin_cnt.p);
     pe.extra_vals[r] = c.extra_vals.p; pe.extra_chunk[r] = static_cast<u32*>(c.extra_chunk.p);
     pe.extra_cnt[r] = static_cast<u32*>(c.extra_cnt.p);
     pe.link[r] = static_cast<u64*>(t->link.p); pe.meta[r] = static_cast<u64*>(c.meta.p);
@@ -494,6 +492,17 @@ void ct_set_self(kh_table* t) {
     pe.contig_pre[r] = static_cast<u32*>(t->contig_pre.p); pe.contig_off[r] = static_cast<u64*>(t->contig_off.p);
     pe.out[r] = static_cast<char*>(t->out.p); pe.out_cap[r] = c.out_cap;
     pe.flags[r] = static_cast<u32*>(c.flags.p);
+}
+
+// empty staging: cursors of the chunk buffers, of the send side and of the receive side
+int ct_reset_staging(kh_table* t) {
+    auto& c = t->ct;
+    KH_CUDA(t, cudaMemsetAsync(c.chunk_cursor.p, 0, ((u64)c.g.chunks_per_rank + 1) * sizeof(u32), t->stream));
+    KH_CUDA(t, cudaMemsetAsync(c.xout_cursor.p, 0, kMaxRanks * sizeof(u32), t->stream));
+    KH_CUDA(t, cudaMemsetAsync(c.xin_cnt.p, 0, kMaxRanks * sizeof(u32), t->stream));
+    KH_CUDA(t, cudaMemsetAsync(c.xin_done.p, 0, (kMaxRanks + 1) * sizeof(u32), t->stream));
+    KH_CUDA(t, cudaMemsetAsync(c.extra_cnt.p, 0, 16, t->stream));
+    return KH_OK;
 }
 
 // Fix the geometry and (re)allocate everything whose size is known up front.  Sharded handles allocate ALL their
@@ -507,16 +516,13 @@ int ct_setup(kh_table* t, int rank, int world, u64 n_local_max, u64 n_total, u64
     const u32 slots_max = CtBuild<W>::kMaxSlots, per_bucket = (u32)Slot<W>::kPerBucket;
     const double mu = std::min(t->lf / 1.35, 0.55) * slots_max;                   // mean k-mers per chunk (see chunk_placement_sim.cpp)
     const u64 C64 = std::max<u64>(1, (u64)std::ceil((double)n_exp / mu));
-    u32 shift = 6;
-    while ((u64)world * ((C64 + (1ull << shift) - 1) >> shift) > kCtMaxRegions) ++shift;
-    if (shift > 10) return fail(t, KH_ERR_ARG, "table too large for one GPU's chunk table (more than 2^20 chunks)");
+    if (C64 * (u64)world > (1ull << 24)) return fail(t, KH_ERR_ARG, "table too large for the chunk table (more than 2^24 chunks)");
     c.g.k = t->k; c.g.m = ct_minimizer_len(t->k); c.g.win = ct_window(t->k);
     c.g.world = world; c.g.rank = rank;
-    c.g.chunks_per_rank = (u32)C64; c.g.cpr_shift = shift;
-    c.g.regions_per_rank = (u32)((C64 + (1ull << shift) - 1) >> shift);
+    c.g.chunks_per_rank = (u32)C64;
     c.g.max_buckets = CtBuild<W>::kMaxBuckets;
     c.g.lf_inv_q16 = (u32)std::min(65536.0 * 64.0, 65536.0 / t->lf + 0.5);
-    const u64 C = C64, R = c.g.regions_per_rank;
+    const u64 C = C64;
     c.n_local_max = n_local_max; c.n_total = n_total; c.n_starts_max = n_starts_max; c.sharded = sharded;
     // table: every chunk gets ceil(load / lf) slots rounded up to whole buckets
     const u64 nb_alloc = (u64)((long double)n_exp / (long double)t->lf / per_bucket) + C + 64;
@@ -527,12 +533,12 @@ int ct_setup(kh_table* t, int rank, int world, u64 n_local_max, u64 n_total, u64
     }
     t->nbuckets = nb_alloc;
     c.caps.nbuckets_alloc = nb_alloc;
-    // staging: one buffer per (local region, source rank)
-    const double share = (double)std::max<u64>(n_local_max, 1) * (double)(1u << shift) / ((double)world * (double)C);
-    u64 cap_rs = (u64)((share * 1.10 + 24.0 * std::sqrt(share + 1.0) + 64.0) * t->debug_cap_pct / 100.0);
-    cap_rs = std::max<u64>(8, (cap_rs + 7) & ~7ull);
-    if (cap_rs >= 0xFFFFFFF0ull) return fail(t, KH_ERR_ARG, "staging buffer too large");
-    c.caps.cap_rs = (u32)cap_rs;
+    // receive buffer for the records other GPUs parse for this one: one part per source rank
+    const double share = (double)std::max<u64>(n_local_max, 1) / (double)world;
+    u64 xin_cap = world > 1 ? (u64)((share * 1.05 + 64.0 * std::sqrt(share + 1.0) + 4096.0) * t->debug_cap_pct / 100.0) : 8;
+    xin_cap = std::max<u64>(8, (xin_cap + 7) & ~7ull);
+    if (xin_cap >= 0xFFFFFFF0ull) return fail(t, KH_ERR_ARG, "receive buffer too large");
+    c.caps.xin_cap = (u32)xin_cap;
     c.caps.extra_cap = (u32)std::min<u64>(0x7FFFFFF0ull, t->debug_cap_pct < 100 ? n_local_max * (u64)world + 65536 : n_exp / 16 + 65536);
     const u64 hcap = sharded ? std::min<u64>(std::max<u64>(n_starts_max, 1), n_local_max + 1) : 0;     // plain handles size it at seal
     c.caps.hcap = (u32)hcap;
@@ -544,12 +550,11 @@ int ct_setup(kh_table* t, int rank, int world, u64 n_local_max, u64 n_total, u64
     // may depend on n_total, n_local_max, the load factor and K only -- never on this rank's own start-node count
     c.caps.inbox_cap = world > 1 ? (u32)std::min<u64>(0x7FFFFFF0ull, ((n_exp + n_local_max) / world) * 9 / 8 + 4096) : 1;
     c.out_cap = n_total + std::max<u64>(n_starts_max, 1) * (u64)(t->k + 1) + 64;
-    c.bprs = (u32)((cap_rs + kSubTile - 1) / kSubTile);
-    const u64 nreg_local = R * (u64)world;
-    KH_TRY(ensure(t, c.stage_vals, nreg_local * cap_rs * sizeof(V)));
-    KH_TRY(ensure(t, c.stage_tags, nreg_local * cap_rs * sizeof(unsigned short)));
-    KH_TRY(ensure(t, c.stage_cnt, nreg_local * sizeof(u32)));
-    KH_TRY(ensure(t, c.reg_cursor, kCtMaxRegions * sizeof(u32)));
+    KH_TRY(ensure(t, c.xin_vals, (u64)world * xin_cap * sizeof(V)));
+    KH_TRY(ensure(t, c.xin_chunk, (u64)world * xin_cap * sizeof(u32)));
+    KH_TRY(ensure(t, c.xin_cnt, kMaxRanks * sizeof(u32)));
+    KH_TRY(ensure(t, c.xin_done, (kMaxRanks + 1) * sizeof(u32)));          // [kMaxRanks] = extras already filed
+    KH_TRY(ensure(t, c.xout_cursor, kMaxRanks * sizeof(u32)));
     KH_TRY(ensure(t, c.extra_vals, (u64)c.caps.extra_cap * sizeof(V)));
     KH_TRY(ensure(t, c.extra_chunk, (u64)c.caps.extra_cap * sizeof(u32)));
     KH_TRY(ensure(t, c.extra_cnt, 16));
@@ -578,15 +583,13 @@ int ct_setup(kh_table* t, int rank, int world, u64 n_local_max, u64 n_total, u64
         KH_TRY(ensure(t, t->tile_offs, (ntiles + 1) * sizeof(u64)));
         KH_TRY(ensure(t, t->scan_blocks, ((std::max(ntiles, hcap + 2) + kScanTile - 1) / kScanTile + 2) * sizeof(u64)));
     }
-    KH_CUDA(t, cudaMemsetAsync(c.reg_cursor.p, 0, kCtMaxRegions * sizeof(u32), t->stream));
-    KH_CUDA(t, cudaMemsetAsync(c.extra_cnt.p, 0, 16, t->stream));
-    KH_CUDA(t, cudaMemsetAsync(c.stage_cnt.p, 0, nreg_local * sizeof(u32), t->stream));
+    KH_TRY(ct_reset_staging(t));
     KH_CUDA(t, cudaMemsetAsync(c.inbox_cnt.p, 0, kMaxRanks * sizeof(u32), t->stream));
     KH_CUDA(t, cudaMemsetAsync(c.flags.p, 0, 2 * kMaxRanks * sizeof(u32), t->stream));
     KH_CUDA(t, cudaStreamSynchronize(t->stream));
     if (!c.attr_set) {
         KH_CUDA(t, cudaFuncSetAttribute(ct_build_kernel<W>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)CtBuild<W>::kSmem));
-        KH_CUDA(t, cudaFuncSetAttribute(ct_stage_kernel<W>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)ct_stage_smem(W, kCtMaxRegions, 18)));
+        KH_CUDA(t, cudaFuncSetAttribute(ct_stage_kernel<W>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)ct_stage_smem(W, 8)));
         c.attr_set = true;
     }
     memset(&c.pe, 0, sizeof(c.pe));
@@ -626,10 +629,9 @@ int ct_stage(kh_table* t, const unsigned char* recs, u64 n) {
     } else if (n > c.n_local_max) {
         return fail(t, KH_ERR_ARG, "more records than kh_shard_init reserved (n_local_max)");
     }
-    const u32 nreg = c.g.regions_per_rank * (u32)c.g.world;
-    ct_stage_kernel<W><<<(unsigned)((n + kPartTile - 1) / kPartTile), kPartThreads, ct_stage_smem(W, nreg, t->pb), t->stream>>>(
-        recs, n, c.g, c.pe, c.caps, static_cast<u32*>(c.reg_cursor.p), static_cast<u32*>(t->mask.p),
-        static_cast<u32*>(t->tile_counts.p), t->d_ctr);
+    ct_stage_kernel<W><<<(unsigned)((n + kStgTile - 1) / kStgTile), kStgThreads, ct_stage_smem(W, c.g.world), t->stream>>>(
+        recs, n, c.g, c.pe, c.caps, static_cast<u32*>(c.chunk_cursor.p), static_cast<V*>(c.fine.p), static_cast<u32*>(c.xout_cursor.p),
+        static_cast<u32*>(t->mask.p), static_cast<u32*>(t->tile_counts.p), t->d_ctr);
     KH_CUDA(t, cudaGetLastError());
     KH_TRY(device_scan(t, static_cast<u32*>(t->tile_counts.p), ntiles, static_cast<u64*>(t->tile_offs.p), &t->d_ctr->scan_total));
     ct_scatter_starts_kernel<W><<<(unsigned)((ntiles * 32 + 255) / 256), 256, 0, t->stream>>>(
@@ -658,20 +660,22 @@ __global__ void ct_init_assemble_kernel(Counters* c) {
     for (int i = 0; i < 40; ++i) c->flags[i] = 0;
 }
 
-// seal, part 0: publish the staging fill to the owners (then a barrier); part 1: group by chunk, lay out, build + contract
+// seal, part 0: tell the owners how much they received (then a barrier); part 1: file it, lay out, build + contract
 template <int W>
 int ct_seal_publish(kh_table* t) {
     auto& c = t->ct;
-    ct_publish_stage_kernel<<<4, 256, 0, t->stream>>>(c.g, c.pe, c.caps, static_cast<const u32*>(c.reg_cursor.p));
-    ++t->n_launches;
-    KH_CUDA(t, cudaGetLastError());
+    if (c.pe.world > 1) {
+        ct_publish_xin_kernel<<<1, 32, 0, t->stream>>>(c.pe, c.caps, static_cast<const u32*>(c.xout_cursor.p));
+        ++t->n_launches;
+        KH_CUDA(t, cudaGetLastError());
+    }
     return ct_barrier(t);
 }
 template <int W>
 int ct_seal_build(kh_table* t) {
     typedef typename Slot<W>::value_t V;
     auto& c = t->ct;
-    const u32 C = c.g.chunks_per_rank, R = c.g.regions_per_rank;
+    const u32 C = c.g.chunks_per_rank;
     if (!c.sharded) {                 // plain handle: the host knows the start count (every insert call synchronises)
         const u64 hcap = c.n_starts_host + 1;
         const u64 seg_cap = hcap + std::max<u64>(t->n_expected, 1) + 64;
@@ -682,17 +686,22 @@ int ct_seal_build(kh_table* t) {
         KH_TRY(ensure(t, c.ext_key, seg_cap * sizeof(V)));
         ct_set_self(t);
     }
-    KH_CUDA(t, cudaMemsetAsync(c.chunk_cursor.p, 0, (C + 1) * sizeof(u32), t->stream));
     ct_init_seal_kernel<<<1, 1, 0, t->stream>>>(t->d_ctr, c.caps.hcap);
-    ct_scatter_kernel<W><<<R * (u32)c.g.world * c.bprs, kSubThreads, 8u << c.g.cpr_shift, t->stream>>>(
-        static_cast<const V*>(c.stage_vals.p), static_cast<const unsigned short*>(c.stage_tags.p), static_cast<const u32*>(c.stage_cnt.p),
-        c.g, c.caps, c.bprs, static_cast<u32*>(c.chunk_cursor.p), static_cast<V*>(c.fine.p), t->d_ctr);
-    ct_extra_kernel<W><<<64, 256, 0, t->stream>>>(static_cast<const V*>(c.extra_vals.p), static_cast<const u32*>(c.extra_chunk.p),
-                                                  static_cast<const u32*>(c.extra_cnt.p), c.caps, static_cast<u32*>(c.chunk_cursor.p),
-                                                  static_cast<V*>(c.fine.p), t->d_ctr);
+    if (c.pe.world > 1) {
+        u32* done = static_cast<u32*>(c.xin_done.p);
+        ct_xin_scatter_kernel<W><<<(unsigned)t->sm_count * 8, 256, 0, t->stream>>>(
+            static_cast<const V*>(c.xin_vals.p), static_cast<const u32*>(c.xin_chunk.p), static_cast<const u32*>(c.xin_cnt.p), done,
+            c.g, c.caps, static_cast<u32*>(c.chunk_cursor.p), static_cast<V*>(c.fine.p), t->d_ctr);
+        ct_extra_kernel<W><<<64, 256, 0, t->stream>>>(static_cast<const V*>(c.extra_vals.p), static_cast<const u32*>(c.extra_chunk.p),
+                                                      static_cast<const u32*>(c.extra_cnt.p), done + kMaxRanks, c.caps,
+                                                      static_cast<u32*>(c.chunk_cursor.p), static_cast<V*>(c.fine.p), t->d_ctr);
+        ct_mark_filed_kernel<<<1, 32, 0, t->stream>>>(static_cast<const u32*>(c.xin_cnt.p), done, static_cast<const u32*>(c.extra_cnt.p),
+                                                      done + kMaxRanks, c.caps, c.pe.world);
+        t->n_launches += 3;
+    }
     ct_layout_kernel<<<1, 1024, 0, t->stream>>>(static_cast<const u32*>(c.chunk_cursor.p), C, c.g, c.caps, (u32)Slot<W>::kPerBucket,
                                                 CtBuild<W>::kMaxSlots, static_cast<u32*>(c.chunk_base.p), static_cast<u32*>(c.pool_off.p), t->d_ctr);
-    t->n_launches += 5;
+    t->n_launches += 2;
     KH_CUDA(t, cudaEventRecord(t->ev[EV_BUILD0], t->stream));
     ct_build_kernel<W><<<C, kCtBuildThreads, CtBuild<W>::kSmem, t->stream>>>(
         static_cast<const V*>(c.fine.p), static_cast<const u32*>(c.chunk_cursor.p), static_cast<const u32*>(c.chunk_base.p),
@@ -983,7 +992,7 @@ int kh_destroy(kh_table* t) {
     for (auto& row : t->ct.ipc_opened) for (void* q : row) if (q) cudaIpcCloseMemHandle(q);
     {
         auto& c = t->ct;
-        for (DevBuf* b : {&c.stage_vals, &c.stage_tags, &c.stage_cnt, &c.reg_cursor, &c.extra_vals, &c.extra_chunk, &c.extra_cnt, &c.fine,
+        for (DevBuf* b : {&c.xin_vals, &c.xin_chunk, &c.xin_cnt, &c.xin_done, &c.xout_cursor, &c.extra_vals, &c.extra_chunk, &c.extra_cnt, &c.fine,
                           &c.chunk_cursor, &c.chunk_base, &c.pool_off, &c.seg_base, &c.ext_key, &c.meta, &c.pool, &c.inbox, &c.inbox_cnt,
                           &c.out_cursor, &c.flags})
             if (b->p) cudaFree(b->p);
@@ -1008,8 +1017,7 @@ int kh_clear(kh_table* t) {
     KH_CUDA(t, cudaSetDevice(t->device));
     KH_CUDA(t, cudaEventRecord(t->ev[EV_CLR0], t->stream));
     if (t->ct.on) {              // a chunk table is rewritten chunk by chunk at the next seal: only the staging cursors go back to zero
-        KH_CUDA(t, cudaMemsetAsync(t->ct.reg_cursor.p, 0, kCtMaxRegions * sizeof(u32), t->stream));
-        KH_CUDA(t, cudaMemsetAsync(t->ct.extra_cnt.p, 0, 16, t->stream));
+        KH_TRY(ct_reset_staging(t));
         t->ct.sealed = false; t->ct.assembled = false;
         t->ct.n_starts_host = 0;
     } else {
@@ -1318,22 +1326,22 @@ int kh_shard_export_count(void) { return CTX_NBUF; }
 // everything two ranks must agree on to index each other's buffers
 static uint64_t ct_geometry_signature(kh_table* t) {
     const auto& c = t->ct;
-    u64 h = fmix64((u64)c.g.chunks_per_rank + 0x9E3779B97F4A7C15ull * (u64)c.g.cpr_shift);
-    h = fmix64(h ^ c.caps.cap_rs); h = fmix64(h ^ c.caps.extra_cap); h = fmix64(h ^ c.caps.inbox_cap);
+    u64 h = fmix64((u64)c.g.chunks_per_rank + 0x9E3779B97F4A7C15ull);
+    h = fmix64(h ^ c.caps.xin_cap); h = fmix64(h ^ c.caps.extra_cap); h = fmix64(h ^ c.caps.inbox_cap);
     return fmix64(h ^ (u64)c.pe.world);
 }
 
 static void ct_export_list(kh_table* t, void* (&bufs)[CTX_NBUF]) {
     auto& c = t->ct;
-    bufs[CTX_STAGE_VALS] = c.stage_vals.p; bufs[CTX_STAGE_TAGS] = c.stage_tags.p; bufs[CTX_STAGE_CNT] = c.stage_cnt.p;
+    bufs[CTX_XIN_VALS] = c.xin_vals.p; bufs[CTX_XIN_CHUNK] = c.xin_chunk.p; bufs[CTX_XIN_CNT] = c.xin_cnt.p;
     bufs[CTX_EXTRA_VALS] = c.extra_vals.p; bufs[CTX_EXTRA_CHUNK] = c.extra_chunk.p; bufs[CTX_EXTRA_CNT] = c.extra_cnt.p;
     bufs[CTX_LINK] = t->link.p; bufs[CTX_META] = c.meta.p; bufs[CTX_INBOX] = c.inbox.p; bufs[CTX_INBOX_CNT] = c.inbox_cnt.p;
     bufs[CTX_PRE] = t->contig_pre.p; bufs[CTX_OFF] = t->contig_off.p; bufs[CTX_OUT] = t->out.p; bufs[CTX_FLAGS] = c.flags.p;
 }
 static void ct_import_list(kh_table* t, int r, void* const (&p)[CTX_NBUF], u64 out_cap) {
     CtPeers& pe = t->ct.pe;
-    pe.stage_vals[r] = p[CTX_STAGE_VALS]; pe.stage_tags[r] = static_cast<unsigned short*>(p[CTX_STAGE_TAGS]);
-    pe.stage_cnt[r] = static_cast<u32*>(p[CTX_STAGE_CNT]);
+    pe.xin_vals[r] = p[CTX_XIN_VALS]; pe.xin_chunk[r] = static_cast<u32*>(p[CTX_XIN_CHUNK]);
+    pe.xin_cnt[r] = static_cast<u32*>(p[CTX_XIN_CNT]);
     pe.extra_vals[r] = p[CTX_EXTRA_VALS]; pe.extra_chunk[r] = static_cast<u32*>(p[CTX_EXTRA_CHUNK]);
     pe.extra_cnt[r] = static_cast<u32*>(p[CTX_EXTRA_CNT]);
     pe.link[r] = static_cast<u64*>(p[CTX_LINK]); pe.meta[r] = static_cast<u64*>(p[CTX_META]);
@@ -1465,13 +1473,13 @@ int kh_debug_buffer(kh_table* t, const char* name, void** ptr_out, uint64_t* byt
     const DevBuf* b = nullptr;
     if (n == "link") b = &t->link; else if (n == "meta") b = &c.meta; else if (n == "ext_key") b = &c.ext_key;
     else if (n == "chunk_base") b = &c.chunk_base; else if (n == "seg_base") b = &c.seg_base; else if (n == "chunk_cursor") b = &c.chunk_cursor;
-    else if (n == "inbox_cnt") b = &c.inbox_cnt; else if (n == "out_cursor") b = &c.out_cursor; else if (n == "stage_cnt") b = &c.stage_cnt;
+    else if (n == "inbox_cnt") b = &c.inbox_cnt; else if (n == "out_cursor") b = &c.out_cursor; else if (n == "xin_cnt") b = &c.xin_cnt;
     else if (n == "contig_len") b = &t->contig_len; else if (n == "pool") b = &c.pool;
     else if (n == "counters") { *ptr_out = t->d_ctr; *bytes_out = sizeof(Counters); return KH_OK; }
     else if (n == "caps") {          // host-side numbers: hcap, seg_cap, inbox_cap, cap_rs, chunks_per_rank, regions_per_rank
         static thread_local uint64_t v[8];
-        v[0] = c.caps.hcap; v[1] = c.caps.seg_cap; v[2] = c.caps.inbox_cap; v[3] = c.caps.cap_rs; v[4] = c.g.chunks_per_rank; v[5] = c.g.regions_per_rank;
-        v[6] = c.epoch; v[7] = c.g.cpr_shift;
+        v[0] = c.caps.hcap; v[1] = c.caps.seg_cap; v[2] = c.caps.inbox_cap; v[3] = c.caps.xin_cap; v[4] = c.g.chunks_per_rank; v[5] = 0;
+        v[6] = c.epoch; v[7] = 0;
         *ptr_out = v; *bytes_out = sizeof(v); return KH_OK;
     }
     if (!b) return fail(t, KH_ERR_ARG, "unknown buffer " + n);

@@ -40,17 +40,22 @@
 namespace kh {
 
 template <int W> struct CtBuild {
-    static constexpr u32 kMaxBuckets = (W == 1) ? 2048u : 2304u;                 // 64 / 72 KB of table per chunk
-    static constexpr u32 kMaxSlots = kMaxBuckets * (u32)Slot<W>::kPerBucket;      // 8192 / 4608
-    // table | succ u16[slots] | heads u16[slots] | characters u8[slots] | two bitmaps u32[slots / 32]
+    // A chunk = one run of buckets that a thread block builds in shared memory.  Shared memory per block:
+    //   table | succ u16[node] (later the characters) | (ancestor, distance) u32[node] | ext code + flags u8[node] | pool offset u16[node]
+    // = 104 448 B (64-bit slots) / 108 800 B (128-bit slots): two blocks of 512 threads per SM.
+    static constexpr u32 kMaxBuckets = (W == 1) ? 1536u : 2176u;                 // 48 / 68 KB of table per chunk
+    static constexpr u32 kMaxSlots = kMaxBuckets * (u32)Slot<W>::kPerBucket;      // 6144 / 4352: also the most records a chunk can take
     static constexpr u32 kOffSucc = kMaxBuckets * 32u;
-    static constexpr u32 kOffHeads = kOffSucc + kMaxSlots * 2u;
-    static constexpr u32 kOffPool = kOffHeads + kMaxSlots * 2u;
-    static constexpr u32 kOffBits = kOffPool + kMaxSlots;
-    static constexpr u32 kSmem = kOffBits + (kMaxSlots / 32u) * 8u;               // 108544 / 97920 B: two blocks per SM
+    static constexpr u32 kOffPd = kOffSucc + kMaxSlots * 2u;
+    static constexpr u32 kOffOff = kOffPd + kMaxSlots * 4u;
+    static constexpr u32 kOffCode = kOffOff + kMaxSlots * 2u;
+    static constexpr u32 kSmem = kOffCode + kMaxSlots;
 };
 constexpr int kCtBuildThreads = 512;
-constexpr u32 kSuccExt = 0xFFFFu, kSuccTail = 0xFFFEu, kSuccNone = 0xFFFDu;
+// s_succ[node]: successor node (< 0x8000) | kSuccExt + own slot (successor is not in this chunk) | kSuccTail | kSuccDead
+constexpr u32 kSuccExt = 0x8000u, kSuccTail = 0xFFFFu, kSuccDead = 0xFFFDu, kPredNone = 0xFFFFu;
+// s_code[node]: forward extension code in bits 0..2, then
+constexpr u32 kCodeBackF = 8u, kCodeMulti = 16u;
 
 template <int W> struct CtReq;                                                      // a pending link on its way to the owner
 template <> struct alignas(16) CtReq<1> { u64 key; u32 src; u32 chunk; };
@@ -58,10 +63,10 @@ template <> struct alignas(16) CtReq<2> { u128 key; u32 src; u32 chunk; u64 pad;
 
 struct CtPeers {
     int world, rank;
-    void* stage_vals[kMaxRanks];          // [R][world][cap_rs] slot values, grouped by (local region, source rank)
-    unsigned short* stage_tags[kMaxRanks];   // chunk inside the region, same shape
-    u32* stage_cnt[kMaxRanks];            // [R][world] published fill of each (region, source) buffer
-    void* extra_vals[kMaxRanks];          // records that found their staging buffer full
+    void* xin_vals[kMaxRanks];            // [world][xin_cap] slot values this rank received, by source rank
+    u32* xin_chunk[kMaxRanks];            // their local chunk ids, same shape
+    u32* xin_cnt[kMaxRanks];              // [world] published fill of each source's part
+    void* extra_vals[kMaxRanks];          // records that found their part of xin full
     u32* extra_chunk[kMaxRanks];
     u32* extra_cnt[kMaxRanks];
     u64* link[kMaxRanks];
@@ -76,7 +81,7 @@ struct CtPeers {
 };
 
 struct CtCaps {
-    u32 cap_rs, extra_cap, inbox_cap, seg_cap, hcap;
+    u32 xin_cap, extra_cap, inbox_cap, seg_cap, hcap;
     u64 nbuckets_alloc, pool_cap;
 };
 
@@ -121,132 +126,186 @@ __global__ void ct_barrier_kernel(const CtPeers pe, u32 epoch, Counters* ctr, in
     }
 }
 
-// ---- pass A: stage records, grouped by table region, in the owner's memory --------------------------------
-// Block-local counting sort of 2048 records by global region (owner rank, region of 2^cpr_shift chunks), then
-// one run per (block, region) appended to this source's buffer of that region ON THE OWNER GPU (peer stores
-// through NVLink when the owner is another GPU; the cursors are local because every source has its own buffer).
+// ---- pass A: every record goes to the per-chunk buffer of its home chunk ----------------------------------------
+// hash_map.hpp:55-80 (insert_all: bucket by owner, one batch per destination) fused with the grouping the build
+// needs.  A block parses a tile of 2048 records (staged through shared memory), computes minimizer -> (owner, chunk)
+// and then
+//   * records this GPU owns: one atomicAdd on the chunk's cursor, one 8/16-byte store into the chunk's buffer.  The
+//     write frontier is one line per chunk (a few MB in all), so L2 merges the stores into full lines: no second
+//     grouping pass, no staging copy;
+//   * records another GPU owns: block-local counting sort by owner (<= 8 bins), then ONE coalesced run per
+//     (block, owner) of values + chunk ids straight into the owner's receive buffer through its NVLink mapping --
+//     NVLink wants long runs; small scattered peer stores run at a few G/s.  The owner scatters what it received
+//     into its chunk buffers after the barrier (ct_xin_scatter_kernel).
 // Also the start bitmask / per-tile start counts for the order-preserving start scan (kmer_hash.cpp:27-31).
+// kmer_pair bytes -> slot value from the aligned 32-bit words that cover the record (sh = 8 * (address & 3)):
+// kmer_pair::init / packKmer (kmer_t.hpp:67-76, packing.hpp:77-92) read back as one big-endian number
+template <int W> __device__ __forceinline__ typename Slot<W>::value_t ct_record_from_words(const u32 (&w)[W == 1 ? 3 : 5], u32 sh, int k, int pl, bool& ok);
+template <> __device__ __forceinline__ u64 ct_record_from_words<1>(const u32 (&w)[3], u32 sh, int k, int pl, bool& ok) {
+    const u32 b0 = __funnelshift_r(w[0], w[1], sh), b1 = __funnelshift_r(w[1], w[2], sh);      // bytes 0-3, 4-7 of the record
+    const u64 be = ((u64)__byte_perm(b0, 0, 0x0123) << 32) | (u64)__byte_perm(b1, 0, 0x0123);
+    const u64 key = be >> (64 - 2 * k);
+    const u32 ext = (u32)((((u64)b1 << 32) | b0) >> (8 * pl));                                     // pl <= 6: both letters inside the 8 bytes
+    const u32 b = ext_code((unsigned char)ext), f = ext_code((unsigned char)(ext >> 8));
+    ok = (b != kExtBad) && (f != kExtBad);
+    return (key << 6) | ((u64)(b & 7u) << 3) | (u64)((f + 1u) & 7u);
+}
+template <> __device__ __forceinline__ u128 ct_record_from_words<2>(const u32 (&w)[5], u32 sh, int k, int pl, bool& ok) {
+    const u32 b0 = __funnelshift_r(w[0], w[1], sh), b1 = __funnelshift_r(w[1], w[2], sh);
+    const u32 b2 = __funnelshift_r(w[2], w[3], sh), b3 = __funnelshift_r(w[3], w[4], sh);
+    const u64 hi = ((u64)__byte_perm(b0, 0, 0x0123) << 32) | (u64)__byte_perm(b1, 0, 0x0123);
+    const u64 lo = ((u64)__byte_perm(b2, 0, 0x0123) << 32) | (u64)__byte_perm(b3, 0, 0x0123);
+    u128 v = Slot<2>::shr_any(u128{lo, hi}, 122 - 2 * k);
+    const int wq = pl >> 2;                                                                          // 1..3 (pl = 6..14), uniform
+    const u32 e0 = wq == 1 ? b1 : (wq == 2 ? b2 : b3), e1 = wq == 1 ? b2 : (wq == 2 ? b3 : 0u);
+    const u32 ext = __funnelshift_r(e0, e1, 8u * (pl & 3));
+    const u32 b = ext_code((unsigned char)ext), f = ext_code((unsigned char)(ext >> 8));
+    ok = (b != kExtBad) && (f != kExtBad);
+    v.lo = (v.lo & ~63ull) | ((u64)(b & 7u) << 3) | (u64)((f + 1u) & 7u);
+    return v;
+}
+
+constexpr int kStgThreads = 256;
+constexpr int kStgPer = 4;
+constexpr int kStgTile = kStgThreads * kStgPer;     // 1024 records per block = one tile of the start scan (kInsTile)
+
 template <int W>
-__global__ void __launch_bounds__(kPartThreads, 4)
+__global__ void __launch_bounds__(kStgThreads, 5)
 ct_stage_kernel(const unsigned char* __restrict__ recs, u64 n, const CtGeom g, const CtPeers pe, const CtCaps caps,
-                u32* __restrict__ reg_cursor, u32* __restrict__ start_mask, u32* __restrict__ tile_starts, Counters* ctr) {
+                u32* __restrict__ chunk_cursor, typename Slot<W>::value_t* __restrict__ fine, u32* __restrict__ xout_cursor,
+                u32* __restrict__ start_mask, u32* __restrict__ tile_starts, Counters* ctr) {
     typedef Slot<W> S;
     typedef typename S::value_t V;
+    constexpr u32 kMaxSlots = CtBuild<W>::kMaxSlots;
     extern __shared__ __align__(16) unsigned char s_raw[];
-    const u32 R = g.regions_per_rank, nreg = R * (u32)g.world;
-    u32* s_hist = reinterpret_cast<u32*>(s_raw);
-    u32* s_off = s_hist + nreg;
-    u32* s_gbase = s_off + nreg;
-    unsigned short* s_pid = reinterpret_cast<unsigned short*>(s_raw + 12 * (size_t)nreg);
-    unsigned short* s_tag = s_pid + kPartTile;
-    unsigned char* s_union = s_raw + ((12 * (size_t)nreg + 4 * kPartTile + 15) & ~(size_t)15);
-    unsigned char* s_rec = s_union;
-    V* s_sorted = reinterpret_cast<V*>(s_union);
-    __shared__ u64 s_warp[33];
-    __shared__ u32 s_starts[kPartTile / kInsTile], s_err;
+    // s_raw (multi-GPU only): the remote values of the tile sorted by owner | their chunk ids
+    V* s_sorted = reinterpret_cast<V*>(s_raw);
+    u32* s_schunk = reinterpret_cast<u32*>(s_raw + (size_t)kStgTile * sizeof(V));
+    __shared__ u32 s_cnt[kMaxRanks], s_off[kMaxRanks + 1], s_gbase[kMaxRanks];
+    __shared__ u32 s_starts[kStgTile / kInsTile], s_err;
     const int k = g.k, pl = (k + 3) >> 2, pb = pl + 2;
-    const u64 rec0 = (u64)blockIdx.x * kPartTile;
-    const u32 cnt = (u32)min((u64)kPartTile, n - rec0);
-    for (u32 i = threadIdx.x; i < nreg; i += blockDim.x) s_hist[i] = 0;
-    if (threadIdx.x < kPartTile / kInsTile) s_starts[threadIdx.x] = 0;
+    const u64 rec0 = (u64)blockIdx.x * kStgTile;
+    const u32 cnt = (u32)min((u64)kStgTile, n - rec0);
+    const bool multi = g.world > 1;
+    if (threadIdx.x < kMaxRanks) s_cnt[threadIdx.x] = 0;
+    if (threadIdx.x < kStgTile / kInsTile) s_starts[threadIdx.x] = 0;
     if (threadIdx.x == 0) s_err = 0;
-    stage_in(s_rec, recs + rec0 * pb, cnt * pb);
-    __syncthreads();
-    V v[kPartPerThread];
-    u32 pid[kPartPerThread], rk[kPartPerThread], tag[kPartPerThread];
-    u32 err = 0;
-    const u32 tag_mask = (1u << g.cpr_shift) - 1u;
+    // Records come straight from global memory into registers: a warp reads 32 consecutive records (a few hundred
+    // contiguous bytes) with aligned 32-bit loads, L1 serves the overlap between neighbours.  All loads of a thread are
+    // issued before the first record is parsed; no shared-memory staging, no barrier on the single-GPU path.
+    constexpr int kWords = W == 1 ? 3 : 5;
+    u32 raw[kStgPer][kWords];
+    u32 shift[kStgPer];
 #pragma unroll
-    for (int r = 0; r < kPartPerThread; ++r) {
-        const u32 j = threadIdx.x + r * kPartThreads;
+    for (int r = 0; r < kStgPer; ++r) {
+        const u32 j = threadIdx.x + r * kStgThreads;
+        const u64 addr = reinterpret_cast<u64>(recs) + (rec0 + j) * (u64)pb;
+        shift[r] = ((u32)addr & 3u) * 8u;
+        const u32* wp = reinterpret_cast<const u32*>(addr & ~3ull);
+        // the last records of the array are read word by word only as far as the array goes
+        const u64 end = reinterpret_cast<u64>(recs) + n * (u64)pb;
+#pragma unroll
+        for (int q = 0; q < kWords; ++q)
+            raw[r][q] = (j < cnt && reinterpret_cast<u64>(wp + q) < end) ? __ldg(wp + q) : 0u;
+    }
+    __syncthreads();                                   // the shared counters above
+    V v[kStgPer];
+    u32 dst[kStgPer];            // local chunk id, or 0xFFFFFFFF for a record that is not placed here
+    u32 at[kStgPer];             // position in the chunk's buffer (local) / rank inside the owner's bin (remote)
+    u32 own[kStgPer];            // owner rank of a remote record, 0xFFFFFFFF otherwise
+    u32 err = 0;
+#pragma unroll
+    for (int r = 0; r < kStgPer; ++r) {
+        const u32 j = threadIdx.x + r * kStgThreads;
         bool ok = true, live = j < cnt;
-        pid[r] = 0xFFFFFFFFu; tag[r] = 0;
-        v[r] = S::zero();
-        if (live) v[r] = S::from_record_staged(s_rec + j * pb, k, pl, ok);
-        if (!ok) { err |= kErrBadInput; live = false; }
+        dst[r] = 0xFFFFFFFFu; own[r] = 0xFFFFFFFFu; at[r] = 0;
+        v[r] = ct_record_from_words<W>(raw[r], shift[r], k, pl, ok);
+        if (!live) v[r] = S::zero();
+        if (live && !ok) { err |= kErrBadInput; live = false; }
         if (live) {
             u32 owner, chunk;
             ct_place(ct_min_hash<W>(v[r], g.m, g.win), g, owner, chunk);
-            pid[r] = owner * R + (chunk >> g.cpr_shift);
-            tag[r] = chunk & tag_mask;
-            rk[r] = atomicAdd(&s_hist[pid[r]], 1u);
+            dst[r] = chunk;
+            if (!multi || owner == (u32)g.rank) at[r] = atomicAdd(&chunk_cursor[chunk], 1u);
+            else own[r] = owner;
+        }
+        if (multi) {                                   // rank of a remote record inside its owner's bin of this tile
+            const unsigned same = __match_any_sync(kFullMask, own[r]);
+            const int leader = __ffs(same) - 1;
+            u32 first = 0;
+            if ((int)lane_id() == leader && own[r] != 0xFFFFFFFFu) first = atomicAdd(&s_cnt[own[r]], (u32)__popc(same));
+            first = __shfl_sync(kFullMask, first, leader);
+            if (own[r] != 0xFFFFFFFFu) at[r] = first + (u32)__popc(same & ((1u << lane_id()) - 1u));
         }
         const u32 bal = __ballot_sync(kFullMask, live && S::back(v[r]) == kExtF);
-        const u64 first = rec0 + (u64)r * kPartThreads + (threadIdx.x & ~31u);
-        if (lane_id() == 0 && first < n) {
-            start_mask[first >> 5] = bal;
-            if (bal) atomicAdd(&s_starts[(r * kPartThreads + threadIdx.x) / kInsTile], (u32)__popc(bal));
+        const u64 first_rec = rec0 + (u64)r * kStgThreads + (threadIdx.x & ~31u);
+        if (lane_id() == 0 && first_rec < n) {
+            start_mask[first_rec >> 5] = bal;
+            if (bal) atomicAdd(&s_starts[(r * kStgThreads + threadIdx.x) / kInsTile], (u32)__popc(bal));
         }
+    }
+    // records of this GPU: straight into their chunk's buffer
+#pragma unroll
+    for (int r = 0; r < kStgPer; ++r) {
+        if (dst[r] == 0xFFFFFFFFu || own[r] != 0xFFFFFFFFu) continue;
+        if (at[r] < kMaxSlots) fine[(u64)dst[r] * kMaxSlots + at[r]] = v[r];
+        else err |= kErrTableFull;                     // more k-mers share this chunk than a chunk can hold
     }
     err = __reduce_or_sync(kFullMask, err);
     if (lane_id() == 0 && err) atomicOr(&s_err, err);
-    __syncthreads();
-    {   // exclusive scan of the histogram (nreg <= 1024 = 4 per thread) + reservations in this source's buffers
-        u32 h[4], sum = 0;
-#pragma unroll
-        for (int q = 0; q < 4; ++q) {
-            const u32 i = threadIdx.x * 4 + q;
-            h[q] = i < nreg ? s_hist[i] : 0u;
-            sum += h[q];
-        }
-        u64 total;
-        u64 run = block_exclusive_scan((u64)sum, s_warp, total);
-#pragma unroll
-        for (int q = 0; q < 4; ++q) {
-            const u32 i = threadIdx.x * 4 + q;
-            if (i < nreg) {
-                s_off[i] = (u32)run;
-                s_gbase[i] = h[q] ? atomicAdd(&reg_cursor[i], h[q]) : 0u;
+    if (multi) {
+        __syncthreads();                               // s_cnt complete
+        if (threadIdx.x == 0) {
+            u32 run = 0;
+            for (int d = 0; d < g.world; ++d) {
+                s_off[d] = run;
+                s_gbase[d] = s_cnt[d] ? atomicAdd(&xout_cursor[d], s_cnt[d]) : 0u;
+                run += s_cnt[d];
             }
-            run += h[q];
+            s_off[g.world] = run;
         }
-    }
-    __syncthreads();
+        __syncthreads();
 #pragma unroll
-    for (int r = 0; r < kPartPerThread; ++r) {
-        if (pid[r] != 0xFFFFFFFFu) {
-            const u32 pos = s_off[pid[r]] + rk[r];
+        for (int r = 0; r < kStgPer; ++r) {
+            if (own[r] == 0xFFFFFFFFu) continue;
+            const u32 pos = s_off[own[r]] + at[r];
             s_sorted[pos] = v[r];
-            s_pid[pos] = (unsigned short)pid[r];
-            s_tag[pos] = (unsigned short)tag[r];
+            s_schunk[pos] = dst[r];
         }
-    }
-    __syncthreads();
-    const u32 good = s_off[nreg - 1] + s_hist[nreg - 1];
-    for (u32 pos = threadIdx.x; pos < good; pos += blockDim.x) {
-        const u32 p = s_pid[pos];
-        const u32 owner = p / R, lr = p - owner * R;
-        const u32 at = s_gbase[p] + (pos - s_off[p]);
-        if (at < caps.cap_rs) {
-            const u64 slot = ((u64)lr * (u32)g.world + (u32)g.rank) * caps.cap_rs + at;
-            static_cast<V*>(pe.stage_vals[owner])[slot] = s_sorted[pos];
-            pe.stage_tags[owner][slot] = s_tag[pos];
-        } else {                                           // this (region, source) buffer is full: hand it to the owner one by one
-            const u32 o = atomicAdd_system(pe.extra_cnt[owner], 1u);
-            if (o < caps.extra_cap) {
-                static_cast<V*>(pe.extra_vals[owner])[o] = s_sorted[pos];
-                pe.extra_chunk[owner][o] = (lr << g.cpr_shift) | s_tag[pos];
-            } else {
-                atomicOr(&s_err, kErrTableFull);            // far more records than the table was sized for
+        __syncthreads();
+        const u32 total = s_off[g.world];
+        for (u32 pos = threadIdx.x; pos < total; pos += kStgThreads) {
+            u32 d = 0;
+#pragma unroll
+            for (int q = 1; q < kMaxRanks; ++q) d += (q < g.world && pos >= s_off[q]) ? 1u : 0u;
+            const u32 i = s_gbase[d] + (pos - s_off[d]);
+            if (i < caps.xin_cap) {
+                const u64 slot = (u64)g.rank * caps.xin_cap + i;
+                static_cast<V*>(pe.xin_vals[d])[slot] = s_sorted[pos];
+                pe.xin_chunk[d][slot] = s_schunk[pos];
+            } else {                                   // this source's part of the owner's buffer is full: hand it over one by one
+                const u32 o = atomicAdd_system(pe.extra_cnt[d], 1u);
+                if (o < caps.extra_cap) {
+                    static_cast<V*>(pe.extra_vals[d])[o] = s_sorted[pos];
+                    pe.extra_chunk[d][o] = s_schunk[pos];
+                } else {
+                    atomicOr(&s_err, kErrTableFull);    // far more records than the table was sized for
+                }
             }
         }
     }
     __syncthreads();
-    if (threadIdx.x < kPartTile / kInsTile) {
-        const u64 tile = (u64)blockIdx.x * (kPartTile / kInsTile) + threadIdx.x;
+    if (threadIdx.x < kStgTile / kInsTile) {
+        const u64 tile = (u64)blockIdx.x * (kStgTile / kInsTile) + threadIdx.x;
         if (tile * kInsTile < n) tile_starts[tile] = s_starts[threadIdx.x];
     }
     if (threadIdx.x == 0 && s_err) atomicOr(&ctr->errors, s_err);
 }
 
-// tell every owner how much this source has put into each of its regions' buffers
-__global__ void __launch_bounds__(256)
-ct_publish_stage_kernel(const CtGeom g, const CtPeers pe, const CtCaps caps, const u32* __restrict__ reg_cursor) {
-    const u32 R = g.regions_per_rank, nreg = R * (u32)g.world;
-    for (u32 i = blockIdx.x * blockDim.x + threadIdx.x; i < nreg; i += gridDim.x * blockDim.x) {
-        const u32 owner = i / R, lr = i - owner * R;
-        pe.stage_cnt[owner][lr * (u32)g.world + (u32)g.rank] = min(reg_cursor[i], caps.cap_rs);
-    }
+// tell every owner how much this source has put into its receive buffer
+__global__ void ct_publish_xin_kernel(const CtPeers pe, const CtCaps caps, const u32* __restrict__ xout_cursor) {
+    const int d = (int)threadIdx.x;
+    if (d < pe.world && d != pe.rank) pe.xin_cnt[d][pe.rank] = min(xout_cursor[d], caps.xin_cap);
 }
 
 // start nodes seen so far live on the device (no host round trip per insert call in the sharded path)
@@ -256,66 +315,50 @@ __global__ void ct_bump_starts_kernel(Counters* ctr, u32 hcap) {
     else ctr->n_starts_dev = total;
 }
 
-// ---- pass B: the staged values of one (region, source) buffer -> per-chunk buffers --------------------------
+// ---- the owner files what it received: receive buffer -> chunk buffers ------------------------------------------
+// done[s] = records of source s already filed (an insert after a seal only adds the new ones)
 template <int W>
-__global__ void __launch_bounds__(kSubThreads, 4)
-ct_scatter_kernel(const typename Slot<W>::value_t* __restrict__ stage_vals, const unsigned short* __restrict__ stage_tags,
-                  const u32* __restrict__ stage_cnt, const CtGeom g, const CtCaps caps, u32 blocks_per_rs,
-                  u32* __restrict__ chunk_cursor, typename Slot<W>::value_t* __restrict__ fine, Counters* ctr) {
-    typedef Slot<W> S;
-    typedef typename S::value_t V;
-    extern __shared__ __align__(16) unsigned char s_raw[];
-    const u32 cpr = 1u << g.cpr_shift;
-    u32* s_hist = reinterpret_cast<u32*>(s_raw);
-    u32* s_gbase = s_hist + cpr;
-    const u32 rs = blockIdx.x / blocks_per_rs, jblk = blockIdx.x % blocks_per_rs;      // rs = lr * world + src
-    const u32 n = min(stage_cnt[rs], caps.cap_rs);
-    const u32 base = jblk * kSubTile;
-    if (base >= n) return;
-    const u32 lr = rs / (u32)g.world;
-    const V* __restrict__ src = stage_vals + (u64)rs * caps.cap_rs;
-    const unsigned short* __restrict__ tags = stage_tags + (u64)rs * caps.cap_rs;
-    for (u32 i = threadIdx.x; i < cpr; i += blockDim.x) s_hist[i] = 0;
-    __syncthreads();
-    V v[kSubPerThread];
-    u32 sid[kSubPerThread], rk[kSubPerThread];
-#pragma unroll
-    for (int r = 0; r < kSubPerThread; ++r) {
-        const u32 i = base + r * kSubThreads + threadIdx.x;
-        sid[r] = 0xFFFFFFFFu;
-        if (i < n) { v[r] = src[i]; sid[r] = tags[i]; }
-    }
-#pragma unroll
-    for (int r = 0; r < kSubPerThread; ++r)
-        if (sid[r] != 0xFFFFFFFFu) rk[r] = atomicAdd(&s_hist[sid[r]], 1u);
-    __syncthreads();
-    const u32 first_chunk = lr << g.cpr_shift;
-    for (u32 i = threadIdx.x; i < cpr; i += blockDim.x)
-        s_gbase[i] = s_hist[i] ? atomicAdd(&chunk_cursor[first_chunk + i], s_hist[i]) : 0u;
-    __syncthreads();
+__global__ void __launch_bounds__(256)
+ct_xin_scatter_kernel(const typename Slot<W>::value_t* __restrict__ xin_vals, const u32* __restrict__ xin_chunk,
+                      const u32* __restrict__ xin_cnt, const u32* __restrict__ xin_done, const CtGeom g, const CtCaps caps,
+                      u32* __restrict__ chunk_cursor, typename Slot<W>::value_t* __restrict__ fine, Counters* ctr) {
     constexpr u32 kMaxSlots = CtBuild<W>::kMaxSlots;
-#pragma unroll
-    for (int r = 0; r < kSubPerThread; ++r) {
-        if (sid[r] == 0xFFFFFFFFu) continue;
-        const u32 at = s_gbase[sid[r]] + rk[r];
-        if (at < kMaxSlots) fine[(u64)(first_chunk + sid[r]) * kMaxSlots + at] = v[r];
-        else atomicOr(&ctr->errors, kErrTableFull);           // more k-mers share this chunk than a chunk can hold
+    u32 err = 0;
+    for (int src = 0; src < g.world; ++src) {
+        if (src == g.rank) continue;
+        const u32 n = min(xin_cnt[src], caps.xin_cap), n0 = min(xin_done[src], n);
+        const u64 base = (u64)src * caps.xin_cap;
+        for (u32 i = n0 + blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) {
+            const u32 c = xin_chunk[base + i];
+            const u32 at = atomicAdd(&chunk_cursor[c], 1u);
+            if (at < kMaxSlots) fine[(u64)c * kMaxSlots + at] = xin_vals[base + i];
+            else err |= kErrTableFull;
+        }
     }
+    if (err) atomicOr(&ctr->errors, err);
 }
 
 template <int W>
 __global__ void __launch_bounds__(256)
 ct_extra_kernel(const typename Slot<W>::value_t* __restrict__ extra_vals, const u32* __restrict__ extra_chunk,
-                const u32* __restrict__ extra_cnt, const CtCaps caps, u32* __restrict__ chunk_cursor,
+                const u32* __restrict__ extra_cnt, const u32* __restrict__ extra_done, const CtCaps caps, u32* __restrict__ chunk_cursor,
                 typename Slot<W>::value_t* __restrict__ fine, Counters* ctr) {
     constexpr u32 kMaxSlots = CtBuild<W>::kMaxSlots;
-    const u32 n = min(*extra_cnt, caps.extra_cap);
-    for (u32 i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) {
+    const u32 n = min(*extra_cnt, caps.extra_cap), n0 = min(*extra_done, n);
+    for (u32 i = n0 + blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) {
         const u32 c = extra_chunk[i];
         const u32 at = atomicAdd(&chunk_cursor[c], 1u);
         if (at < kMaxSlots) fine[(u64)c * kMaxSlots + at] = extra_vals[i];
         else atomicOr(&ctr->errors, kErrTableFull);
     }
+}
+
+// what has been filed so far (runs after the two kernels above)
+__global__ void ct_mark_filed_kernel(const u32* __restrict__ xin_cnt, u32* __restrict__ xin_done, const u32* __restrict__ extra_cnt,
+                                     u32* __restrict__ extra_done, const CtCaps caps, int world) {
+    const int s = (int)threadIdx.x;
+    if (s < world) xin_done[s] = min(xin_cnt[s], caps.xin_cap);
+    if (s == 0) *extra_done = min(*extra_cnt, caps.extra_cap);
 }
 
 // ---- layout: every chunk gets load / load_factor slots ------------------------------------------------------
@@ -350,55 +393,111 @@ ct_layout_kernel(const u32* __restrict__ chunk_cursor, u32 nchunks, const CtGeom
     }
 }
 
-// ---- pass C: build a chunk in shared memory and contract its chains ------------------------------------------
-template <int W>
-__device__ __forceinline__ void ct_lds_bucket(unsigned saddr, u64 (&q)[4]) {
-    asm volatile("ld.shared.v2.u64 {%0,%1}, [%2];" : "=l"(q[0]), "=l"(q[1]) : "r"(saddr));
-    asm volatile("ld.shared.v2.u64 {%0,%1}, [%2+16];" : "=l"(q[2]), "=l"(q[3]) : "r"(saddr));
+// ---- pass B: build a chunk in shared memory and contract its chains ------------------------------------------
+// Nodes are the chunk's RECORDS (dense ids 0 .. cnt-1), so every phase after the insert runs with full warps at any
+// load factor; while the chunk is being built a slot's index bits carry 1 + the node id of the k-mer stored there.
+//
+// Probing compares 32-bit tags (key bits 0..31; an occupied slot has a non-zero forward field, so "empty" is a test
+// of three bits) and touches the rest of a slot only on a tag match: two LDS.64 per 128-bit bucket instead of 32 bytes.
+template <int W> __device__ __forceinline__ u32 ct_tag(typename Slot<W>::value_t v);
+template <> __device__ __forceinline__ u32 ct_tag<1>(u64 v) { return (u32)(v >> 6); }
+template <> __device__ __forceinline__ u32 ct_tag<2>(u128 v) { return (u32)(v.lo >> 6); }
+
+template <int W, bool VOLATILE>
+__device__ __forceinline__ void ct_lds_tags(unsigned saddr, u64 (&w)[4]) {        // the word of each slot of a bucket that holds ext bits + low key bits
+    if (W == 1) {
+        if (VOLATILE) {
+            asm volatile("ld.volatile.shared.v2.u64 {%0,%1}, [%2];" : "=l"(w[0]), "=l"(w[1]) : "r"(saddr) : "memory");
+            asm volatile("ld.volatile.shared.v2.u64 {%0,%1}, [%2+16];" : "=l"(w[2]), "=l"(w[3]) : "r"(saddr) : "memory");
+        } else {
+            asm volatile("ld.shared.v2.u64 {%0,%1}, [%2];" : "=l"(w[0]), "=l"(w[1]) : "r"(saddr));
+            asm volatile("ld.shared.v2.u64 {%0,%1}, [%2+16];" : "=l"(w[2]), "=l"(w[3]) : "r"(saddr));
+        }
+    } else {
+        if (VOLATILE) {
+            asm volatile("ld.volatile.shared.u64 %0, [%1];" : "=l"(w[0]) : "r"(saddr) : "memory");
+            asm volatile("ld.volatile.shared.u64 %0, [%1+16];" : "=l"(w[1]) : "r"(saddr) : "memory");
+        } else {
+            asm volatile("ld.shared.u64 %0, [%1];" : "=l"(w[0]) : "r"(saddr));
+            asm volatile("ld.shared.u64 %0, [%1+16];" : "=l"(w[1]) : "r"(saddr));
+        }
+    }
+}
+__device__ __forceinline__ u64 ct_lds64(unsigned saddr) {
+    u64 x;
+    asm volatile("ld.volatile.shared.u64 %0, [%1];" : "=l"(x) : "r"(saddr) : "memory");
+    return x;
+}
+// full comparison of slot i of the bucket at saddr with `key` (extension and index bits ignored), given its low word
+template <int W> __device__ __forceinline__ bool ct_verify(unsigned saddr, int i, u64 low, typename Slot<W>::value_t key, u64& idx_word);
+template <> __device__ __forceinline__ bool ct_verify<1>(unsigned, int, u64 low, u64 key, u64& idx_word) {
+    idx_word = low;
+    return CtSlot<1>::same_key(low, key);
+}
+template <> __device__ __forceinline__ bool ct_verify<2>(unsigned saddr, int i, u64 low, u128 key, u64& idx_word) {
+    idx_word = ct_lds64(saddr + 16u * i + 8u);
+    return (((idx_word ^ key.hi) << kIdxBits) | ((low ^ key.lo) >> 6)) == 0ull;
 }
 
-// insert into the chunk held in shared memory; linear probing that wraps inside the chunk
+// insert `val` (slot value with the node id in its index bits) into the chunk held in shared memory; linear probing
+// that wraps inside the chunk.  Returns the slot index, or -1 for a duplicate key, -2 if the chunk is full.
 template <int W>
-__device__ __forceinline__ int ct_smem_insert(typename Slot<W>::value_t* s_tab, u32 nb, typename Slot<W>::value_t v) {
+__device__ __forceinline__ int ct_smem_insert(typename Slot<W>::value_t* s_tab, unsigned s_base, u32 nb, typename Slot<W>::value_t val) {
     typedef Slot<W> S;
     typedef typename S::value_t V;
-    const unsigned s_base = (unsigned)__cvta_generic_to_shared(s_tab);
-    u32 b = ct_bucket_in_chunk(CtSlot<W>::hash32(S::key_only(v)), nb);
+    const u32 tag = ct_tag<W>(val);
+    u32 b = ct_bucket_in_chunk(CtSlot<W>::hash32(val), nb);
     for (u32 tries = 0; tries < nb;) {
-        u64 q[4];
-        lds_bucket(s_base + b * 32u, q);
+        u64 w[4];
+        ct_lds_tags<W, true>(s_base + b * 32u, w);
         int j = -1;
-        bool dup = false;
+        u32 match = 0;
 #pragma unroll
         for (int i = S::kPerBucket - 1; i >= 0; --i) {
-            const V c = S::from_bucket(q, i);
-            if (S::empty(c)) j = i;
-            else if (S::same_key(c, v)) dup = true;
+            const bool e = ((u32)w[i] & 7u) == 0u;
+            j = e ? i : j;
+            match |= (!e && (u32)(w[i] >> 6) == tag) ? (1u << i) : 0u;
         }
-        if (dup) return kInsDuplicate;
+        if (match) {                                     // rare: the same 32 low key bits -- look at the whole key
+#pragma unroll
+            for (int i = 0; i < S::kPerBucket; ++i) {
+                u64 iw;
+                if ((match >> i) & 1u) if (ct_verify<W>(s_base + b * 32u, i, w[i], val, iw)) return -1;
+            }
+        }
         if (j < 0) { b = (b + 1 == nb) ? 0u : b + 1; ++tries; continue; }
-        const V old = S::cas_shared(s_tab + b * S::kPerBucket + j, S::zero(), v);
-        if (S::empty(old)) return kInsInserted;
-        if (S::same_key(old, v)) return kInsDuplicate;
+        const V old = S::cas_shared(s_tab + b * S::kPerBucket + j, S::zero(), val);
+        if (S::empty(old)) return (int)(b * S::kPerBucket + j);
+        if (CtSlot<W>::same_key(old, val)) return -1;
     }
-    return kInsFull;
+    return -2;
 }
 
-// slot index of `key` (ext and index bits 0) in the finished chunk, or -1
+// node id of the k-mer `key` in the finished chunk (from the index bits of its slot), or -1
 template <int W>
-__device__ __forceinline__ int ct_smem_find(unsigned s_base, u32 nb, typename Slot<W>::value_t key) {
+__device__ __forceinline__ int ct_smem_find_node(unsigned s_base, u32 nb, typename Slot<W>::value_t key) {
     typedef Slot<W> S;
-    typedef typename S::value_t V;
+    const u32 tag = ct_tag<W>(key);
     u32 b = ct_bucket_in_chunk(CtSlot<W>::hash32(key), nb);
     for (u32 tries = 0; tries < nb; ++tries) {
-        u64 q[4];
-        ct_lds_bucket<W>(s_base + b * 32u, q);
+        u64 w[4];
+        ct_lds_tags<W, false>(s_base + b * 32u, w);
+        u32 match = 0;
+        bool hole = false;
 #pragma unroll
-        for (int i = 0; i < S::kPerBucket; ++i) {
-            const V c = S::from_bucket(q, i);
-            if (S::empty(c)) return -1;
-            if (S::same_key(c, key)) return (int)(b * S::kPerBucket + i);
+        for (int i = S::kPerBucket - 1; i >= 0; --i) {          // slots fill in order: a hit can only sit before the first hole
+            const bool e = ((u32)w[i] & 7u) == 0u;
+            hole = hole || e;
+            match = e ? 0u : (match | (((u32)(w[i] >> 6) == tag) ? (1u << i) : 0u));
         }
+        if (match) {
+#pragma unroll
+            for (int i = 0; i < S::kPerBucket; ++i) {
+                u64 iw;
+                if ((match >> i) & 1u) if (ct_verify<W>(s_base + b * 32u, i, w[i], key, iw)) return (int)(iw >> (64 - kIdxBits)) - 1;
+            }
+        }
+        if (hole) return -1;
         b = (b + 1 == nb) ? 0u : b + 1;
     }
     return -1;
@@ -415,13 +514,14 @@ ct_build_kernel(const typename Slot<W>::value_t* __restrict__ fine, const u32* _
     typedef CtSlot<W> CS;
     typedef typename S::value_t V;
     typedef CtBuild<W> B;
-    extern __shared__ __align__(16) unsigned char s_raw[];
+    extern __shared__ __align__(128) unsigned char s_bld[];
+    unsigned char* const s_raw = s_bld;
     V* s_tab = reinterpret_cast<V*>(s_raw);
     unsigned short* s_succ = reinterpret_cast<unsigned short*>(s_raw + B::kOffSucc);
-    unsigned short* s_heads = reinterpret_cast<unsigned short*>(s_raw + B::kOffHeads);
-    unsigned char* s_pool = s_raw + B::kOffPool;
-    u32* s_haspred = reinterpret_cast<u32*>(s_raw + B::kOffBits);
-    u32* s_multi = s_haspred + B::kMaxSlots / 32u;
+    unsigned char* s_pool = s_raw + B::kOffSucc;                 // the characters take over s_succ's memory once the links are out
+    u32* s_pd = reinterpret_cast<u32*>(s_raw + B::kOffPd);       // (ancestor node << 16) | distance to it; a segment head: (itself << 16) | its segment index
+    unsigned short* s_off = reinterpret_cast<unsigned short*>(s_raw + B::kOffOff);
+    unsigned char* s_code = s_raw + B::kOffCode;
     __shared__ u32 s_inserted, s_dups, s_nheads, s_seg0, s_chars, s_err;
     const u32 c = blockIdx.x;
     const u32 b0 = chunk_base[c], nb = chunk_base[c + 1] - b0;
@@ -430,7 +530,6 @@ ct_build_kernel(const typename Slot<W>::value_t* __restrict__ fine, const u32* _
         if (threadIdx.x == 0) seg_base[c] = 0;
         return;
     }
-    const u32 nslots = nb * S::kPerBucket;
     const V* __restrict__ recs = fine + (u64)c * B::kMaxSlots;
     const unsigned s_base = (unsigned)__cvta_generic_to_shared(s_tab);
     const int k = g.k;
@@ -444,11 +543,11 @@ ct_build_kernel(const typename Slot<W>::value_t* __restrict__ fine, const u32* _
     if (threadIdx.x == 0) { s_inserted = 0; s_dups = 0; s_nheads = 0; s_chars = 0; s_err = 0; }
     {
         uint4* s4 = reinterpret_cast<uint4*>(s_raw);
-        for (u32 i = threadIdx.x; i < nb * 2u; i += blockDim.x) s4[i] = make_uint4(0, 0, 0, 0);
-        for (u32 i = threadIdx.x; i < B::kMaxSlots / 16u; i += blockDim.x) s_haspred[i] = 0;      // both bitmaps
+        for (u32 i = threadIdx.x; i < nb * 2u; i += kCtBuildThreads) s4[i] = make_uint4(0, 0, 0, 0);
+        for (u32 i = threadIdx.x; i < cnt; i += kCtBuildThreads) s_pd[i] = (kPredNone << 16) | 1u;
     }
     __syncthreads();
-    // ---- 1. insert ----
+    // ---- 1. insert (hash_map.hpp:33-35): s_succ[node] = the slot the record went to, for phase 2 ----
     u32 inserted = 0, dups = 0, err = 0;
     for (u32 base = 0; base < cnt; base += kCtBuildThreads * kBatch) {
         V nxt[kBatch];
@@ -459,11 +558,13 @@ ct_build_kernel(const typename Slot<W>::value_t* __restrict__ fine, const u32* _
         }
 #pragma unroll
         for (int r = 0; r < kBatch; ++r) {
-            if (S::empty(v[r])) continue;
-            const int rc = ct_smem_insert<W>(s_tab, nb, v[r]);
-            inserted += (rc == kInsInserted);
-            dups += (rc == kInsDuplicate);
-            if (rc == kInsFull) err |= kErrTableFull;
+            const u32 node = base + threadIdx.x + r * kCtBuildThreads;
+            if (node >= cnt) continue;
+            const int slot = ct_smem_insert<W>(s_tab, s_base, nb, CS::with_idx(v[r], node + 1u));
+            inserted += (slot >= 0);
+            dups += (slot == -1);
+            if (slot == -2) err |= kErrTableFull;
+            s_succ[node] = (unsigned short)(slot >= 0 ? (u32)slot : kSuccDead);
         }
 #pragma unroll
         for (int r = 0; r < kBatch; ++r) v[r] = nxt[r];
@@ -478,46 +579,46 @@ ct_build_kernel(const typename Slot<W>::value_t* __restrict__ fine, const u32* _
     }
     __syncthreads();
     // ---- 2. successor of every k-mer, if it lives in this chunk (kmer_hash.cpp:44-51 as an LDS probe) ----
-    for (u32 i = threadIdx.x; i < nslots; i += blockDim.x) {
-        const V cur = s_tab[i];
-        u32 s = kSuccNone;
-        if (!S::empty(cur)) {
-            if (S::fwd(cur) == kExtF) {
-                s = kSuccTail;
+#pragma unroll 1
+    for (u32 node = threadIdx.x; node < cnt; node += kCtBuildThreads) {
+        const u32 slot = s_succ[node];
+        if (slot == kSuccDead) { s_code[node] = (unsigned char)kExtF; continue; }       // a duplicate: not in the table, on no chain
+        const V cur = s_tab[slot];
+        const u32 f = S::fwd(cur);
+        s_code[node] = (unsigned char)(f | (S::back(cur) == kExtF ? kCodeBackF : 0u));
+        u32 s = kSuccTail;
+        if (f != kExtF) {
+            const int j = ct_smem_find_node<W>(s_base, nb, S::next_key(CS::strip(cur), k));
+            if (j < 0) {
+                s = kSuccExt | slot;
             } else {
-                const int j = ct_smem_find<W>(s_base, nb, S::next_key(cur, k));
-                if (j < 0) {
-                    s = kSuccExt;
-                } else {
-                    s = (u32)j;
-                    const u32 bit = 1u << (j & 31);
-                    const u32 old = atomicOr(&s_haspred[j >> 5], bit);
-                    if (old & bit) atomicOr(&s_multi[j >> 5], bit);       // two predecessors: j must start a segment of its own
-                }
+                s = (u32)j;
+                s_pd[j] = (node << 16) | 1u;            // plain store: with two predecessors one of them wins, phase 3 notices
             }
         }
-        s_succ[i] = (unsigned short)s;
+        s_succ[node] = (unsigned short)s;
     }
     __syncthreads();
     // ---- 3. heads: k-mers no chain of this chunk runs into (or that two run into, or with backward ext 'F') ----
-    for (u32 base = 0; base < nslots; base += blockDim.x) {
-        const u32 i = base + threadIdx.x;
-        bool head = false;
-        V cur = S::zero();
-        if (i < nslots && s_succ[i] != kSuccNone) {
-            cur = s_tab[i];
-            const u32 bit = 1u << (i & 31);
-            head = !(s_haspred[i >> 5] & bit) || (s_multi[i >> 5] & bit) || S::back(cur) == kExtF;
+#pragma unroll 1
+    for (u32 node = threadIdx.x; node < cnt; node += kCtBuildThreads) {
+        const u32 s = s_succ[node];
+        if (s < kSuccExt && (s_pd[s] >> 16) != node) s_code[s] |= (unsigned char)kCodeMulti;      // rare; every writer stores the same bit
+    }
+    __syncthreads();
+    for (u32 base = 0; base < cnt; base += kCtBuildThreads) {
+        const u32 node = base + threadIdx.x;
+        bool head = false, dead = true;
+        if (node < cnt) {
+            dead = s_succ[node] == kSuccDead;
+            head = !dead && ((s_pd[node] >> 16) == kPredNone || (s_code[node] & (kCodeBackF | kCodeMulti)));
         }
         const u32 bal = __ballot_sync(kFullMask, head);
         u32 first = 0;
         if (lane_id() == 0 && bal) first = atomicAdd(&s_nheads, (u32)__popc(bal));
         first = __shfl_sync(kFullMask, first, 0);
-        if (head) {
-            const u32 idx = first + __popc(bal & ((1u << lane_id()) - 1u));
-            s_heads[idx] = (unsigned short)i;
-            s_tab[i] = CS::with_idx(cur, idx + 1u);
-        }
+        if (head) s_pd[node] = (node << 16) | (first + __popc(bal & ((1u << lane_id()) - 1u)));      // a root: (itself, segment index)
+        else if (dead && node < cnt) s_pd[node] = node << 16;                                          // never looked at again
     }
     __syncthreads();
     const u32 nheads = s_nheads;
@@ -527,47 +628,99 @@ ct_build_kernel(const typename Slot<W>::value_t* __restrict__ fine, const u32* _
         s_seg0 = seg0;
         seg_base[c] = seg0;
     }
+    // ---- 4. pointer jumping in shared memory: every k-mer learns its segment head and its distance from it ----
+    // In place: a stale read is still a valid (ancestor, distance) pair.  A root's low half is its segment index, which a
+    // child never adds (it stops as soon as its ancestor is a root).  Chains are <= ~40 k-mers: ~6 rounds; a cycle
+    // without a head (no chain enters it: kmer_hash.cpp never visits it) never settles and is cut off after 14 rounds.
+    for (int round = 0; round < 14; ++round) {
+        bool changed = false;
+    #pragma unroll 1
+    for (u32 node = threadIdx.x; node < cnt; node += kCtBuildThreads) {
+            const u32 pd = s_pd[node], a = pd >> 16;
+            if (a == node) continue;
+            const u32 pa = s_pd[a], a2 = pa >> 16;
+            if (a2 == a) continue;
+            s_pd[node] = (a2 << 16) | ((pd + pa) & 0xFFFFu);
+            changed = true;
+        }
+        if (!__syncthreads_or(changed)) break;
+    }
     __syncthreads();
     const u32 seg0 = s_seg0;
     const u32 my_bits = (u32)g.rank << kRankShift;
     const u64 pool0 = pool_off[c];
-    // ---- 4. one lane per head: walk its chain through shared memory, write the contracted segment ----
+    // ---- 5. the last k-mer of every segment writes the segment: link, meta, pending key; reserves its characters ----
     if (seg0 < caps.seg_cap) {
-        for (u32 h = threadIdx.x; h < nheads; h += blockDim.x) {
-            const u32 i0 = s_heads[h];
-            u32 j = i0, last = i0, n = 0, next_hi = kLinkTail;
-            for (u32 guard = 0; guard <= cnt; ++guard) {
-                const V cur = s_tab[j];
-                if (S::fwd(cur) == kExtF) { next_hi = kLinkTail; break; }
-                ++n; last = j;
-                const u32 s = s_succ[j];
-                if (s == kSuccExt) { next_hi = kLinkPending; break; }
-                const u32 sidx = CS::idx(s_tab[s]);
-                if (sidx) { next_hi = my_bits | (seg0 + sidx - 1u); break; }      // the successor starts its own segment
-                j = s;
+    #pragma unroll 1
+    for (u32 node = threadIdx.x; node < cnt; node += kCtBuildThreads) {
+            const u32 s = s_succ[node];
+            if (s == kSuccDead) continue;
+            const u32 pd = s_pd[node], a = pd >> 16;
+            const bool root = a == node;
+            const u32 pa = root ? pd : s_pd[a];
+            if ((pa >> 16) != a) continue;                                   // on a headless cycle
+            const u32 f = s_code[node] & 7u;
+            bool last = f == kExtF || s >= kSuccExt;
+            u32 next_hi = f == kExtF ? kLinkTail : kLinkPending;
+            if (!last) {
+                const u32 ps = s_pd[s];
+                if ((ps >> 16) == s) { last = true; next_hi = my_bits | (seg0 + (ps & 0xFFFFu)); }      // the successor starts its own segment
             }
+            if (!last) continue;
+            const u32 n = (root ? 0u : (pd & 0xFFFFu)) + (f != kExtF ? 1u : 0u);      // extract_contig (read_kmers.hpp:86-90): no character for 'F'
             const u32 off = atomicAdd(&s_chars, n);
-            j = i0;
-            for (u32 t = 0; t < n; ++t) {
-                s_pool[off + t] = ext_char(S::fwd(s_tab[j]));                      // extract_contig: read_kmers.hpp:86-90
-                j = s_succ[j];
-            }
-            const u32 gseg = seg0 + h;
+            s_off[a] = (unsigned short)off;
+            const u32 gseg = seg0 + (pa & 0xFFFFu);
             link[gseg] = ((u64)next_hi << 32) | (next_hi == kLinkTail ? 0u : n);
             meta[gseg] = ((pool0 + off) << 24) | n;
-            if (next_hi == kLinkPending) ext_key[gseg] = S::next_key(CS::strip(s_tab[last]), k);
+            if (next_hi == kLinkPending) ext_key[gseg] = S::next_key(CS::strip(s_tab[s & 0x7FFFu]), k);
         }
     }
     __syncthreads();
-    // ---- 5. characters and the finished chunk go to HBM in coalesced sweeps ----
+    // ---- 6. every k-mer drops its forward extension at (segment's characters + distance from the head) ----
+#pragma unroll 1
+    for (u32 node = threadIdx.x; node < cnt; node += kCtBuildThreads) {
+        const u32 code = s_code[node];
+        if ((code & 7u) == kExtF) continue;                                  // also the dead ones
+        const u32 pd = s_pd[node], a = pd >> 16;
+        const bool root = a == node;
+        if (!root && (s_pd[a] >> 16) != a) continue;
+        s_pool[(u32)s_off[a] + (root ? 0u : (pd & 0xFFFFu))] = ext_char(code & 7u);
+    }
+    // ---- 7. index bits: node id -> 1 + segment index for the k-mers that start a segment, 0 for the others ----
     {
-        const u32 nv = (s_chars + 15u) >> 4;
-        const uint4* sp = reinterpret_cast<const uint4*>(s_pool);
-        uint4* gp = reinterpret_cast<uint4*>(pool + pool0);
-        for (u32 i = threadIdx.x; i < nv; i += blockDim.x) gp[i] = sp[i];
-        const uint4* s4 = reinterpret_cast<const uint4*>(s_raw);
-        uint4* g4 = reinterpret_cast<uint4*>(table + (u64)b0 * S::kPerBucket);
-        for (u32 i = threadIdx.x; i < nb * 2u; i += blockDim.x) g4[i] = s4[i];
+        const u32 nslots = nb * S::kPerBucket;
+        for (u32 i = threadIdx.x; i < nslots; i += kCtBuildThreads) {
+            const V cur = s_tab[i];
+            if (S::empty(cur)) continue;
+            const u32 node = CS::idx(cur) - 1u, pd = s_pd[node];
+            s_tab[i] = CS::with_idx(cur, (pd >> 16) == node ? (pd & 0xFFFFu) + 1u : 0u);
+        }
+    }
+    // ---- 8. characters and the finished chunk go to HBM: bulk copies shared -> global (TMA engine), 8 KB pieces ----
+    asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+    __syncthreads();
+    {
+        const u32 tab_bytes = nb * 32u, pool_bytes = (s_chars + 15u) & ~15u;
+        constexpr u32 kPiece = 8192u;
+        const u32 tab_pieces = (tab_bytes + kPiece - 1u) / kPiece, pool_pieces = (pool_bytes + kPiece - 1u) / kPiece;
+        if (lane_id() == 0) {
+            unsigned char* g_tab = reinterpret_cast<unsigned char*>(table + (u64)b0 * S::kPerBucket);
+            bool any = false;
+            for (u32 pc = threadIdx.x >> 5; pc < tab_pieces + pool_pieces; pc += kCtBuildThreads / 32) {
+                const bool is_tab = pc < tab_pieces;
+                const u32 o = (is_tab ? pc : pc - tab_pieces) * kPiece;
+                const u32 bytes = min(kPiece, (is_tab ? tab_bytes : pool_bytes) - o);
+                const unsigned src = (unsigned)__cvta_generic_to_shared(is_tab ? s_raw + o : s_pool + o);
+                unsigned char* dst = is_tab ? g_tab + o : pool + pool0 + o;
+                asm volatile("cp.async.bulk.global.shared::cta.bulk_group [%0], [%1], %2;" ::"l"(dst), "r"(src), "r"(bytes) : "memory");
+                any = true;
+            }
+            if (any) {
+                asm volatile("cp.async.bulk.commit_group;" ::: "memory");
+                asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory");
+            }
+        }
     }
     if (threadIdx.x == 0) {
         if (s_inserted) atomicAdd(&ctr->n_inserted, (u64)s_inserted);

@@ -42,6 +42,20 @@ __device__ __forceinline__ void stage_in(unsigned char* s_dst, const unsigned ch
         for (u32 i = threadIdx.x; i < bytes; i += blockDim.x) s_dst[i] = g_src[i];
     }
 }
+// same with the block size known at compile time (a run-time stride costs a division per loop for the trip count)
+template <int THREADS>
+__device__ __forceinline__ void stage_in_fixed(unsigned char* s_dst, const unsigned char* g_src, u32 bytes) {
+    if ((reinterpret_cast<uintptr_t>(g_src) & 15u) == 0) {
+        const u32 nv = bytes >> 4;
+        const uint4* s4 = reinterpret_cast<const uint4*>(g_src);
+        uint4* d4 = reinterpret_cast<uint4*>(s_dst);
+#pragma unroll 4
+        for (u32 i = threadIdx.x; i < nv; i += THREADS) d4[i] = load128_stream(s4 + i);
+        for (u32 i = (nv << 4) + threadIdx.x; i < bytes; i += THREADS) s_dst[i] = g_src[i];
+    } else {
+        for (u32 i = threadIdx.x; i < bytes; i += THREADS) s_dst[i] = g_src[i];
+    }
+}
 __device__ __forceinline__ void stage_out(unsigned char* g_dst, const unsigned char* s_src, u32 bytes) {
     if ((reinterpret_cast<uintptr_t>(g_dst) & 15u) == 0) {
         const u32 nv = bytes >> 4;

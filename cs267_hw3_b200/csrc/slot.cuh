@@ -402,8 +402,8 @@ __host__ __device__ __forceinline__ u64 place_bucket(typename Slot<W>::value_t v
 // the `win` RIGHTMOST m-mers of the k-mer (win <= 32); that value is a bijection of the m-mer, so the minimum
 // itself identifies the minimizer and is what gets hashed.
 constexpr u32 kIdxBits = 14;                     // top bits of a ctable slot: 1 + index of the segment that STARTS at this k-mer (0: none)
-constexpr u32 kMinSeed = 0x5BD1E995u;
-constexpr u32 kMinMul = 0x9E3779B1u;
+constexpr u32 kMinMul = 0x9E3779B1u;             // odd: x -> x * kMinMul is a bijection of the m-mers
+constexpr u32 kMinAdd = 0x7F4A7C15u;             // moves poly-A (x = 0) away from the bottom of the order
 
 __host__ __device__ __forceinline__ int ct_minimizer_len(int k) { return k >= 31 ? 15 : (k >= 23 ? 13 : (k >= 17 ? k - 6 : k)); }
 __host__ __device__ __forceinline__ int ct_window(int k) { const int w = k - ct_minimizer_len(k) + 1; return w > 32 ? 32 : w; }
@@ -418,18 +418,35 @@ __host__ __device__ __forceinline__ u32 ct_funnel_r(u32 lo, u32 hi, u32 s) {    
     return s ? ((lo >> s) | (hi << (32 - s))) : lo;
 #endif
 }
+__host__ __device__ __forceinline__ u32 ct_mulhi32(u32 a, u32 b) {
+#ifdef __CUDA_ARCH__
+    return __umulhi(a, b);
+#else
+    return (u32)(((u64)a * b) >> 32);
+#endif
+}
+// Order value of the m-mer in the low 2m bits of a 16-base window w: (w mod 4^m) * odd, moved to the top of the word
+// -- the shift drops the bases of the window that are not part of the m-mer, so no mask is needed.  Three
+// instructions per window position on the GPU (funnel shift, multiply-add, minimum).
 // key words: a = bits 0..31 of the key (the LAST bases), b, c, d the following 32-bit words
 __host__ __device__ __forceinline__ u32 ct_min_hash_words(u32 a, u32 b, u32 c, u32 d, int m, int win) {
-    const u32 mmask = (m >= 16) ? 0xFFFFFFFFu : ((1u << (2 * m)) - 1u);
+    const u32 mul = kMinMul << (32 - 2 * m);          // m <= 16
     u32 best = 0xFFFFFFFFu;
     int rem = win;
     for (int it = 0; it < 2; ++it) {
+        if (rem >= 16) {
 #pragma unroll
-        for (int j = 0; j < 16; ++j) {
-            const u32 x = ct_funnel_r(a, b, 2u * j) & mmask;
-            u32 h = (x ^ kMinSeed) * kMinMul;
-            h = (j < rem) ? h : 0xFFFFFFFFu;
-            best = h < best ? h : best;
+            for (int j = 0; j < 16; ++j) {
+                const u32 h = ct_funnel_r(a, b, 2u * j) * mul + kMinAdd;
+                best = h < best ? h : best;
+            }
+        } else {
+#pragma unroll
+            for (int j = 0; j < 16; ++j) {
+                u32 h = ct_funnel_r(a, b, 2u * j) * mul + kMinAdd;
+                h = (j < rem) ? h : 0xFFFFFFFFu;
+                best = h < best ? h : best;
+            }
         }
         if (rem <= 16) break;
         rem -= 16; a = b; b = c; c = d; d = 0;
@@ -447,6 +464,11 @@ template <> __host__ __device__ __forceinline__ u32 ct_min_hash<2>(u128 v, int m
 }
 
 // slot helpers that know about the index bits
+__host__ __device__ __forceinline__ u32 ct_fmix32_hi(u32 h) {       // finaliser whose HIGH bits are used (range reduction by mulhi)
+    h ^= h >> 15; h *= 0x85EBCA6Bu;
+    h ^= h >> 13; h *= 0xC2B2AE35u;
+    return h;
+}
 template <int W> struct CtSlot;
 template <> struct CtSlot<1> {
     typedef u64 V;
@@ -454,7 +476,11 @@ template <> struct CtSlot<1> {
     static __host__ __device__ __forceinline__ u32 idx(V v) { return (u32)(v >> (64 - kIdxBits)); }
     static __host__ __device__ __forceinline__ V with_idx(V v, u32 i) { return strip(v) | ((u64)i << (64 - kIdxBits)); }
     static __host__ __device__ __forceinline__ bool same_key(V a, V b) { return (((a ^ b) << kIdxBits) >> (kIdxBits + 6)) == 0ull; }
-    static __host__ __device__ __forceinline__ u32 hash32(V key) { return (u32)(fmix64(key >> 6) >> 32); }      // key: stripped
+    // bucket hash of the key bits of a slot value (extension and index bits ignored): 32-bit multiplies only
+    static __host__ __device__ __forceinline__ u32 hash32(V v) {
+        const u32 x0 = (u32)v & ~63u, x1 = (u32)(v >> 32) & (0xFFFFFFFFu >> kIdxBits);
+        return ct_fmix32_hi((x0 * 0x9E3779B1u) ^ x1);
+    }
 };
 template <> struct CtSlot<2> {
     typedef u128 V;
@@ -462,34 +488,31 @@ template <> struct CtSlot<2> {
     static __host__ __device__ __forceinline__ u32 idx(V v) { return (u32)(v.hi >> (64 - kIdxBits)); }
     static __host__ __device__ __forceinline__ V with_idx(V v, u32 i) { return u128{v.lo, (v.hi & (~0ull >> kIdxBits)) | ((u64)i << (64 - kIdxBits))}; }
     static __host__ __device__ __forceinline__ bool same_key(V a, V b) { return (((a.hi ^ b.hi) << kIdxBits) | ((a.lo ^ b.lo) >> 6)) == 0ull; }
-    static __host__ __device__ __forceinline__ u32 hash32(V key) {
-        return (u32)(fmix64((key.lo >> 6) ^ (key.hi * 0x9E3779B97F4A7C15ull) ^ (key.hi >> 29)) >> 32);
+    static __host__ __device__ __forceinline__ u32 hash32(V v) {
+        const u32 x0 = (u32)v.lo & ~63u, x1 = (u32)(v.lo >> 32), x2 = (u32)v.hi, x3 = (u32)(v.hi >> 32) & (0xFFFFFFFFu >> kIdxBits);
+        u32 h = x0 * 0x9E3779B1u;
+        h = (h ^ x1) * 0x85EBCA77u;
+        h = (h ^ x2) * 0xC2B2AE3Du;
+        return ct_fmix32_hi(h ^ x3);
     }
 };
 // bucket inside a chunk of nb buckets
-__host__ __device__ __forceinline__ u32 ct_bucket_in_chunk(u32 h32, u32 nb) { return (u32)(((u64)h32 * nb) >> 32); }
+__host__ __device__ __forceinline__ u32 ct_bucket_in_chunk(u32 h32, u32 nb) { return ct_mulhi32(h32, nb); }
 
 // chunk geometry shared by host and device
 struct CtGeom {
     int k, m, win;
     int world, rank;
-    u32 chunks_per_rank;        // C
-    u32 cpr_shift;              // a region = 2^cpr_shift chunks (the unit of the first grouping pass)
-    u32 regions_per_rank;       // R = ceil(C / 2^cpr_shift);  world * R <= kCtMaxRegions
+    u32 chunks_per_rank;        // C: rank r owns the global chunks [r * C, (r + 1) * C)
     u32 max_buckets;            // buckets a chunk may have (shared-memory budget of the build kernel)
     u32 lf_inv_q16;             // 65536 / load factor
 };
-constexpr u32 kCtMaxRegions = 1024;
-// minimizer hash -> (owner rank, local chunk) without a division: h * world = owner . fraction, fraction * C = chunk
+// minimizer hash -> (owner rank, local chunk) without a division: u * world = owner . fraction, and the global chunk
+// floor(u * world * C / 2^32) lies in the owner's range because floor(floor(x C) / C) = floor(x)
 __host__ __device__ __forceinline__ void ct_place(u32 minhash, const CtGeom& g, u32& owner, u32& chunk) {
-    const u64 h = fmix64((u64)minhash + 0x632BE59BD9B4E019ull);
-#ifdef __CUDA_ARCH__
-    owner = (u32)__umul64hi(h, (u64)g.world);
-    chunk = (u32)__umul64hi(h * (u64)g.world, (u64)g.chunks_per_rank);
-#else
-    owner = (u32)(((unsigned __int128)h * (u64)g.world) >> 64);
-    chunk = (u32)(((unsigned __int128)(h * (u64)g.world) * (u64)g.chunks_per_rank) >> 64);
-#endif
+    const u32 u = ct_fmix32_hi(minhash ^ (minhash >> 16));       // the minimum of a window is biased towards 0: remix before reducing
+    owner = ct_mulhi32(u, (u32)g.world);
+    chunk = ct_mulhi32(u, (u32)g.world * g.chunks_per_rank) - owner * g.chunks_per_rank;
 }
 
 // multi-GPU: global segment id = (rank << kRankShift) | local id

@@ -64,16 +64,24 @@ def ct_window(k: int) -> int:
 
 
 def ct_min_hash(slot: int, k: int) -> int:
-    """Mirror of ct_min_hash<W>() (csrc/slot.cuh): min over the `win` rightmost m-mers of (x ^ seed) * odd mod 2^32."""
+    """Mirror of ct_min_hash<W>() (csrc/slot.cuh): min over the `win` rightmost m-mers x of
+    (x * odd << (32 - 2m)) + c mod 2^32."""
     key, m, win = slot >> 6, ct_minimizer_len(k), ct_window(k)
-    mask = (1 << (2 * m)) - 1
-    return min((((key >> (2 * j)) & mask) ^ 0x5BD1E995) * 0x9E3779B1 & _M32 for j in range(win))
+    mul = (0x9E3779B1 << (32 - 2 * m)) & _M32
+    return min((((key >> (2 * j)) & _M32) * mul + 0x7F4A7C15) & _M32 for j in range(win))
+
+
+def _fmix32_hi(h: int) -> int:
+    h ^= h >> 15
+    h = (h * 0x85EBCA6B) & _M32
+    h ^= h >> 13
+    return (h * 0xC2B2AE35) & _M32
 
 
 def owner_of_slot(slot: int, k: int, world: int) -> int:
     """Mirror of ct_place() (csrc/slot.cuh): the rank that owns a k-mer (tests compare it with where the GPU put it)."""
-    h = _fmix64((ct_min_hash(slot, k) + 0x632BE59BD9B4E019) & _M64)
-    return (h * world) >> 64
+    mh = ct_min_hash(slot, k)
+    return (_fmix32_hi(mh ^ (mh >> 16)) * world) >> 32
 
 
 def slot_bytes(k: int) -> int:
