@@ -80,8 +80,10 @@ struct kh_table {
         u64 n_local_max = 0, n_total = 0, n_starts_max = 0, out_cap = 0;
         u64 n_starts_host = 0;            // non-sharded handles learn it at every insert (they sync anyway)
         DevBuf xin_vals, xin_chunk, xin_cnt, xin_done, xout_cursor, extra_vals, extra_chunk, extra_cnt, fine, chunk_cursor,
-               chunk_base, pool_off, seg_base, ext_key, meta, pool, inbox, inbox_cnt, out_cursor, flags;
-        void* ipc_opened[kMaxRanks][16] = {};
+               chunk_base, pool_off, seg_base, ext_key, meta, pool, inbox, inbox_cnt, out_cursor, flags,
+               answers, req_seg, g_link, g_meta, g_pool, g_hdr;
+        bool slow = false;                // this traverse ranks by pointer jumping (a contig too long for the bounded walk)
+        void* ipc_opened[kMaxRanks][24] = {};
     } ct;
     int ct_env = 1;                   // KH_CT: 0 never, 1 tables of >= 2^20 k-mers (and every sharded handle), 2 always
 };
@@ -473,7 +475,7 @@ int set_option(kh_table* t, const std::string& name, int64_t value) {
 namespace {
 
 enum { CTX_XIN_VALS, CTX_XIN_CHUNK, CTX_XIN_CNT, CTX_EXTRA_VALS, CTX_EXTRA_CHUNK, CTX_EXTRA_CNT, CTX_LINK, CTX_META,
-       CTX_INBOX, CTX_INBOX_CNT, CTX_PRE, CTX_OFF, CTX_OUT, CTX_FLAGS, CTX_NBUF };
+       CTX_INBOX, CTX_INBOX_CNT, CTX_PRE, CTX_OFF, CTX_OUT, CTX_FLAGS, CTX_ANSWERS, CTX_GLINK, CTX_GMETA, CTX_GPOOL, CTX_GHDR, CTX_NBUF };
 
 size_t ct_stage_smem(int W, int world) {       // multi-GPU: the remote values of a tile sorted by owner + their chunk ids
     return world > 1 ? (size_t)kStgTile * ((W == 1 ? 8 : 16) + 4) : 0;
@@ -492,6 +494,9 @@ void ct_set_self(kh_table* t) {
     pe.contig_pre[r] = static_cast<u32*>(t->contig_pre.p); pe.contig_off[r] = static_cast<u64*>(t->contig_off.p);
     pe.out[r] = static_cast<char*>(t->out.p); pe.out_cap[r] = c.out_cap;
     pe.flags[r] = static_cast<u32*>(c.flags.p);
+    pe.answers[r] = static_cast<u32*>(c.answers.p);
+    pe.g_link[r] = static_cast<u64*>(c.g_link.p); pe.g_meta[r] = static_cast<u64*>(c.g_meta.p);
+    pe.g_pool[r] = static_cast<unsigned char*>(c.g_pool.p); pe.g_hdr[r] = static_cast<u32*>(c.g_hdr.p);
 }
 
 // empty staging: cursors of the chunk buffers, of the send side and of the receive side
@@ -568,6 +573,15 @@ int ct_setup(kh_table* t, int rank, int world, u64 n_local_max, u64 n_total, u64
     KH_TRY(ensure(t, c.inbox_cnt, kMaxRanks * sizeof(u32)));
     KH_TRY(ensure(t, c.out_cursor, kMaxRanks * sizeof(u32)));
     KH_TRY(ensure(t, c.flags, 2 * kMaxRanks * sizeof(u32)));
+    // answers to this rank's link requests, and the copies of the other ranks' segment arrays the contig walk reads
+    c.caps.g_seg_stride = world > 1 ? ((n_local_max + 1 + n_exp + 64 + 15) & ~15ull) : 0;
+    c.caps.g_pool_stride = world > 1 ? ((c.caps.pool_cap + 64 + 15) & ~15ull) : 0;
+    KH_TRY(ensure(t, c.answers, std::max<u64>(16, (u64)(world > 1 ? world : 0) * c.caps.inbox_cap * sizeof(u32))));
+    KH_TRY(ensure(t, c.req_seg, std::max<u64>(16, (u64)(world > 1 ? world : 0) * c.caps.inbox_cap * sizeof(u32))));
+    KH_TRY(ensure(t, c.g_link, std::max<u64>(16, (u64)world * c.caps.g_seg_stride * sizeof(u64))));
+    KH_TRY(ensure(t, c.g_meta, std::max<u64>(16, (u64)world * c.caps.g_seg_stride * sizeof(u64))));
+    KH_TRY(ensure(t, c.g_pool, std::max<u64>(16, (u64)world * c.caps.g_pool_stride)));
+    KH_TRY(ensure(t, c.g_hdr, 2 * kMaxRanks * sizeof(u32)));
     if (sharded) {
         KH_TRY(ensure(t, t->link, seg_cap * sizeof(u64)));
         KH_TRY(ensure(t, c.meta, seg_cap * sizeof(u64)));
@@ -657,8 +671,11 @@ __global__ void ct_init_assemble_kernel(Counters* c) {
     c->contig_bytes = 0;
     c->rank_rounds = 0;
     c->rank_done = 0;
+    c->need_jump = 0;
+    c->use_jump = 0;
     for (int i = 0; i < 40; ++i) c->flags[i] = 0;
 }
+__global__ void ct_reset_nodes_kernel(Counters* c) { c->n_nodes = 0; }
 
 // seal, part 0: tell the owners how much they received (then a barrier); part 1: file it, lay out, build + contract
 template <int W>
@@ -717,14 +734,18 @@ int ct_seal_build(kh_table* t) {
 
 // The traverse, in parts that each end with a barrier across the ranks (kh_shard_assemble runs them all; a host that
 // emulates several ranks on ONE device enqueues part p for every rank before part p + 1, see kh_capi.h):
-//   0  publish staging fill | barrier
+//   0  tell the owners what they received | barrier
 //   1  seal (if not sealed) + head stubs + resolve the pending links (local lookups; requests to the owners) | barrier
-//   2  answer the requests that arrived (peer store into the sender's link) | barrier
-//   3 .. 3+R-1  one pointer-jumping round each | barrier that also agrees on "nobody moved" (then the rest return at once)
-//   3+R  contig lengths, claims, offsets | barrier
-//   4+R  emit | barrier
+//   2  answer the requests that arrived (one coalesced run of answers per requester) | barrier
+//   3  file the answers; send segment links / meta / characters to every other rank | barrier
+//   4  contig lengths by walking each contig's segments (bounded) | barrier that agrees on "some contig is too long"
+//   5  [the host reads that one flag]  fast path: offsets, second walk that copies the characters | barrier -- done
+//   6 .. 6+R-1  (slow path only) one pointer-jumping round each | barrier that also agrees on "nobody moved"
+//   6+R  (slow path only) contig lengths, claims, offsets | barrier
+//   7+R  (slow path only) emit | barrier
 constexpr int kCtMaxRounds = 24;            // chains of up to 2^24 segments
-constexpr int kCtParts = 5 + kCtMaxRounds;
+constexpr int kCtParts = 8 + kCtMaxRounds;
+constexpr u32 kCtWalkMaxSteps = 512;        // segments a lane follows before the step falls back to pointer jumping
 
 template <int W>
 int ct_assemble_part(kh_table* t, int part) {
@@ -732,9 +753,17 @@ int ct_assemble_part(kh_table* t, int part) {
     auto& c = t->ct;
     const unsigned gb = (unsigned)t->sm_count * 8;
     u64* link = static_cast<u64*>(t->link.p);
+    CtGathered gt = {};
+    for (int r = 0; r < c.pe.world; ++r) {
+        const bool me = r == c.pe.rank;
+        gt.link[r] = me ? link : static_cast<const u64*>(c.g_link.p) + (u64)r * c.caps.g_seg_stride;
+        gt.meta[r] = me ? static_cast<const u64*>(c.meta.p) : static_cast<const u64*>(c.g_meta.p) + (u64)r * c.caps.g_seg_stride;
+        gt.pool[r] = me ? static_cast<const unsigned char*>(c.pool.p) : static_cast<const unsigned char*>(c.g_pool.p) + (u64)r * c.caps.g_pool_stride;
+    }
     switch (part) {
     case 0:
-        if (c.assembled) { c.sealed = false; c.assembled = false; }      // claims and jumped links of the last traverse: rebuild
+        if (c.assembled) { c.sealed = false; c.assembled = false; }      // claims and jumped links of a slow traverse: rebuild
+        c.slow = false;
         KH_CUDA(t, cudaEventRecord(t->ev[EV_AS0], t->stream));
         if (!c.sealed) return ct_seal_publish<W>(t);
         return ct_barrier(t);
@@ -748,14 +777,13 @@ int ct_assemble_part(kh_table* t, int part) {
             c.out_cap = t->h_ctr->n_inserted + c.n_starts_host * (u64)(t->k + 1) + 64;       // n_inserted: refreshed by the seal's sync below
             ct_set_self(t);
         }
-        c.assembled = true;
         ct_init_assemble_kernel<<<1, 1, 0, t->stream>>>(t->d_ctr);
         KH_CUDA(t, cudaMemsetAsync(c.out_cursor.p, 0, kMaxRanks * sizeof(u32), t->stream));
         ct_stub_kernel<W><<<std::max(1u, std::min(gb, (c.caps.hcap + 255u) / 256u)), 256, 0, t->stream>>>(
             static_cast<const V*>(t->starts.p), t->d_ctr, c.caps.hcap, link, static_cast<u64*>(c.meta.p), static_cast<V*>(c.ext_key.p));
         ct_resolve_kernel<W><<<gb, 256, 0, t->stream>>>(static_cast<const V*>(t->table), static_cast<const u32*>(c.chunk_base.p),
                                                         static_cast<const u32*>(c.seg_base.p), link, static_cast<const V*>(c.ext_key.p),
-                                                        c.g, c.pe, c.caps, static_cast<u32*>(c.out_cursor.p), t->d_ctr);
+                                                        c.g, c.pe, c.caps, static_cast<u32*>(c.out_cursor.p), static_cast<u32*>(c.req_seg.p), t->d_ctr);
         if (c.pe.world > 1) { ct_publish_inbox_kernel<<<1, 32, 0, t->stream>>>(c.pe, c.caps, static_cast<const u32*>(c.out_cursor.p)); ++t->n_launches; }
         t->n_launches += 3;
         KH_CUDA(t, cudaGetLastError());
@@ -769,19 +797,53 @@ int ct_assemble_part(kh_table* t, int part) {
             KH_CUDA(t, cudaGetLastError());
             ++t->n_launches;
         }
+        return ct_barrier(t);
+    case 3:
+        if (c.pe.world > 1) {
+            ct_apply_kernel<<<gb, 256, 0, t->stream>>>(link, static_cast<const u32*>(c.answers.p), static_cast<const u32*>(c.req_seg.p),
+                                                       static_cast<const u32*>(c.out_cursor.p), c.caps, c.pe.world, c.pe.rank);
+            ct_gather_kernel<<<gb, 256, 0, t->stream>>>(c.pe, c.caps, link, static_cast<const u64*>(c.meta.p), static_cast<const unsigned char*>(c.pool.p),
+                                                        static_cast<const u32*>(c.pool_off.p), c.g.chunks_per_rank, t->d_ctr);
+            KH_CUDA(t, cudaGetLastError());
+            t->n_launches += 2;
+        }
         KH_CUDA(t, cudaEventRecord(t->ev[EV_WALK], t->stream));
         return ct_barrier(t);
-    case 3 + kCtMaxRounds: {
+    case 4:
+        ct_walk_len_kernel<<<gb, 256, 0, t->stream>>>(gt, link, c.caps, t->k, kCtWalkMaxSteps, static_cast<u32*>(t->contig_len.p), t->d_ctr);
+        KH_CUDA(t, cudaGetLastError());
+        ++t->n_launches;
+        return ct_barrier(t, -2);
+    case 5: {
+        KH_TRY(read_counters(t));                    // the step's one mid-way host wait: which way do all ranks go?
+        c.slow = (c.pe.world > 1 ? t->h_ctr->use_jump : t->h_ctr->need_jump) != 0;
+        if (c.slow) { c.assembled = true; return KH_OK; }
+        KH_TRY(device_scan(t, static_cast<u32*>(t->contig_len.p), (u64)c.caps.hcap + 1, static_cast<u64*>(t->contig_off.p), &t->d_ctr->contig_bytes));
+        KH_CUDA(t, cudaEventRecord(t->ev[EV_RANK], t->stream));
+        ct_emit_heads_kernel<W><<<gb, 256, 0, t->stream>>>(static_cast<const V*>(t->starts.p), c.caps, t->k, static_cast<const u32*>(t->contig_len.p),
+                                                          static_cast<const u64*>(t->contig_off.p), t->d_ctr, c.out_cap, static_cast<char*>(t->out.p));
+        ct_walk_emit_kernel<<<gb, 256, 0, t->stream>>>(gt, link, c.caps, t->k, static_cast<const u32*>(t->contig_len.p),
+                                                       static_cast<const u64*>(t->contig_off.p), c.out_cap, static_cast<char*>(t->out.p), t->d_ctr);
+        KH_CUDA(t, cudaGetLastError());
+        t->n_launches += 2;
+        KH_CUDA(t, cudaEventRecord(t->ev[EV_AS1], t->stream));
+        t->have_as = true;
+        return ct_barrier(t);
+    }
+    case 6 + kCtMaxRounds: {
+        if (!c.slow) return KH_OK;
+        ct_reset_nodes_kernel<<<1, 1, 0, t->stream>>>(t->d_ctr);
         ct_lengths_kernel<<<gb, 256, 0, t->stream>>>(c.pe, link, c.caps, t->k, static_cast<u32*>(t->contig_len.p),
                                                      static_cast<u32*>(t->contig_pre.p), t->d_ctr);
         ct_claim_kernel<<<gb, 256, 0, t->stream>>>(c.pe, link, c.caps, static_cast<const u32*>(t->contig_len.p), t->d_ctr);
         KH_CUDA(t, cudaGetLastError());
-        t->n_launches += 2;
+        t->n_launches += 3;
         KH_TRY(device_scan(t, static_cast<u32*>(t->contig_len.p), (u64)c.caps.hcap + 1, static_cast<u64*>(t->contig_off.p), &t->d_ctr->contig_bytes));
         KH_CUDA(t, cudaEventRecord(t->ev[EV_RANK], t->stream));
         return ct_barrier(t);
     }
-    case 4 + kCtMaxRounds:
+    case 7 + kCtMaxRounds:
+        if (!c.slow) return KH_OK;
         ct_emit_kernel<<<gb, 256, 0, t->stream>>>(c.pe, link, static_cast<const u64*>(c.meta.p), static_cast<const unsigned char*>(c.pool.p),
                                                   c.caps, t->d_ctr, t->k);
         ct_emit_heads_kernel<W><<<gb, 256, 0, t->stream>>>(static_cast<const V*>(t->starts.p), c.caps, t->k, static_cast<const u32*>(t->contig_len.p),
@@ -792,8 +854,9 @@ int ct_assemble_part(kh_table* t, int part) {
         t->have_as = true;
         return ct_barrier(t);
     default: {
-        if (part < 3 || part >= 3 + kCtMaxRounds) return fail(t, KH_ERR_ARG, "unknown assemble part");
-        const int r = part - 3;
+        if (part < 6 || part >= 6 + kCtMaxRounds) return fail(t, KH_ERR_ARG, "unknown assemble part");
+        if (!c.slow) return KH_OK;
+        const int r = part - 6;
         ct_rank_round_kernel<<<gb, 256, 0, t->stream>>>(c.pe, link, c.caps, t->d_ctr, t->d_ctr->flags, r);
         KH_CUDA(t, cudaGetLastError());
         ++t->n_launches;
@@ -994,7 +1057,7 @@ int kh_destroy(kh_table* t) {
         auto& c = t->ct;
         for (DevBuf* b : {&c.xin_vals, &c.xin_chunk, &c.xin_cnt, &c.xin_done, &c.xout_cursor, &c.extra_vals, &c.extra_chunk, &c.extra_cnt, &c.fine,
                           &c.chunk_cursor, &c.chunk_base, &c.pool_off, &c.seg_base, &c.ext_key, &c.meta, &c.pool, &c.inbox, &c.inbox_cnt,
-                          &c.out_cursor, &c.flags})
+                          &c.out_cursor, &c.flags, &c.answers, &c.req_seg, &c.g_link, &c.g_meta, &c.g_pool, &c.g_hdr})
             if (b->p) cudaFree(b->p);
     }
     if (t->table) cudaFree(t->table);
@@ -1328,6 +1391,7 @@ static uint64_t ct_geometry_signature(kh_table* t) {
     const auto& c = t->ct;
     u64 h = fmix64((u64)c.g.chunks_per_rank + 0x9E3779B97F4A7C15ull);
     h = fmix64(h ^ c.caps.xin_cap); h = fmix64(h ^ c.caps.extra_cap); h = fmix64(h ^ c.caps.inbox_cap);
+    h = fmix64(h ^ c.caps.g_seg_stride); h = fmix64(h ^ c.caps.g_pool_stride);
     return fmix64(h ^ (u64)c.pe.world);
 }
 
@@ -1337,6 +1401,7 @@ static void ct_export_list(kh_table* t, void* (&bufs)[CTX_NBUF]) {
     bufs[CTX_EXTRA_VALS] = c.extra_vals.p; bufs[CTX_EXTRA_CHUNK] = c.extra_chunk.p; bufs[CTX_EXTRA_CNT] = c.extra_cnt.p;
     bufs[CTX_LINK] = t->link.p; bufs[CTX_META] = c.meta.p; bufs[CTX_INBOX] = c.inbox.p; bufs[CTX_INBOX_CNT] = c.inbox_cnt.p;
     bufs[CTX_PRE] = t->contig_pre.p; bufs[CTX_OFF] = t->contig_off.p; bufs[CTX_OUT] = t->out.p; bufs[CTX_FLAGS] = c.flags.p;
+    bufs[CTX_ANSWERS] = c.answers.p; bufs[CTX_GLINK] = c.g_link.p; bufs[CTX_GMETA] = c.g_meta.p; bufs[CTX_GPOOL] = c.g_pool.p; bufs[CTX_GHDR] = c.g_hdr.p;
 }
 static void ct_import_list(kh_table* t, int r, void* const (&p)[CTX_NBUF], u64 out_cap) {
     CtPeers& pe = t->ct.pe;
@@ -1349,6 +1414,9 @@ static void ct_import_list(kh_table* t, int r, void* const (&p)[CTX_NBUF], u64 o
     pe.contig_pre[r] = static_cast<u32*>(p[CTX_PRE]); pe.contig_off[r] = static_cast<u64*>(p[CTX_OFF]);
     pe.out[r] = static_cast<char*>(p[CTX_OUT]); pe.out_cap[r] = out_cap;
     pe.flags[r] = static_cast<u32*>(p[CTX_FLAGS]);
+    pe.answers[r] = static_cast<u32*>(p[CTX_ANSWERS]);
+    pe.g_link[r] = static_cast<u64*>(p[CTX_GLINK]); pe.g_meta[r] = static_cast<u64*>(p[CTX_GMETA]);
+    pe.g_pool[r] = static_cast<unsigned char*>(p[CTX_GPOOL]); pe.g_hdr[r] = static_cast<u32*>(p[CTX_GHDR]);
 }
 
 int kh_shard_export(kh_table* t, void* handles_out, uint64_t* meta_out) {

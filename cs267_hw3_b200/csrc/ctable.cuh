@@ -73,6 +73,11 @@ struct CtPeers {
     u64* meta[kMaxRanks];
     void* inbox[kMaxRanks];               // [world][inbox_cap] link requests, by source rank
     u32* inbox_cnt[kMaxRanks];
+    u32* answers[kMaxRanks];              // [world][inbox_cap] on the REQUESTER: answers[o * inbox_cap + i] = owner o's answer to its request i
+    u64* g_link[kMaxRanks];               // [world][seg_cap]: every rank's copy of every other rank's segment links ...
+    u64* g_meta[kMaxRanks];               //   ... and segment meta words (gather before the contig walk)
+    unsigned char* g_pool[kMaxRanks];     // [world][pool_stride]: ... and contig characters
+    u32* g_hdr[kMaxRanks];                // [world][2]: segments / pool bytes each rank has sent
     u32* contig_pre[kMaxRanks];
     u64* contig_off[kMaxRanks];
     char* out[kMaxRanks];
@@ -83,6 +88,7 @@ struct CtPeers {
 struct CtCaps {
     u32 xin_cap, extra_cap, inbox_cap, seg_cap, hcap;
     u64 nbuckets_alloc, pool_cap;
+    u64 g_seg_stride, g_pool_stride;      // per-rank strides of the gathered copies (the same on every rank)
 };
 
 __device__ __forceinline__ void ct_internal(Counters* ctr, u32 site) {
@@ -101,7 +107,7 @@ __device__ __forceinline__ void ct_internal(Counters* ctr, u32 site) {
 __global__ void ct_barrier_kernel(const CtPeers pe, u32 epoch, Counters* ctr, int round) {
     const int r = (int)threadIdx.x;
     if (round >= 0 && ctr->rank_done) return;                    // agreed on by all ranks: nobody waits here any more
-    const u32 bit = round >= 0 ? (ctr->flags[round] ? 1u : 0u) : 0u;
+    const u32 bit = round >= 0 ? (ctr->flags[round] ? 1u : 0u) : (round == -2 ? (ctr->need_jump ? 1u : 0u) : 0u);
     u32 peer_bit = 0;
     if (r < pe.world) {
         __threadfence_system();
@@ -123,6 +129,9 @@ __global__ void ct_barrier_kernel(const CtPeers pe, u32 epoch, Counters* ctr, in
     if (round >= 0) {
         const u32 any = __ballot_sync(kFullMask, peer_bit != 0);
         if (r == 0 && any == 0) ctr->rank_done = 1;
+    } else if (round == -2) {                                    // some rank has a contig too long for the bounded walk: all take the slow path
+        const u32 any = __ballot_sync(kFullMask, peer_bit != 0);
+        if (r == 0) ctr->use_jump = any ? 1u : 0u;
     }
 }
 
@@ -819,7 +828,7 @@ template <int W>
 __global__ void __launch_bounds__(256)
 ct_resolve_kernel(const typename Slot<W>::value_t* __restrict__ table, const u32* __restrict__ chunk_base,
                   const u32* __restrict__ seg_base, u64* __restrict__ link, const typename Slot<W>::value_t* __restrict__ ext_key,
-                  const CtGeom g, const CtPeers pe, const CtCaps caps, u32* __restrict__ out_cursor, Counters* ctr) {
+                  const CtGeom g, const CtPeers pe, const CtCaps caps, u32* __restrict__ out_cursor, u32* __restrict__ req_seg, Counters* ctr) {
     typedef Slot<W> S;
     typedef typename S::value_t V;
     __shared__ u32 s_cnt[kMaxRanks], s_base[kMaxRanks];
@@ -860,8 +869,12 @@ ct_resolve_kernel(const typename Slot<W>::value_t* __restrict__ table, const u32
         for (int r = 0; r < kResPerThread; ++r) {
             if (dest[r] == 0xFFFFFFFFu) continue;
             const u32 at = s_base[dest[r]] + rk[r];
-            if (at < caps.inbox_cap) static_cast<CtReq<W>*>(pe.inbox[dest[r]])[(u64)g.rank * caps.inbox_cap + at] = e[r];
-            else ct_internal(ctr, kSiteInbox);
+            if (at < caps.inbox_cap) {
+                static_cast<CtReq<W>*>(pe.inbox[dest[r]])[(u64)g.rank * caps.inbox_cap + at] = e[r];
+                req_seg[(u64)dest[r] * caps.inbox_cap + at] = e[r].src & kLocalMask;
+            } else {
+                ct_internal(ctr, kSiteInbox);
+            }
         }
         __syncthreads();
     }
@@ -872,7 +885,8 @@ __global__ void ct_publish_inbox_kernel(const CtPeers pe, const CtCaps caps, con
     if (d < pe.world) pe.inbox_cnt[d][pe.rank] = min(out_cursor[d], caps.inbox_cap);
 }
 
-// the owner answers: local lookup, then one peer store into the high word of the sender's link
+// the owner answers: local lookup, then the answer goes into the requester's answer array at the request's index --
+// consecutive threads, consecutive addresses: NVLink sees long runs instead of one 4-byte store per link
 template <int W>
 __global__ void __launch_bounds__(256)
 ct_answer_kernel(const typename Slot<W>::value_t* __restrict__ table, const u32* __restrict__ chunk_base,
@@ -885,8 +899,137 @@ ct_answer_kernel(const typename Slot<W>::value_t* __restrict__ table, const u32*
         const CtReq<W>* __restrict__ box = inbox + (u64)src * caps.inbox_cap;
         for (u32 i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) {
             const CtReq<W> e = box[i];
-            const u32 hi = ct_resolve_one<W>(table, chunk_base, seg_base, e.chunk, e.key, my_bits);
-            reinterpret_cast<u32*>(pe.link[e.src >> kRankShift] + (e.src & kLocalMask))[1] = hi;
+            pe.answers[src][(u64)g.rank * caps.inbox_cap + i] = ct_resolve_one<W>(table, chunk_base, seg_base, e.chunk, e.key, my_bits);
+        }
+    }
+}
+
+// the requester files the answers: link[segment of request i to owner o].high = answers[o][i]
+__global__ void __launch_bounds__(256)
+ct_apply_kernel(u64* __restrict__ link, const u32* __restrict__ answers, const u32* __restrict__ req_seg, const u32* __restrict__ out_cursor,
+                const CtCaps caps, int world, int rank) {
+    for (int o = 0; o < world; ++o) {
+        if (o == rank) continue;
+        const u32 n = min(out_cursor[o], caps.inbox_cap);
+        const u64 base = (u64)o * caps.inbox_cap;
+        for (u32 i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x)
+            reinterpret_cast<u32*>(link + req_seg[base + i])[1] = answers[base + i];
+    }
+}
+
+// ---- gather: every rank sends its segment links, meta words and characters to every other rank -----------------------
+// After this the contig walk reads local memory only.  What crosses NVLink is one long coalesced stream per peer
+// (16 bytes per segment + one byte per k-mer); fine-grained peer reads and writes ran at a few G/s.
+__global__ void __launch_bounds__(256)
+ct_gather_kernel(const CtPeers pe, const CtCaps caps, const u64* __restrict__ link, const u64* __restrict__ meta,
+                 const unsigned char* __restrict__ pool, const u32* __restrict__ pool_off, u32 nchunks, const Counters* __restrict__ ctr) {
+    const u32 nseg = min(ctr->next_seg, caps.seg_cap);
+    const u32 first = caps.hcap;                                   // head stubs are only ever read by their own rank
+    const u32 cnt = nseg > first ? nseg - first : 0u;
+    const u64 pool_vecs = ((u64)pool_off[nchunks] + 15u) >> 4;
+    const u64 tid = (u64)blockIdx.x * blockDim.x + threadIdx.x, stride = (u64)gridDim.x * blockDim.x;
+    for (int d = 1; d < pe.world; ++d) {
+        const int p = (pe.rank + d) % pe.world;                    // every rank starts with a different peer
+        u64* gl = pe.g_link[p] + (u64)pe.rank * caps.g_seg_stride;
+        u64* gm = pe.g_meta[p] + (u64)pe.rank * caps.g_seg_stride;
+        uint4* gp = reinterpret_cast<uint4*>(pe.g_pool[p] + (u64)pe.rank * caps.g_pool_stride);
+        for (u64 i = tid; i < cnt; i += stride) { gl[first + i] = link[first + i]; gm[first + i] = meta[first + i]; }
+        const uint4* sp = reinterpret_cast<const uint4*>(pool);
+        for (u64 i = tid; i < pool_vecs; i += stride) gp[i] = sp[i];
+        if (tid == 0) { pe.g_hdr[p][2 * pe.rank] = nseg; pe.g_hdr[p][2 * pe.rank + 1] = (u32)pool_vecs; }
+    }
+}
+
+// ---- ranking by walking: one lane per contig follows its segments (kmer_hash.cpp:38-55, a segment per step) ----------
+// Contigs are short (~100 k-mers = 4..30 segments), there are hundreds of thousands of them, and every array the walk
+// reads is local (own arrays + gathered copies), so a lane per contig keeps the memory system busy with ONE read per
+// segment.  A contig of more than max_steps segments sets need_jump: the whole step then falls back to pointer jumping.
+struct CtGathered {
+    const u64* link[kMaxRanks];
+    const u64* meta[kMaxRanks];
+    const unsigned char* pool[kMaxRanks];
+};
+
+__global__ void __launch_bounds__(256)
+ct_walk_len_kernel(const CtGathered gt, const u64* __restrict__ link, const CtCaps caps, int k, u32 max_steps,
+                   u32* __restrict__ contig_len, Counters* ctr) {
+    const u32 n_starts = (u32)min(ctr->n_starts_dev, (u64)caps.hcap);
+    u64 nodes = 0;
+    u32 err = 0, too_long = 0;
+    for (u64 c = (u64)blockIdx.x * blockDim.x + threadIdx.x; c <= caps.hcap; c += (u64)gridDim.x * blockDim.x) {
+        if (c >= n_starts) { contig_len[c] = 0; continue; }           // the offsets scan runs over hcap + 1 entries
+        u32 gid = (u32)(__ldg(link + c) >> 32), chars = 0, e = 0, steps = 0;
+        if (gid == kLinkMissing) e = kErrNotFound;                     // the start k-mer itself is not in the table
+        else if (gid == kLinkConverge) e = kErrConverge;
+        else if (gid >= kLinkCtFirstMarker) e = kErrInternal;
+        while (!e) {
+            const u64 l = __ldg(gt.link[gid >> kRankShift] + (gid & kLocalMask));
+            const u32 hi = (u32)(l >> 32);
+            if (hi == kLinkTail) { chars += (u32)(__ldg(gt.meta[gid >> kRankShift] + (gid & kLocalMask)) & 0xFFFFFFu); break; }
+            if (hi == kLinkMissing) { e = kErrNotFound; break; }       // kmer_hash.cpp:47-49
+            if (hi == kLinkConverge) { e = kErrConverge; break; }
+            if (hi >= kLinkCtFirstMarker) { e = kErrInternal; break; }
+            chars += (u32)l;
+            gid = hi;
+            if (++steps > max_steps) { too_long = 1; break; }
+        }
+        if (e || too_long) { err |= e; contig_len[c] = 0; continue; }
+        contig_len[c] = (u32)k + chars + 1u;
+        nodes += (u64)chars + 1u;
+    }
+    nodes = warp_sum_u64(nodes);
+    err = __reduce_or_sync(kFullMask, err);
+    too_long = __reduce_or_sync(kFullMask, too_long);
+    if (lane_id() == 0) {
+        if (nodes) atomicAdd(&ctr->n_nodes, nodes);
+        if (err) atomicOr(&ctr->errors, err);
+        if (err & kErrInternal) atomicOr(&ctr->err_where, kSiteStubOpen);
+        if (too_long) atomicOr(&ctr->need_jump, 1u);
+    }
+}
+
+// copy n bytes (source and destination arbitrarily aligned): destination-aligned 32-bit words built with funnel shifts
+__device__ __forceinline__ void ct_copy_chars(char* dst, const unsigned char* src, u32 n) {
+    while (n && (reinterpret_cast<uintptr_t>(dst) & 3u)) { *dst++ = (char)*src++; --n; }
+    if (n >= 4) {
+        const u32 sh = ((u32)reinterpret_cast<uintptr_t>(src) & 3u) * 8u;
+        const u32* sw = reinterpret_cast<const u32*>(reinterpret_cast<uintptr_t>(src) & ~(uintptr_t)3);
+        u32 w0 = __ldg(sw);
+        u32* dw = reinterpret_cast<u32*>(dst);
+        const u32 nw = n >> 2;
+        for (u32 i = 0; i < nw; ++i) {
+            const u32 w1 = __ldg(sw + i + 1);                      // the pools have 64 bytes of slack behind them
+            dw[i] = __funnelshift_r(w0, w1, sh);
+            w0 = w1;
+        }
+        dst += 4 * nw; src += 4 * nw; n &= 3u;
+    }
+    while (n) { *dst++ = (char)*src++; --n; }
+}
+
+// second walk: the characters of every segment go to their place in the contig (extract_contig, read_kmers.hpp:81-92)
+__global__ void __launch_bounds__(256)
+ct_walk_emit_kernel(const CtGathered gt, const u64* __restrict__ link, const CtCaps caps, int k,
+                    const u32* __restrict__ contig_len, const u64* __restrict__ contig_off, u64 out_cap, char* __restrict__ out,
+                    const Counters* __restrict__ ctr) {
+    if (ctr->use_jump || (ctr->errors & (kErrConverge | kErrCycle | kErrInternal | kErrNotFound)) || ctr->contig_bytes > out_cap) return;
+    const u32 n_starts = (u32)min(ctr->n_starts_dev, (u64)caps.hcap);
+    for (u64 c = (u64)blockIdx.x * blockDim.x + threadIdx.x; c < n_starts; c += (u64)gridDim.x * blockDim.x) {
+        const u32 len = contig_len[c];
+        if (len == 0) continue;
+        char* dst = out + contig_off[c] + (u32)k;
+        char* const end = out + contig_off[c] + len - 1u;
+        u32 gid = (u32)(__ldg(link + c) >> 32);
+        for (;;) {
+            const u32 r = gid >> kRankShift, i = gid & kLocalMask;
+            const u64 l = __ldg(gt.link[r] + i), mt = __ldg(gt.meta[r] + i);
+            const u32 n = (u32)(mt & 0xFFFFFFu);
+            if (dst + n > end) break;                                  // cannot happen after the length walk; never write outside the contig
+            ct_copy_chars(dst, gt.pool[r] + (mt >> 24), n);
+            dst += n;
+            const u32 hi = (u32)(l >> 32);
+            if (hi >= kLinkCtFirstMarker) break;
+            gid = hi;
         }
     }
 }
