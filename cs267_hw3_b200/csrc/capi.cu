@@ -63,6 +63,7 @@ struct kh_table {
     u32 split_shift = 5, seg_chars = 64;     // every 32nd bucket's first slot is a splitter (tools/probes/sweep_walk.sh)
     cudaEvent_t ev[EV_COUNT] = {};
     cudaEvent_t ev_copied[2] = {}, ev_consumed[2] = {};
+    cudaEvent_t ev_built = nullptr, ev_gathered = nullptr;     // chunk table, multi-GPU: the gather of meta words + characters runs beside the link resolution
     bool have_ins = false, have_as = false, have_pack = false, have_clr = false, have_build = false, have_stage = false;
     u64 n_launches = 0;               // kernels launched by this handle since create (kh_get_stats)
     kh_stats stats = {};
@@ -563,7 +564,7 @@ int ct_setup(kh_table* t, int rank, int world, u64 n_local_max, u64 n_total, u64
     KH_TRY(ensure(t, c.extra_vals, (u64)c.caps.extra_cap * sizeof(V)));
     KH_TRY(ensure(t, c.extra_chunk, (u64)c.caps.extra_cap * sizeof(u32)));
     KH_TRY(ensure(t, c.extra_cnt, 16));
-    KH_TRY(ensure(t, c.fine, C * (u64)slots_max * sizeof(V)));
+    KH_TRY(ensure(t, c.fine, C * (u64)((slots_max + 15) & ~15u) * sizeof(V)));      // position-major groups of a 128-byte line (ct_fine_index)
     KH_TRY(ensure(t, c.chunk_cursor, (C + 1) * sizeof(u32)));
     KH_TRY(ensure(t, c.chunk_base, (C + 2) * sizeof(u32)));
     KH_TRY(ensure(t, c.pool_off, (C + 2) * sizeof(u32)));
@@ -710,7 +711,7 @@ int ct_seal_build(kh_table* t) {
             static_cast<const V*>(c.xin_vals.p), static_cast<const u32*>(c.xin_chunk.p), static_cast<const u32*>(c.xin_cnt.p), done,
             c.g, c.caps, static_cast<u32*>(c.chunk_cursor.p), static_cast<V*>(c.fine.p), t->d_ctr);
         ct_extra_kernel<W><<<64, 256, 0, t->stream>>>(static_cast<const V*>(c.extra_vals.p), static_cast<const u32*>(c.extra_chunk.p),
-                                                      static_cast<const u32*>(c.extra_cnt.p), done + kMaxRanks, c.caps,
+                                                      static_cast<const u32*>(c.extra_cnt.p), done + kMaxRanks, c.caps, C,
                                                       static_cast<u32*>(c.chunk_cursor.p), static_cast<V*>(c.fine.p), t->d_ctr);
         ct_mark_filed_kernel<<<1, 32, 0, t->stream>>>(static_cast<const u32*>(c.xin_cnt.p), done, static_cast<const u32*>(c.extra_cnt.p),
                                                       done + kMaxRanks, c.caps, c.pe.world);
@@ -777,6 +778,14 @@ int ct_assemble_part(kh_table* t, int part) {
             c.out_cap = t->h_ctr->n_inserted + c.n_starts_host * (u64)(t->k + 1) + 64;       // n_inserted: refreshed by the seal's sync below
             ct_set_self(t);
         }
+        if (c.pe.world > 1) {             // meta words and characters are final: send them while the links are being resolved
+            KH_CUDA(t, cudaEventRecord(t->ev_built, t->stream));
+            KH_CUDA(t, cudaStreamWaitEvent(t->copy_stream, t->ev_built, 0));
+            ct_gather_kernel<<<gb, 256, 0, t->copy_stream>>>(c.pe, c.caps, link, static_cast<const u64*>(c.meta.p), static_cast<const unsigned char*>(c.pool.p),
+                                                             static_cast<const u32*>(c.pool_off.p), c.g.chunks_per_rank, t->d_ctr, 0);
+            KH_CUDA(t, cudaEventRecord(t->ev_gathered, t->copy_stream));
+            ++t->n_launches;
+        }
         ct_init_assemble_kernel<<<1, 1, 0, t->stream>>>(t->d_ctr);
         KH_CUDA(t, cudaMemsetAsync(c.out_cursor.p, 0, kMaxRanks * sizeof(u32), t->stream));
         ct_stub_kernel<W><<<std::max(1u, std::min(gb, (c.caps.hcap + 255u) / 256u)), 256, 0, t->stream>>>(
@@ -803,7 +812,8 @@ int ct_assemble_part(kh_table* t, int part) {
             ct_apply_kernel<<<gb, 256, 0, t->stream>>>(link, static_cast<const u32*>(c.answers.p), static_cast<const u32*>(c.req_seg.p),
                                                        static_cast<const u32*>(c.out_cursor.p), c.caps, c.pe.world, c.pe.rank);
             ct_gather_kernel<<<gb, 256, 0, t->stream>>>(c.pe, c.caps, link, static_cast<const u64*>(c.meta.p), static_cast<const unsigned char*>(c.pool.p),
-                                                        static_cast<const u32*>(c.pool_off.p), c.g.chunks_per_rank, t->d_ctr);
+                                                        static_cast<const u32*>(c.pool_off.p), c.g.chunks_per_rank, t->d_ctr, 1);
+            KH_CUDA(t, cudaStreamWaitEvent(t->stream, t->ev_gathered, 0));
             KH_CUDA(t, cudaGetLastError());
             t->n_launches += 2;
         }
@@ -981,10 +991,13 @@ int kh_create(int k, uint64_t n_expected, double load_factor, int device, kh_tab
     auto bail = [&](int rc) { kh_destroy(t); return rc; };
     t->k = k; t->device = device; t->lf = load_factor; t->n_expected = n_expected;
     t->pl = (k + 3) / 4; t->pb = t->pl + 2;
-    // Large tables (and every sharded handle, kh_shard_init) are chunk tables (ctable.cuh); small ones, and K outside
-    // 17..54, stay plain open-addressing tables built with global atomics.  KH_CT: 0 never, 1 auto, 2 always.
+    // Every sharded handle (kh_shard_init) and large single-GPU tables with long k-mers are chunk tables (ctable.cuh);
+    // the others stay plain open-addressing tables.  KH_CT: 0 never, 1 auto, 2 always.
     t->ct_env = env_int("KH_CT", 1);
-    const bool use_ct = ct_supported(k) && (t->ct_env == 2 || (t->ct_env != 0 && n_expected >= (1ull << 20)));
+    // auto: single-GPU tables whose plain form needs 128-bit slots anyway (K >= 30) and that are far larger than L2.
+    // With 64-bit slots (K <= 29) the plain table's shared-memory build + walk is the faster single-GPU path
+    // (5.6 vs 9.2 ms on the chr14 shape at K=19: short supermers mean ~4 k-mers per segment).
+    const bool use_ct = ct_supported(k) && (t->ct_env == 2 || (t->ct_env != 0 && n_expected >= (1ull << 20) && 2 * k + 6 > 64));
     t->W = use_ct ? ct_slot_words(k) : ((2 * k + 6 <= 64) ? 1 : 2);
     t->slot_bytes = t->W == 1 ? 8 : 16;
     t->per_bucket = 32 / t->slot_bytes;
@@ -1012,6 +1025,8 @@ int kh_create(int k, uint64_t n_expected, double load_factor, int device, kh_tab
     for (auto& e : t->ev) ck(cudaEventCreate(&e));
     for (auto& e : t->ev_copied) ck(cudaEventCreateWithFlags(&e, cudaEventDisableTiming));
     for (auto& e : t->ev_consumed) ck(cudaEventCreateWithFlags(&e, cudaEventDisableTiming));
+    ck(cudaEventCreateWithFlags(&t->ev_built, cudaEventDisableTiming));
+    ck(cudaEventCreateWithFlags(&t->ev_gathered, cudaEventDisableTiming));
     if (rc != KH_OK) { fprintf(stderr, "libkh_b200: kh_create: %s\n", t->err.c_str()); return bail(rc); }
     if (!use_ct) ck(cudaMemsetAsync(t->table, 0, t->table_bytes, t->stream));
     ck(cudaMemsetAsync(t->d_ctr, 0, sizeof(Counters), t->stream));
@@ -1068,6 +1083,8 @@ int kh_destroy(kh_table* t) {
     for (auto& e : t->ev) if (e) cudaEventDestroy(e);
     for (auto& e : t->ev_copied) if (e) cudaEventDestroy(e);
     for (auto& e : t->ev_consumed) if (e) cudaEventDestroy(e);
+    if (t->ev_built) cudaEventDestroy(t->ev_built);
+    if (t->ev_gathered) cudaEventDestroy(t->ev_gathered);
     if (t->own_stream) cudaStreamDestroy(t->own_stream);
     if (t->copy_stream) cudaStreamDestroy(t->copy_stream);
     cudaGetLastError();

@@ -52,6 +52,15 @@ template <int W> struct CtBuild {
     static constexpr u32 kSmem = kOffCode + kMaxSlots;
 };
 constexpr int kCtBuildThreads = 512;
+// Where record number `at` of chunk `chunk` lives in the chunk buffers: position-major, in groups of one 128-byte
+// line (8 or 16 records).  All chunks fill at about the same rate, so at any moment the appends of the staging pass
+// land in a window of a few hundred MB instead of being spread over every chunk's own multi-KB buffer (3.7 GB in
+// all): far fewer TLB misses (tools/probes/scatter_probe.cu: 1.99 -> 1.42 ms for the chr14 shape).
+template <int W>
+__host__ __device__ __forceinline__ u64 ct_fine_index(u32 chunk, u32 at, u32 nchunks) {
+    constexpr u32 G = 128u / (u32)sizeof(typename Slot<W>::value_t);
+    return ((u64)(at / G) * nchunks + chunk) * G + (at % G);
+}
 // s_succ[node]: successor node (< 0x8000) | kSuccExt + own slot (successor is not in this chunk) | kSuccTail | kSuccDead
 constexpr u32 kSuccExt = 0x8000u, kSuccTail = 0xFFFFu, kSuccDead = 0xFFFDu, kPredNone = 0xFFFFu;
 // s_code[node]: forward extension code in bits 0..2, then
@@ -257,7 +266,7 @@ ct_stage_kernel(const unsigned char* __restrict__ recs, u64 n, const CtGeom g, c
 #pragma unroll
     for (int r = 0; r < kStgPer; ++r) {
         if (dst[r] == 0xFFFFFFFFu || own[r] != 0xFFFFFFFFu) continue;
-        if (at[r] < kMaxSlots) fine[(u64)dst[r] * kMaxSlots + at[r]] = v[r];
+        if (at[r] < kMaxSlots) fine[ct_fine_index<W>(dst[r], at[r], g.chunks_per_rank)] = v[r];
         else err |= kErrTableFull;                     // more k-mers share this chunk than a chunk can hold
     }
     err = __reduce_or_sync(kFullMask, err);
@@ -340,7 +349,7 @@ ct_xin_scatter_kernel(const typename Slot<W>::value_t* __restrict__ xin_vals, co
         for (u32 i = n0 + blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) {
             const u32 c = xin_chunk[base + i];
             const u32 at = atomicAdd(&chunk_cursor[c], 1u);
-            if (at < kMaxSlots) fine[(u64)c * kMaxSlots + at] = xin_vals[base + i];
+            if (at < kMaxSlots) fine[ct_fine_index<W>(c, at, g.chunks_per_rank)] = xin_vals[base + i];
             else err |= kErrTableFull;
         }
     }
@@ -350,14 +359,14 @@ ct_xin_scatter_kernel(const typename Slot<W>::value_t* __restrict__ xin_vals, co
 template <int W>
 __global__ void __launch_bounds__(256)
 ct_extra_kernel(const typename Slot<W>::value_t* __restrict__ extra_vals, const u32* __restrict__ extra_chunk,
-                const u32* __restrict__ extra_cnt, const u32* __restrict__ extra_done, const CtCaps caps, u32* __restrict__ chunk_cursor,
+                const u32* __restrict__ extra_cnt, const u32* __restrict__ extra_done, const CtCaps caps, u32 nchunks, u32* __restrict__ chunk_cursor,
                 typename Slot<W>::value_t* __restrict__ fine, Counters* ctr) {
     constexpr u32 kMaxSlots = CtBuild<W>::kMaxSlots;
     const u32 n = min(*extra_cnt, caps.extra_cap), n0 = min(*extra_done, n);
     for (u32 i = n0 + blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) {
         const u32 c = extra_chunk[i];
         const u32 at = atomicAdd(&chunk_cursor[c], 1u);
-        if (at < kMaxSlots) fine[(u64)c * kMaxSlots + at] = extra_vals[i];
+        if (at < kMaxSlots) fine[ct_fine_index<W>(c, at, nchunks)] = extra_vals[i];
         else atomicOr(&ctr->errors, kErrTableFull);
     }
 }
@@ -482,34 +491,40 @@ __device__ __forceinline__ int ct_smem_insert(typename Slot<W>::value_t* s_tab, 
     return -2;
 }
 
-// node id of the k-mer `key` in the finished chunk (from the index bits of its slot), or -1
+// One bucket of a lookup in the finished chunk: node id of `key` (from the index bits of its slot) if it is here,
+// kFindMiss if the bucket has a hole (the key is not in the chunk), kFindNext if the probe must go on.
+// The whole bucket is loaded (most lookups hit); the comparison is straight-line code, so two lookups of one
+// thread can be in flight together.
+constexpr int kFindMiss = -1, kFindNext = -2;
 template <int W>
-__device__ __forceinline__ int ct_smem_find_node(unsigned s_base, u32 nb, typename Slot<W>::value_t key) {
-    typedef Slot<W> S;
-    const u32 tag = ct_tag<W>(key);
-    u32 b = ct_bucket_in_chunk(CtSlot<W>::hash32(key), nb);
-    for (u32 tries = 0; tries < nb; ++tries) {
-        u64 w[4];
-        ct_lds_tags<W, false>(s_base + b * 32u, w);
-        u32 match = 0;
-        bool hole = false;
+__device__ __forceinline__ void ct_lds_bucket(unsigned saddr, u64 (&q)[4]) {
+    asm volatile("ld.shared.v2.u64 {%0,%1}, [%2];" : "=l"(q[0]), "=l"(q[1]) : "r"(saddr));
+    asm volatile("ld.shared.v2.u64 {%0,%1}, [%2+16];" : "=l"(q[2]), "=l"(q[3]) : "r"(saddr));
+}
+template <int W> __device__ __forceinline__ int ct_find_step(unsigned saddr, typename Slot<W>::value_t key);
+template <> __device__ __forceinline__ int ct_find_step<1>(unsigned saddr, u64 key) {
+    u64 q[4];
+    ct_lds_bucket<1>(saddr, q);
+    int res = kFindNext;
 #pragma unroll
-        for (int i = S::kPerBucket - 1; i >= 0; --i) {          // slots fill in order: a hit can only sit before the first hole
-            const bool e = ((u32)w[i] & 7u) == 0u;
-            hole = hole || e;
-            match = e ? 0u : (match | (((u32)(w[i] >> 6) == tag) ? (1u << i) : 0u));
-        }
-        if (match) {
-#pragma unroll
-            for (int i = 0; i < S::kPerBucket; ++i) {
-                u64 iw;
-                if ((match >> i) & 1u) if (ct_verify<W>(s_base + b * 32u, i, w[i], key, iw)) return (int)(iw >> (64 - kIdxBits)) - 1;
-            }
-        }
-        if (hole) return -1;
-        b = (b + 1 == nb) ? 0u : b + 1;
+    for (int i = 3; i >= 0; --i) {              // slots fill in order: a hit can only sit before the first hole
+        const bool e = ((u32)q[i] & 7u) == 0u;
+        const bool m = (((q[i] ^ key) << kIdxBits) >> (kIdxBits + 6)) == 0ull;
+        res = e ? kFindMiss : (m ? (int)(q[i] >> (64 - kIdxBits)) - 1 : res);
     }
-    return -1;
+    return res;
+}
+template <> __device__ __forceinline__ int ct_find_step<2>(unsigned saddr, u128 key) {
+    u64 q[4];
+    ct_lds_bucket<2>(saddr, q);
+    int res = kFindNext;
+#pragma unroll
+    for (int i = 1; i >= 0; --i) {
+        const bool e = ((u32)q[2 * i] & 7u) == 0u;
+        const bool m = (((q[2 * i + 1] ^ key.hi) << kIdxBits) | ((q[2 * i] ^ key.lo) >> 6)) == 0ull;
+        res = e ? kFindMiss : (m ? (int)(q[2 * i + 1] >> (64 - kIdxBits)) - 1 : res);
+    }
+    return res;
 }
 
 template <int W>
@@ -539,7 +554,6 @@ ct_build_kernel(const typename Slot<W>::value_t* __restrict__ fine, const u32* _
         if (threadIdx.x == 0) seg_base[c] = 0;
         return;
     }
-    const V* __restrict__ recs = fine + (u64)c * B::kMaxSlots;
     const unsigned s_base = (unsigned)__cvta_generic_to_shared(s_tab);
     const int k = g.k;
     constexpr int kBatch = 4;
@@ -547,7 +561,7 @@ ct_build_kernel(const typename Slot<W>::value_t* __restrict__ fine, const u32* _
 #pragma unroll
     for (int r = 0; r < kBatch; ++r) {
         const u32 i = threadIdx.x + r * kCtBuildThreads;
-        v[r] = i < cnt ? recs[i] : S::zero();
+        v[r] = i < cnt ? fine[ct_fine_index<W>(c, i, g.chunks_per_rank)] : S::zero();
     }
     if (threadIdx.x == 0) { s_inserted = 0; s_dups = 0; s_nheads = 0; s_chars = 0; s_err = 0; }
     {
@@ -563,7 +577,7 @@ ct_build_kernel(const typename Slot<W>::value_t* __restrict__ fine, const u32* _
 #pragma unroll
         for (int r = 0; r < kBatch; ++r) {
             const u32 i = base + kCtBuildThreads * kBatch + threadIdx.x + r * kCtBuildThreads;
-            nxt[r] = i < cnt ? recs[i] : S::zero();
+            nxt[r] = i < cnt ? fine[ct_fine_index<W>(c, i, g.chunks_per_rank)] : S::zero();
         }
 #pragma unroll
         for (int r = 0; r < kBatch; ++r) {
@@ -588,24 +602,50 @@ ct_build_kernel(const typename Slot<W>::value_t* __restrict__ fine, const u32* _
     }
     __syncthreads();
     // ---- 2. successor of every k-mer, if it lives in this chunk (kmer_hash.cpp:44-51 as an LDS probe) ----
+    // Two k-mers per thread and iteration: both first probes are issued before either is looked at.
 #pragma unroll 1
-    for (u32 node = threadIdx.x; node < cnt; node += kCtBuildThreads) {
-        const u32 slot = s_succ[node];
-        if (slot == kSuccDead) { s_code[node] = (unsigned char)kExtF; continue; }       // a duplicate: not in the table, on no chain
-        const V cur = s_tab[slot];
-        const u32 f = S::fwd(cur);
-        s_code[node] = (unsigned char)(f | (S::back(cur) == kExtF ? kCodeBackF : 0u));
-        u32 s = kSuccTail;
-        if (f != kExtF) {
-            const int j = ct_smem_find_node<W>(s_base, nb, S::next_key(CS::strip(cur), k));
-            if (j < 0) {
-                s = kSuccExt | slot;
-            } else {
-                s = (u32)j;
-                s_pd[j] = (node << 16) | 1u;            // plain store: with two predecessors one of them wins, phase 3 notices
+    for (u32 base = threadIdx.x; base < cnt; base += 2 * kCtBuildThreads) {
+        u32 slot[2], b[2], code[2];
+        V key[2];
+        int res[2];
+#pragma unroll
+        for (int q = 0; q < 2; ++q) {
+            const u32 node = base + q * kCtBuildThreads;
+            slot[q] = node < cnt ? (u32)s_succ[node] : kSuccDead;
+        }
+#pragma unroll
+        for (int q = 0; q < 2; ++q) {
+            const V cur = slot[q] != kSuccDead ? s_tab[slot[q]] : S::zero();
+            const u32 f = slot[q] != kSuccDead ? S::fwd(cur) : kExtF;       // a duplicate is not in the table and on no chain
+            code[q] = f | ((slot[q] != kSuccDead && S::back(cur) == kExtF) ? kCodeBackF : 0u);
+            key[q] = S::next_key(CS::strip(cur), k);
+            b[q] = ct_bucket_in_chunk(CS::hash32(key[q]), nb);
+        }
+#pragma unroll
+        for (int q = 0; q < 2; ++q) res[q] = (code[q] & 7u) != kExtF ? ct_find_step<W>(s_base + b[q] * 32u, key[q]) : kFindMiss;
+#pragma unroll
+        for (int q = 0; q < 2; ++q) {
+            for (u32 tries = 1; res[q] == kFindNext && tries < nb; ++tries) {      // the home bucket was full of other keys: go on
+                b[q] = (b[q] + 1 == nb) ? 0u : b[q] + 1;
+                res[q] = ct_find_step<W>(s_base + b[q] * 32u, key[q]);
             }
         }
-        s_succ[node] = (unsigned short)s;
+#pragma unroll
+        for (int q = 0; q < 2; ++q) {
+            const u32 node = base + q * kCtBuildThreads;
+            if (node >= cnt) continue;
+            s_code[node] = (unsigned char)code[q];
+            u32 sc = slot[q] == kSuccDead ? kSuccDead : kSuccTail;
+            if ((code[q] & 7u) != kExtF) {
+                if (res[q] < 0) {
+                    sc = kSuccExt | slot[q];
+                } else {
+                    sc = (u32)res[q];
+                    s_pd[res[q]] = (node << 16) | 1u;       // plain store: with two predecessors one of them wins, phase 3 notices
+                }
+            }
+            s_succ[node] = (unsigned short)sc;
+        }
     }
     __syncthreads();
     // ---- 3. heads: k-mers no chain of this chunk runs into (or that two run into, or with backward ext 'F') ----
@@ -641,18 +681,23 @@ ct_build_kernel(const typename Slot<W>::value_t* __restrict__ fine, const u32* _
     // In place: a stale read is still a valid (ancestor, distance) pair.  A root's low half is its segment index, which a
     // child never adds (it stops as soon as its ancestor is a root).  Chains are <= ~40 k-mers: ~6 rounds; a cycle
     // without a head (no chain enters it: kmer_hash.cpp never visits it) never settles and is cut off after 14 rounds.
+    // A thread keeps a bit per node of its own that has not settled yet: later rounds only touch those.
+    u32 active = 0;
+#pragma unroll 1
+    for (u32 i = 0, node = threadIdx.x; node < cnt; ++i, node += kCtBuildThreads) {
+        const u32 pd = s_pd[node];
+        active |= ((pd >> 16) != node) ? (1u << i) : 0u;            // heads and dead nodes are roots already
+    }
     for (int round = 0; round < 14; ++round) {
-        bool changed = false;
-    #pragma unroll 1
-    for (u32 node = threadIdx.x; node < cnt; node += kCtBuildThreads) {
+#pragma unroll 1
+        for (u32 m = active; m; m &= m - 1u) {
+            const u32 i = (u32)__ffs((int)m) - 1u, node = threadIdx.x + i * kCtBuildThreads;
             const u32 pd = s_pd[node], a = pd >> 16;
-            if (a == node) continue;
             const u32 pa = s_pd[a], a2 = pa >> 16;
-            if (a2 == a) continue;
+            if (a2 == a) { active &= ~(1u << i); continue; }        // the ancestor is a root: this node is done
             s_pd[node] = (a2 << 16) | ((pd + pa) & 0xFFFFu);
-            changed = true;
         }
-        if (!__syncthreads_or(changed)) break;
+        if (!__syncthreads_or(active != 0u)) break;
     }
     __syncthreads();
     const u32 seg0 = s_seg0;
@@ -922,7 +967,8 @@ ct_apply_kernel(u64* __restrict__ link, const u32* __restrict__ answers, const u
 // (16 bytes per segment + one byte per k-mer); fine-grained peer reads and writes ran at a few G/s.
 __global__ void __launch_bounds__(256)
 ct_gather_kernel(const CtPeers pe, const CtCaps caps, const u64* __restrict__ link, const u64* __restrict__ meta,
-                 const unsigned char* __restrict__ pool, const u32* __restrict__ pool_off, u32 nchunks, const Counters* __restrict__ ctr) {
+                 const unsigned char* __restrict__ pool, const u32* __restrict__ pool_off, u32 nchunks, const Counters* __restrict__ ctr,
+                 int what) {           // 0: meta words + characters (final once the chunks are built), 1: links (final once they are resolved)
     const u32 nseg = min(ctr->next_seg, caps.seg_cap);
     const u32 first = caps.hcap;                                   // head stubs are only ever read by their own rank
     const u32 cnt = nseg > first ? nseg - first : 0u;
@@ -933,10 +979,14 @@ ct_gather_kernel(const CtPeers pe, const CtCaps caps, const u64* __restrict__ li
         u64* gl = pe.g_link[p] + (u64)pe.rank * caps.g_seg_stride;
         u64* gm = pe.g_meta[p] + (u64)pe.rank * caps.g_seg_stride;
         uint4* gp = reinterpret_cast<uint4*>(pe.g_pool[p] + (u64)pe.rank * caps.g_pool_stride);
-        for (u64 i = tid; i < cnt; i += stride) { gl[first + i] = link[first + i]; gm[first + i] = meta[first + i]; }
-        const uint4* sp = reinterpret_cast<const uint4*>(pool);
-        for (u64 i = tid; i < pool_vecs; i += stride) gp[i] = sp[i];
-        if (tid == 0) { pe.g_hdr[p][2 * pe.rank] = nseg; pe.g_hdr[p][2 * pe.rank + 1] = (u32)pool_vecs; }
+        if (what == 1) {
+            for (u64 i = tid; i < cnt; i += stride) gl[first + i] = link[first + i];
+        } else {
+            for (u64 i = tid; i < cnt; i += stride) gm[first + i] = meta[first + i];
+            const uint4* sp = reinterpret_cast<const uint4*>(pool);
+            for (u64 i = tid; i < pool_vecs; i += stride) gp[i] = sp[i];
+            if (tid == 0) { pe.g_hdr[p][2 * pe.rank] = nseg; pe.g_hdr[p][2 * pe.rank + 1] = (u32)pool_vecs; }
+        }
     }
 }
 
