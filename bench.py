@@ -352,8 +352,9 @@ def measure_shape_n1(args, workload: str, steps: int, warmup: int, local_rank: i
     out = {
         "ms_per_step": ms_per_step, "value": n / (ms_per_step * 1e-3), "ms_each_step": ms,
         "config": {"workload": workload, "k": k, "n_kmers": n, "n_contigs": c, "load_factor": args.load_factor, "seed": SEED,
-                   "table": ("chunk table (csrc/ctable.cuh): staged by region, built + contracted per chunk in shared memory"
-                             if chunk_table else "plain open-addressing table"),
+                   "table": ("chunk table (csrc/ctable.cuh): one staging pass into per-chunk buffers, every chunk built + contracted in "
+                             "shared memory, one HBM lookup per segment, contigs ranked and emitted by per-contig walks"
+                             if chunk_table else "plain open-addressing table (csrc/kernels.cuh): shared-memory chunk build, splitter walk"),
                    "slot_bytes": slot_b,
                    "l2": "inputs (records, staging buffers, table) far larger than L2; every step starts from an empty table",
                    "table_clear": "between steps, outside the per-step event pair (the reference constructs its map "
@@ -369,7 +370,7 @@ def measure_shape_n1(args, workload: str, steps: int, warmup: int, local_rank: i
                      "peak_source": peak_src,
                      "units_per_launch": n, "alg_bytes_per_unit": dom_bytes // n, "kernel_ms": dom_ms,
                      "alg_bytes_per_kmer": alg,
-                     "insert_stage": {"kernels": "ct_stage + ct_scatter + ct_layout + ct_build (the build also does the traverse's lookups)"
+                     "insert_stage": {"kernels": "ct_stage + ct_layout + ct_build (the build also does the traverse's lookups)"
                                       if chunk_table else "partition + subpartition + build_chunks / insert_slots",
                                       "ms": sm["ms_insert"]},
                      "path": {"achieved": path_gbs, "frac": path_gbs / peak,

@@ -846,12 +846,21 @@ __device__ __forceinline__ bool lookup(const typename Slot<W>::value_t* __restri
     for (u64 tries = 0; tries < nbuckets; ++tries) {
         u64 q[4];
         load256_nc(table + b * S::kPerBucket, q);
+        // Branch-free inside the bucket: every lane of a warp leaves the slot scan at the same instruction (returning
+        // from inside the loop made the lanes exit at different slot indices, and everything after the lookup in
+        // walk_kernel then ran with ~9 of ~24 live lanes -- profiles/r01_final_lines_walk_kernel.txt).
+        bool hole = false, hit = false;
 #pragma unroll
         for (int i = 0; i < S::kPerBucket; ++i) {
             const typename S::value_t cur = S::from_bucket(q, i);
-            if (S::empty(cur)) return false;          // buckets fill in order: first hole ends the probe
-            if (S::same_key(cur, keybits)) { found = cur; bucket = b; slot = i; return true; }
+            const bool e = S::empty(cur);             // buckets fill in order: the first hole ends the probe
+            const bool m_ = !hole && !hit && !e && S::same_key(cur, keybits);
+            if (m_) { found = cur; slot = i; }
+            hit = hit || m_;
+            hole = hole || e;
         }
+        if (hit) { bucket = b; return true; }
+        if (hole) return false;
         b = (b + 1 == nbuckets) ? 0 : b + 1;
     }
     return false;
@@ -937,7 +946,7 @@ walk_kernel(const WalkParams p) {
     auto close = [&](u32 next) {
         if (n & 7u) *reinterpret_cast<u64*>(p.tmp + (u64)seg * p.seg_chars + (n & ~7u)) = acc;
         p.seglen[seg] = (unsigned char)n;
-        p.link[seg] = ((u64)next << 32) | (next == kLinkTail ? 0u : n);
+        p.link[seg] = ((u64)next << 32) | (next >= kLinkCtFirstMarker ? 0u : n);
         active = false;
     };
 
@@ -1014,16 +1023,17 @@ walk_kernel(const WalkParams p) {
                 }
                 V nxt; u64 b; int s;
                 if (!lookup<W>(table, p.nbuckets, p.k, p.m, S::next_key(cur, p.k), nxt, b, s)) {
-                    atomicOr(&p.ctr->errors, kErrNotFound);         // kmer_hash.cpp:47-49
-                    close(kLinkTail);
+                    // kmer_hash.cpp:47-49 throws only for chains it walks: mark the segment, rank_kernel raises the
+                    // error if a START-rooted contig ends here (a walker started at a splitter may sit on a chain no
+                    // start node reaches, which the reference never visits)
+                    close(kLinkMissing);
                 } else if (s == 0 && (b & split_mask) == 0) {
                     close(p.n_starts + (u32)(b >> p.split_shift));  // the splitter's walker takes over
                 } else {
                     cur = nxt;
                     // Brent: a splitter-free cycle would never end this segment
                     if (S::same_key(cur, chk)) {
-                        atomicOr(&p.ctr->errors, kErrCycle);
-                        close(kLinkTail);
+                        close(kLinkLoop);                           // reported only if a start-rooted contig runs into it
                     } else if (++steps == limit) {
                         chk = cur; steps = 0; limit <<= 1;
                     }
@@ -1069,11 +1079,11 @@ rank_kernel(const RankParams p) {
         for (u64 i = gtid; i < nseg; i += gsize) {
             const u64 li = ld_cg64(p.link + i);
             const u32 pi = (u32)(li >> 32);
-            if (pi >= kLinkClaimed) continue;
+            if (pi >= kLinkCtFirstMarker || pi == (u32)i) continue;       // ends here / unused; a one-segment cycle never moves
             const u64 lp = ld_cg64(p.link + pi);
             const u32 pp = (u32)(lp >> 32);
-            if (pp == kLinkTail) continue;                   // final
-            if (pp >= kLinkClaimed) { atomicOr(&p.ctr->errors, kErrInternal); continue; }
+            if (pp == kLinkTail || pp == kLinkMissing || pp == kLinkLoop) continue;      // final: pi is the chain's last segment
+            if (pp >= kLinkCtFirstMarker) { atomicOr(&p.ctr->errors, kErrInternal); continue; }
             __stcg(p.link + i, ((u64)pp << 32) | (u32)((u32)li + (u32)lp));
             changed = true;
         }
@@ -1088,14 +1098,15 @@ rank_kernel(const RankParams p) {
     for (u64 c = gtid; c < p.n_starts; c += gsize) {
         const u64 lc = ld_cg64(p.link + c);
         const u32 pc = (u32)(lc >> 32);
-        u32 tail = (u32)c, pre = 0;
-        bool ok = true;
-        if (pc != kLinkTail) {
+        u32 tail = (u32)c, pre = 0, end = pc;                // end = marker of the chain's last segment
+        if (pc < kLinkCtFirstMarker) {
             tail = pc; pre = (u32)lc;
-            ok = pc < kLinkClaimed && (u32)(ld_cg64(p.link + pc) >> 32) == kLinkTail;
+            end = (u32)(ld_cg64(p.link + pc) >> 32);
         }
-        if (!ok) {      // still open after max_rounds: the chain runs into a cycle (kmer_hash.cpp:44 never exits)
-            atomicOr(&p.ctr->errors, kErrCycle);
+        if (end != kLinkTail) {
+            // a missing successor on a start-rooted chain (kmer_hash.cpp:47-49), or the chain runs into a cycle / is
+            // still open after max_rounds (kmer_hash.cpp:44 never exits)
+            atomicOr(&p.ctr->errors, end == kLinkMissing ? kErrNotFound : kErrCycle);
             p.contig_pre[c] = 0; p.contig_len[c] = 0;
             continue;
         }
@@ -1138,7 +1149,7 @@ emit_segments_kernel(const u64* __restrict__ link, const unsigned char* __restri
     if (seg < nseg) {
         const u64 li = link[seg];
         const u32 pi = (u32)(li >> 32);
-        if (pi != kLinkUnused && pi != kLinkTail) {         // never walked / not on any start-rooted chain
+        if (pi < kLinkCtFirstMarker || pi == kLinkClaimed) {      // else: never walked / not on any start-rooted chain
             bool ok = true;
             u32 c = 0, pos = 0;
             if (pi == kLinkClaimed) {

@@ -525,6 +525,7 @@ constexpr u32 kLinkFinalBit = 0x80000000u;
 constexpr u32 kLinkDistMask = 0x7FFFFFFFu;
 constexpr u32 kLinkMissing = 0xFFFFFFFBu;   // ctable: the successor k-mer is in no table (raised only if a start-rooted contig ends here)
 constexpr u32 kLinkConverge = 0xFFFFFFFAu;  // ctable: the successor k-mer sits in the middle of another segment (it has two predecessors)
+constexpr u32 kLinkLoop = kLinkConverge;        // plain table: the walker found itself on a cycle (same value, different path)
 constexpr u32 kLinkCtFirstMarker = kLinkConverge;
 
 // Error bits accumulated on the device (Counters::errors)

@@ -465,9 +465,10 @@ def bench(args, workload, rank, world, local_rank, steps, warmup):
                        "seed": 267, "per_gpu_kmers": n_local, "slot_bytes": sb,
                        "sharding": f"chunk table sharded over {world} GPUs (a rank owns a contiguous range of chunks; the chunk, and "
                        "so the owner, follows from the k-mer's minimizer); input lines block-partitioned (read_kmers.hpp:55-58); "
-                       "slot values reach the owner through NVLink peer stores inside the grouping kernel; one lookup per "
-                       "segment chains the segments, requests to other GPUs and their answers are peer stores; pointer "
-                       "jumping and the contig text across GPUs over peer mappings; in-stream flag barriers, one host wait per step",
+                       "records reach the owner as owner-sorted runs of NVLink peer stores inside the staging kernel; one lookup per "
+                       "segment chains the segments, requests to other GPUs and their answers travel as coalesced runs; segment "
+                       "links, meta words and characters are gathered on every rank, contigs ranked and emitted by per-contig walks "
+                       "over local memory; in-stream flag barriers, two host waits per step",
                        "timing": "CUDA events on the launching stream per step (after the step's opening barrier .. after its "
                                  "closing barrier), max over ranks, mean of steps",
                        "l2": "per-GPU staging buffers and table larger than L2; every step starts from an empty table"},
@@ -482,10 +483,10 @@ def bench(args, workload, rank, world, local_rank, steps, warmup):
                          "alg_bytes_per_kmer": alg,
                          "path": {"achieved": path_gbs, "peak": peak * world, "frac": path_gbs / (peak * world),
                                   "note": "N x B_alg / t(insert+traverse) against the measured HBM peak x GPUs"},
-                         "nvlink_bytes_per_step": int(n_total * (world - 1) / world * (sb + 2)),
-                         "nvlink_note": "(P-1)/P of the slot values (+ 2-byte chunk tags) cross in the staging pass; per segment "
-                                        "that continues on another GPU one 16/32-byte request and a 4-byte answer; per round one "
-                                        "8-byte read per open link; the contig characters of segments whose contig lives elsewhere"},
+                         "nvlink_bytes_per_step": int(n_total * (world - 1) / world * (sb + 4) + (world - 1) * (16 * segs_all + n_total)),
+                         "nvlink_note": "(P-1)/P of the slot values (+ 4-byte chunk ids) cross in the staging pass; per segment "
+                                        "that continues on another GPU one 16/32-byte request and a 4-byte answer (not counted); "
+                                        "the gather sends 16 bytes per segment + 1 byte per k-mer to each of the P-1 peers"},
             "e2e": ({"value": n_total / (e2e_ms_max * 1e-3), "unit": UNIT, "ms_per_step": e2e_ms_max,
                      "h2d_bytes_per_step": int(n_total * pb), "d2h_bytes_per_step": int(bytes_all),
                      "note": "each rank copies its block of records from pinned host memory and its contigs back"}

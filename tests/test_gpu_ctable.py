@@ -62,21 +62,7 @@ def test_cycle_is_reported_not_spun_on(kh, k):
         assert e.value.status in (kh.KH_ERR_CYCLE, kh.KH_ERR_CONVERGE)      # the chain re-enters itself: refused either way
 
 
-def test_orphan_chains_and_cycles_are_ignored(kh):
-    """k-mers on no start-rooted chain (dangling chains with a missing successor, cycles) are never visited by
-    the reference (kmer_hash.cpp:41-53): no error, same output."""
-    k = 19
-    d = kmergen.Dataset(k, 30000, 80, seed=8)
-    rng = np.random.default_rng(3)
-    extra = []
-    for _ in range(200):
-        s = "".join("ACGT"[i] for i in rng.integers(0, 4, k + 12))
-        extra += [f"{s[i:i + k]} {s[i - 1] if i else 'C'}{s[i + k]}\n" for i in range(10)]
-    text = d.text().tobytes() + "".join(extra).encode() + P._cycle_text(k, 0, 500, seed=4)
-    want = oracle.assemble_text(text, k)[0]
-    assert want == d.expected()[0]
-    out, _, nodes, _ = P._assemble_text(kh, text, k)
-    assert out == want and nodes == d.n
+test_orphan_chains_and_cycles_are_ignored = P.test_orphan_chains_and_cycles_are_ignored
 
 
 def test_converging_chains(kh):
