@@ -740,8 +740,9 @@ int ct_seal_build(kh_table* t) {
 //   2  answer the requests that arrived (one coalesced run of answers per requester) | barrier
 //   3  file the answers; send segment links / meta / characters to every other rank | barrier
 //   4  contig lengths by walking each contig's segments (bounded) | barrier that agrees on "some contig is too long"
-//   5  [the host reads that one flag]  fast path: offsets, second walk that copies the characters | barrier -- done
-//   6 .. 6+R-1  (slow path only) one pointer-jumping round each | barrier that also agrees on "nobody moved"
+//   5  fast path, enqueued unconditionally (its kernels look at the agreed flag): offsets, second walk that copies the characters
+//   6  [the host reads the flag -- it would wait here anyway, the step is over]  slow path only from here on:
+//   6 .. 6+R-1  one pointer-jumping round each | barrier that also agrees on "nobody moved"
 //   6+R  (slow path only) contig lengths, claims, offsets | barrier
 //   7+R  (slow path only) emit | barrier
 constexpr int kCtMaxRounds = 24;            // chains of up to 2^24 segments
@@ -825,20 +826,28 @@ int ct_assemble_part(kh_table* t, int part) {
         ++t->n_launches;
         return ct_barrier(t, -2);
     case 5: {
-        KH_TRY(read_counters(t));                    // the step's one mid-way host wait: which way do all ranks go?
-        c.slow = (c.pe.world > 1 ? t->h_ctr->use_jump : t->h_ctr->need_jump) != 0;
-        if (c.slow) { c.assembled = true; return KH_OK; }
+        // The fast path is enqueued without asking: its kernels return at once if the ranks agreed on pointer jumping
+        // (a device-side flag).  No barrier after it: from here on a rank only reads its own memory, and the next
+        // step's opening barrier keeps a fast rank from touching a slow one's buffers.
         KH_TRY(device_scan(t, static_cast<u32*>(t->contig_len.p), (u64)c.caps.hcap + 1, static_cast<u64*>(t->contig_off.p), &t->d_ctr->contig_bytes));
         KH_CUDA(t, cudaEventRecord(t->ev[EV_RANK], t->stream));
-        ct_emit_heads_kernel<W><<<gb, 256, 0, t->stream>>>(static_cast<const V*>(t->starts.p), c.caps, t->k, static_cast<const u32*>(t->contig_len.p),
-                                                          static_cast<const u64*>(t->contig_off.p), t->d_ctr, c.out_cap, static_cast<char*>(t->out.p));
-        ct_walk_emit_kernel<<<gb, 256, 0, t->stream>>>(gt, link, c.caps, t->k, static_cast<const u32*>(t->contig_len.p),
-                                                       static_cast<const u64*>(t->contig_off.p), c.out_cap, static_cast<char*>(t->out.p), t->d_ctr);
+        ct_walk_emit_kernel<W><<<gb, 256, 0, t->stream>>>(gt, link, static_cast<const V*>(t->starts.p), c.caps, t->k, static_cast<const u32*>(t->contig_len.p),
+                                                          static_cast<const u64*>(t->contig_off.p), c.out_cap, static_cast<char*>(t->out.p), t->d_ctr);
         KH_CUDA(t, cudaGetLastError());
-        t->n_launches += 2;
+        ++t->n_launches;
         KH_CUDA(t, cudaEventRecord(t->ev[EV_AS1], t->stream));
         t->have_as = true;
-        return ct_barrier(t);
+        return KH_OK;
+    }
+    case 6: {
+        KH_TRY(read_counters(t));                    // which way did all ranks go?  (the host would wait here anyway: the step is over)
+        c.slow = (c.pe.world > 1 ? t->h_ctr->use_jump : t->h_ctr->need_jump) != 0;
+        if (!c.slow) return KH_OK;
+        c.assembled = true;                          // the slow path jumps links in place and claims tails: the next traverse re-seals
+        ct_rank_round_kernel<<<gb, 256, 0, t->stream>>>(c.pe, link, c.caps, t->d_ctr, t->d_ctr->flags, 0);
+        KH_CUDA(t, cudaGetLastError());
+        ++t->n_launches;
+        return ct_barrier(t, 0);
     }
     case 6 + kCtMaxRounds: {
         if (!c.slow) return KH_OK;
@@ -864,7 +873,7 @@ int ct_assemble_part(kh_table* t, int part) {
         t->have_as = true;
         return ct_barrier(t);
     default: {
-        if (part < 6 || part >= 6 + kCtMaxRounds) return fail(t, KH_ERR_ARG, "unknown assemble part");
+        if (part < 7 || part >= 6 + kCtMaxRounds) return fail(t, KH_ERR_ARG, "unknown assemble part");
         if (!c.slow) return KH_OK;
         const int r = part - 6;
         ct_rank_round_kernel<<<gb, 256, 0, t->stream>>>(c.pe, link, c.caps, t->d_ctr, t->d_ctr->flags, r);

@@ -385,23 +385,35 @@ __global__ void __launch_bounds__(1024)
 ct_layout_kernel(const u32* __restrict__ chunk_cursor, u32 nchunks, const CtGeom g, const CtCaps caps, u32 per_bucket, u32 max_slots,
                  u32* __restrict__ chunk_base, u32* __restrict__ pool_off, Counters* ctr) {
     __shared__ u64 s_warp[33];
+    constexpr u32 kPer = 8;                                       // consecutive chunks per thread: 8192 chunks per block-wide scan
     u64 carry_b = 0, carry_p = 0;
-    for (u32 c0 = 0; c0 < nchunks; c0 += blockDim.x) {
-        const u32 c = c0 + threadIdx.x;
-        u32 capb = 0, chars = 0;
-        if (c < nchunks) {
-            const u32 load = min(chunk_cursor[c], max_slots);
-            if (load) {
-                const u64 want_slots = ((u64)load * g.lf_inv_q16 + 65535u) >> 16;
-                capb = (u32)min((u64)g.max_buckets, max((want_slots + per_bucket - 1) / per_bucket, (u64)(load / per_bucket + 1)));
-                capb = min(capb, g.max_buckets);
+    for (u32 c0 = 0; c0 < nchunks; c0 += blockDim.x * kPer) {
+        const u32 first = c0 + threadIdx.x * kPer;
+        u32 capb[kPer], chars[kPer];
+        u64 sum_b = 0, sum_p = 0;
+#pragma unroll
+        for (u32 q = 0; q < kPer; ++q) {
+            const u32 c = first + q;
+            capb[q] = 0; chars[q] = 0;
+            if (c < nchunks) {
+                const u32 load = min(chunk_cursor[c], max_slots);
+                if (load) {
+                    const u64 want_slots = ((u64)load * g.lf_inv_q16 + 65535u) >> 16;
+                    capb[q] = (u32)min((u64)g.max_buckets, max((want_slots + per_bucket - 1) / per_bucket, (u64)(load / per_bucket + 1)));
+                }
+                chars[q] = (load + 15u) & ~15u;
             }
-            chars = (load + 15u) & ~15u;
+            sum_b += capb[q]; sum_p += chars[q];
         }
         u64 tot_b, tot_p;
-        const u64 eb = block_exclusive_scan((u64)capb, s_warp, tot_b);
-        const u64 ep = block_exclusive_scan((u64)chars, s_warp, tot_p);
-        if (c < nchunks) { chunk_base[c] = (u32)(carry_b + eb); pool_off[c] = (u32)(carry_p + ep); }
+        u64 eb = carry_b + block_exclusive_scan(sum_b, s_warp, tot_b);
+        u64 ep = carry_p + block_exclusive_scan(sum_p, s_warp, tot_p);
+#pragma unroll
+        for (u32 q = 0; q < kPer; ++q) {
+            const u32 c = first + q;
+            if (c < nchunks) { chunk_base[c] = (u32)eb; pool_off[c] = (u32)ep; }
+            eb += capb[q]; ep += chars[q];
+        }
         carry_b += tot_b; carry_p += tot_p;
     }
     if (threadIdx.x == 0) {
@@ -1057,18 +1069,33 @@ __device__ __forceinline__ void ct_copy_chars(char* dst, const unsigned char* sr
     while (n) { *dst++ = (char)*src++; --n; }
 }
 
-// second walk: the characters of every segment go to their place in the contig (extract_contig, read_kmers.hpp:81-92)
+// second walk: the first k-mer's K characters, then the characters of every segment, then the newline
+// (extract_contig, read_kmers.hpp:81-92; kmer_hash.cpp:66)
+template <int W>
 __global__ void __launch_bounds__(256)
-ct_walk_emit_kernel(const CtGathered gt, const u64* __restrict__ link, const CtCaps caps, int k,
-                    const u32* __restrict__ contig_len, const u64* __restrict__ contig_off, u64 out_cap, char* __restrict__ out,
-                    const Counters* __restrict__ ctr) {
-    if (ctr->use_jump || (ctr->errors & (kErrConverge | kErrCycle | kErrInternal | kErrNotFound)) || ctr->contig_bytes > out_cap) return;
+ct_walk_emit_kernel(const CtGathered gt, const u64* __restrict__ link, const typename Slot<W>::value_t* __restrict__ starts,
+                    const CtCaps caps, int k, const u32* __restrict__ contig_len, const u64* __restrict__ contig_off, u64 out_cap,
+                    char* __restrict__ out, const Counters* __restrict__ ctr) {
+    typedef Slot<W> S;
+    if (ctr->use_jump || ctr->need_jump || (ctr->errors & (kErrConverge | kErrCycle | kErrInternal | kErrNotFound)) || ctr->contig_bytes > out_cap) return;
     const u32 n_starts = (u32)min(ctr->n_starts_dev, (u64)caps.hcap);
     for (u64 c = (u64)blockIdx.x * blockDim.x + threadIdx.x; c < n_starts; c += (u64)gridDim.x * blockDim.x) {
         const u32 len = contig_len[c];
         if (len == 0) continue;
-        char* dst = out + contig_off[c] + (u32)k;
-        char* const end = out + contig_off[c] + len - 1u;
+        char* dst = out + contig_off[c];
+        char* const end = dst + len - 1u;
+        *end = '\n';
+        {                                                              // the start k-mer, four bases per aligned 32-bit store
+            const typename S::value_t v0 = starts[c];
+            int j = 0;
+            while (j < k && (reinterpret_cast<uintptr_t>(dst) & 3u)) { *dst++ = (char)ext_char(S::base_at(v0, k, j)); ++j; }
+            for (; j + 4 <= k; j += 4, dst += 4) {
+                const u32 w = (u32)ext_char(S::base_at(v0, k, j)) | ((u32)ext_char(S::base_at(v0, k, j + 1)) << 8) |
+                              ((u32)ext_char(S::base_at(v0, k, j + 2)) << 16) | ((u32)ext_char(S::base_at(v0, k, j + 3)) << 24);
+                *reinterpret_cast<u32*>(dst) = w;
+            }
+            for (; j < k; ++j) *dst++ = (char)ext_char(S::base_at(v0, k, j));
+        }
         u32 gid = (u32)(__ldg(link + c) >> 32);
         for (;;) {
             const u32 r = gid >> kRankShift, i = gid & kLocalMask;
