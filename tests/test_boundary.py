@@ -41,6 +41,8 @@ def test_library_is_sm100a_and_uses_wide_sector_ops():
     assert "ATOMG.E.CAS.128" in r.stdout      # 128-bit slots are claimed with one CAS
     assert "ATOMG.E.CAS.64" in r.stdout
     assert ".256" in r.stdout                 # one 32-byte bucket per load
+    assert "ATOMS.CAS.128" in r.stdout        # chunk table: 128-bit slots claimed in shared memory
+    assert "UBLKCP" in r.stdout               # chunk table: built chunks leave through bulk shared->global copies (cp.async.bulk)
 
 
 def test_pure_helpers_need_no_gpu():
