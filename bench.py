@@ -80,26 +80,64 @@ def alg_bytes_per_kmer(k: int) -> dict:
 
 
 class ClockSampler:
-    """nvidia-smi clocks / throttle reasons during the timed region."""
+    """SM clock, power and throttle reasons of one GPU during the timed region.  NVML in a background thread (the
+    numbers `nvidia-smi --query-gpu=clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.*` prints; nvidia-smi itself
+    needs more than a second to start on an 8-GPU box, longer than a whole timed loop), nvidia-smi as the fallback."""
 
     Q = ("clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,clocks_event_reasons.hw_slowdown,"
          "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,"
          "clocks_event_reasons.sw_power_cap")
 
     def __init__(self, index: int):
-        self.index, self.proc, self.lines = index, None, []
+        self.index, self.proc, self.lines, self.samples, self.t, self.stop_flag, self.mode = index, None, [], [], None, False, None
+
+    def _nvml_loop(self, nv, h):
+        bits = {"hw_slowdown": nv.nvmlClocksEventReasonHwSlowdown, "hw_thermal_slowdown": nv.nvmlClocksEventReasonHwThermalSlowdown,
+                "sw_thermal_slowdown": nv.nvmlClocksEventReasonSwThermalSlowdown, "sw_power_cap": nv.nvmlClocksEventReasonSwPowerCap}
+        mx = float(nv.nvmlDeviceGetMaxClockInfo(h, nv.NVML_CLOCK_SM))
+        while not self.stop_flag:
+            try:
+                sm = float(nv.nvmlDeviceGetClockInfo(h, nv.NVML_CLOCK_SM))
+                pw = nv.nvmlDeviceGetPowerUsage(h) / 1000.0
+                r = nv.nvmlDeviceGetCurrentClocksEventReasons(h)
+                self.samples.append((sm, mx, pw, [k for k, b in bits.items() if r & b]))
+            except Exception:
+                pass
+            time.sleep(0.002)
 
     def start(self):
+        try:
+            import pynvml as nv
+            nv.nvmlInit()
+            vis = os.environ.get("CUDA_VISIBLE_DEVICES")
+            idx = int(vis.split(",")[self.index]) if vis and all(x.strip().isdigit() for x in vis.split(",")) else self.index
+            h = nv.nvmlDeviceGetHandleByIndex(idx)
+            self.mode = "nvml"
+            self.t = threading.Thread(target=self._nvml_loop, args=(nv, h), daemon=True)
+            self.t.start()
+            return
+        except Exception:
+            self.mode = None
         try:
             self.proc = subprocess.Popen(["nvidia-smi", f"--id={self.index}", f"--query-gpu={self.Q}",
                                           "--format=csv,noheader,nounits", "-lms", "20"],
                                          stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
             self.t = threading.Thread(target=lambda: self.lines.extend(self.proc.stdout), daemon=True)
             self.t.start()
+            self.mode = "nvidia-smi"
         except Exception:
             self.proc = None
 
     def stop(self) -> dict:
+        if self.mode == "nvml":
+            self.stop_flag = True
+            self.t.join(timeout=2)
+            if not self.samples:
+                return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["no samples"]}
+            reasons = sorted({r for s_ in self.samples for r in s_[3]})
+            return {"sm_mhz": float(np.median([s_[0] for s_ in self.samples])), "sm_max_mhz": max(s_[1] for s_ in self.samples),
+                    "power_w_max": max(s_[2] for s_ in self.samples), "samples": len(self.samples), "reasons": reasons,
+                    "source": "NVML (clock, power, clocks-event reasons), 2 ms period"}
         if not self.proc:
             return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
         time.sleep(0.15)
@@ -121,7 +159,7 @@ class ClockSampler:
         if not sm:
             return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["no samples"]}
         return {"sm_mhz": float(np.median(sm)), "sm_max_mhz": max(mx), "power_w_max": max(power),
-                "samples": len(sm), "reasons": sorted(reasons)}
+                "samples": len(sm), "reasons": sorted(reasons), "source": "nvidia-smi -lms 20"}
 
 
 # ------------------------------------------------------------------ reference arm ---------
