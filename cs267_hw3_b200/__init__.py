@@ -31,7 +31,7 @@ ABI_SYMBOLS = [
     # sharded (multi-GPU) path
     "kh_slot_bytes", "kh_shard_init", "kh_shard_export_count", "kh_shard_export", "kh_shard_connect", "kh_shard_connect_local",
     "kh_shard_begin", "kh_shard_insert", "kh_shard_assemble", "kh_shard_assemble_parts", "kh_shard_assemble_part",
-    "kh_shard_finish", "kh_shard_result", "kh_debug_buffer",
+    "kh_shard_finish", "kh_shard_result", "kh_debug_buffer", "kh_get_device_view", "kh_sorted_order",
     "kh_device_alloc", "kh_device_alloc_on", "kh_device_free", "kh_copy_to_host", "kh_copy_device",
 ]
 

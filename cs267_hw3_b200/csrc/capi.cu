@@ -13,6 +13,9 @@
 #include <cstdlib>
 #include <cstring>
 #include <string>
+#include <vector>
+
+#include <cub/device/device_radix_sort.cuh>
 
 #include "../../include/kh_capi.h"
 #include "kernels.cuh"
@@ -58,6 +61,7 @@ struct kh_table {
     Counters* h_ctr = nullptr;
     DevBuf link, seglen, tmp, contig_len, contig_pre, contig_off, out;
     DevBuf stage[2], text_stage, scratch_a, scratch_b, scratch_c;
+    DevBuf sort_keys[2], sort_vals[2], sort_tmp;     // kh_sorted_order
     void* h_out = nullptr; size_t h_out_cap = 0;
     void* h_off = nullptr; size_t h_off_cap = 0;
     u32 split_shift = 5, seg_chars = 64;     // every 32nd bucket's first slot is a splitter (tools/probes/sweep_walk.sh)
@@ -1074,7 +1078,7 @@ int kh_destroy(kh_table* t) {
     if (t->own_stream) cudaStreamSynchronize(t->own_stream);
     DevBuf* bufs[] = {&t->starts, &t->mask, &t->tile_counts, &t->tile_offs, &t->scan_blocks, &t->link, &t->seglen,
                       &t->tmp, &t->part_cursor, &t->grouped, &t->fine, &t->chunk_cursor, &t->overflow, &t->contig_len, &t->contig_pre, &t->contig_off, &t->out, &t->stage[0], &t->stage[1],
-                      &t->text_stage, &t->scratch_a, &t->scratch_b, &t->scratch_c};
+                      &t->text_stage, &t->scratch_a, &t->scratch_b, &t->scratch_c, &t->sort_keys[0], &t->sort_keys[1], &t->sort_vals[0], &t->sort_vals[1], &t->sort_tmp};
     for (DevBuf* b : bufs) if (b->p) cudaFree(b->p);
     for (auto& row : t->ct.ipc_opened) for (void* q : row) if (q) cudaIpcCloseMemHandle(q);
     {
@@ -1344,6 +1348,80 @@ int kh_get_stats(kh_table* t, kh_stats* out) {
     if (t->have_stage && t->have_ins) s.ms_stage = elapsed(t->ev[EV_INS0], t->ev[EV_STAGE1]);
     s.n_launches = t->n_launches;
     *out = s;
+    return KH_OK;
+}
+
+// ---- output side (scripts/check_it.sh:47-48: `cat test*.dat | sort`) ------------------------------------------
+// sort key of a contig: its first 21 characters, 3 bits each (0 = the line ended, 1..4 = A C G T), most significant
+// first -- bytewise (LC_ALL=C) order of the lines as far as 21 characters decide it
+__global__ void __launch_bounds__(256)
+contig_sort_keys_kernel(const char* __restrict__ text, const u64* __restrict__ off, u64 n, u64* __restrict__ keys, u32* __restrict__ idx) {
+    const u64 c = (u64)blockIdx.x * blockDim.x + threadIdx.x;
+    if (c >= n) return;
+    const u64 b = off[c], len = off[c + 1] - b - 1;                 // without the newline
+    u64 key = 0;
+    for (u32 j = 0; j < 21; ++j) {
+        u32 code = 0;
+        if (j < len) code = base_code_fast((unsigned char)text[b + j]) + 1u;
+        key = (key << 3) | code;
+    }
+    keys[c] = key;
+    idx[c] = (u32)c;
+}
+
+int kh_sorted_order(kh_table* t, uint64_t* order_host_out, uint64_t* n_contigs_out) {
+    if (!t || !order_host_out) return KH_ERR_ARG;
+    KH_CUDA(t, cudaSetDevice(t->device));
+    const u64 n = t->last_n_contigs, bytes = t->last_contig_bytes;
+    if (n_contigs_out) *n_contigs_out = n;
+    if (n == 0) return KH_OK;
+    if (n >= 0xFFFFFFFFull) return fail(t, KH_ERR_ARG, "kh_sorted_order: more than 2^32 contigs");
+    for (int i = 0; i < 2; ++i) { KH_TRY(ensure(t, t->sort_keys[i], n * sizeof(u64))); KH_TRY(ensure(t, t->sort_vals[i], n * sizeof(u32))); }
+    const char* text = static_cast<const char*>(t->out.p);
+    const u64* off = static_cast<const u64*>(t->contig_off.p);
+    contig_sort_keys_kernel<<<(unsigned)((n + 255) / 256), 256, 0, t->stream>>>(text, off, n, static_cast<u64*>(t->sort_keys[0].p), static_cast<u32*>(t->sort_vals[0].p));
+    size_t tmp_bytes = 0;
+    cub::DeviceRadixSort::SortPairs(nullptr, tmp_bytes, static_cast<const u64*>(t->sort_keys[0].p), static_cast<u64*>(t->sort_keys[1].p),
+                                    static_cast<const u32*>(t->sort_vals[0].p), static_cast<u32*>(t->sort_vals[1].p), (int)n, 0, 63, t->stream);
+    KH_TRY(ensure(t, t->sort_tmp, tmp_bytes + 16));
+    KH_CUDA(t, cub::DeviceRadixSort::SortPairs(t->sort_tmp.p, tmp_bytes, static_cast<const u64*>(t->sort_keys[0].p), static_cast<u64*>(t->sort_keys[1].p),
+                                               static_cast<const u32*>(t->sort_vals[0].p), static_cast<u32*>(t->sort_vals[1].p), (int)n, 0, 63, t->stream));
+    t->n_launches += 4;
+    std::vector<u64> keys(n);
+    std::vector<u32> idx(n);
+    KH_CUDA(t, cudaMemcpyAsync(keys.data(), t->sort_keys[1].p, n * sizeof(u64), cudaMemcpyDeviceToHost, t->stream));
+    KH_CUDA(t, cudaMemcpyAsync(idx.data(), t->sort_vals[1].p, n * sizeof(u32), cudaMemcpyDeviceToHost, t->stream));
+    KH_CUDA(t, cudaStreamSynchronize(t->stream));
+    for (u64 i = 0; i < n; ++i) order_host_out[i] = idx[i];
+    // contigs that agree on their first 21 characters (rare): finish those runs on the host with the whole lines
+    std::vector<char> host_text;
+    std::vector<u64> host_off;
+    for (u64 i = 0; i < n;) {
+        u64 j = i + 1;
+        while (j < n && keys[j] == keys[i]) ++j;
+        if (j - i > 1) {
+            if (host_off.empty()) {
+                host_text.resize(bytes); host_off.resize(n + 1);
+                KH_CUDA(t, cudaMemcpy(host_text.data(), text, bytes, cudaMemcpyDeviceToHost));
+                KH_CUDA(t, cudaMemcpy(host_off.data(), off, (n + 1) * sizeof(u64), cudaMemcpyDeviceToHost));
+            }
+            std::stable_sort(order_host_out + i, order_host_out + j, [&](uint64_t a, uint64_t b) {
+                const u64 la = host_off[a + 1] - host_off[a], lb = host_off[b + 1] - host_off[b];      // incl. '\n' (0x0A < 'A'): a prefix sorts first
+                const int c = memcmp(host_text.data() + host_off[a], host_text.data() + host_off[b], std::min(la, lb));
+                return c != 0 ? c < 0 : la < lb;
+            });
+        }
+        i = j;
+    }
+    return KH_OK;
+}
+
+int kh_get_device_view(kh_table* t, kh_device_view* out) {
+    if (!t || !out) return KH_ERR_ARG;
+    if (t->ct.on) return fail(t, KH_ERR_ARG, "kh_get_device_view: a chunk table has no single-record device interface (KH_CT=0 forces a plain table)");
+    out->table = t->table; out->n_buckets = t->nbuckets; out->k = t->k; out->slot_bytes = t->slot_bytes;
+    out->placement_m = t->mlen; out->device = t->device;
+    t->table_dirty = true;              // the caller may insert behind our back: the next bulk insert must not assume an empty table
     return KH_OK;
 }
 

@@ -44,6 +44,8 @@ inline uint64_t shard_capacity(uint64_t n_total, int world) {
 
 struct RankOutput {
     std::vector<char> text;       // contigs of this rank, '\n'-terminated, in start-line order
+    std::vector<uint64_t> offsets;   // n_contigs + 1 byte offsets into text
+    std::vector<uint64_t> sorted;    // with want_sorted: this rank's contig indices in bytewise order of their lines
     uint64_t n_contigs = 0, n_nodes = 0;
 };
 
@@ -105,7 +107,8 @@ class Cluster {
     }
 
     // assemble_contigs across ranks (kmer_hash.cpp:38-55); returns what each rank writes to <prefix>_<rank>.dat
-    std::vector<RankOutput> assemble() {
+    // want_sorted: also sort every rank's contigs on its GPU (kh_sorted_order), for a merged, already-sorted solution
+    std::vector<RankOutput> assemble(bool want_sorted = false) {
         if (lockstep_) {
             const int parts = kh_shard_assemble_parts();
             for (int p = 0; p < parts; ++p)
@@ -126,10 +129,17 @@ class Cluster {
         std::vector<RankOutput> out(world_);
         each_rank([&](int r) {
             const char* dev_text = nullptr;
+            const uint64_t* dev_off = nullptr;
             uint64_t bytes = 0;
-            must(kh_shard_result(t_[r], &dev_text, nullptr, &out[r].n_contigs, &bytes, &out[r].n_nodes), t_[r], "result");
+            must(kh_shard_result(t_[r], &dev_text, &dev_off, &out[r].n_contigs, &bytes, &out[r].n_nodes), t_[r], "result");
             out[r].text.resize(bytes);
             must(kh_copy_to_host(t_[r], out[r].text.data(), dev_text, bytes), t_[r], "copy result");
+            if (want_sorted) {
+                out[r].offsets.resize(out[r].n_contigs + 1);
+                must(kh_copy_to_host(t_[r], out[r].offsets.data(), dev_off, (out[r].n_contigs + 1) * sizeof(uint64_t)), t_[r], "copy offsets");
+                out[r].sorted.resize(out[r].n_contigs);
+                must(kh_sorted_order(t_[r], out[r].sorted.data(), nullptr), t_[r], "sorted order");
+            }
         });
         return out;
     }

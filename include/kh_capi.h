@@ -130,7 +130,27 @@ int kh_assemble(kh_table* t, const char** contigs_host, const uint64_t** offsets
 int kh_assemble_device(kh_table* t, const char** contigs_dev, const uint64_t** offsets_dev,
                        uint64_t* n_contigs, uint64_t* contig_bytes, uint64_t* n_nodes);
 
+/* Output side -- `cat test*.dat | sort` of scripts/check_it.sh:47-48 without the host sort: the contigs of the last
+ * kh_assemble / kh_assemble_device / kh_shard_assemble on this handle in bytewise (LC_ALL=C) order of their lines.
+ * The sort runs on the GPU over a 21-character prefix key; contigs that agree on it are ordered on the host.
+ * order_host_out: room for n_contigs indices into the offsets array. */
+int kh_sorted_order(kh_table* t, uint64_t* order_host_out, uint64_t* n_contigs_out);
+
 int kh_get_stats(kh_table* t, kh_stats* out);
+
+/* What a CUDA kernel of the caller needs to use the table directly (include/kh/device_table.cuh: kh::device_find,
+ * kh::device_insert -- the per-k-mer HashMap::insert / find of README.md:95-99 as __device__ functions).  Plain tables
+ * only: returns KH_ERR_ARG for a chunk table (large K >= 30 tables and sharded handles; create with KH_CT=0 to force a
+ * plain one).  The view stays valid until kh_destroy; kh_clear empties the table it points to. */
+typedef struct kh_device_view {
+    void* table;               /* device pointer: n_buckets x 32 bytes                         */
+    uint64_t n_buckets;
+    int32_t k;
+    int32_t slot_bytes;        /* 8 or 16                                                      */
+    int32_t placement_m;       /* internal: minimizer length of the bucket placement (0 = none) */
+    int32_t device;            /* CUDA ordinal that owns the table                             */
+} kh_device_view;
+int kh_get_device_view(kh_table* t, kh_device_view* out);
 const char* kh_last_error(kh_table* t);
 
 /* Pinned host memory for callers that want full-speed host<->device copies. */

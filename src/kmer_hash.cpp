@@ -26,7 +26,9 @@
 #include <cstdio>
 #include <cstdlib>
 #include <stdexcept>
+#include <cstring>
 #include <string>
+#include <thread>
 #include <vector>
 
 #include "butil.hpp"
@@ -60,6 +62,37 @@ kmer_pair* read_and_pack(kh_table* t, const std::string& fname, size_t n_kmers) 
     must(kh_pack_lines(t, static_cast<const char*>(text), n_kmers, pairs), t, "pack_lines");
     kh_host_free(text);
     return static_cast<kmer_pair*>(pairs);
+}
+
+// `cat <prefix>_*.dat | sort` (scripts/check_it.sh:47-48) without the sort: every rank's contigs were sorted on its GPU,
+// the host only merges the P sorted lists
+void write_merged_solution(const char* path, const std::vector<kh_sharded::RankOutput>& outs) {
+    FILE* sol = fopen(path, "w");
+    if (sol == nullptr) throw std::runtime_error(std::string("could not open ") + path);
+    const int P = (int)outs.size();
+    std::vector<size_t> pos(P, 0);
+    auto line = [&](int r, size_t i, const char*& p, size_t& len) {
+        const uint64_t c = outs[r].sorted[i];
+        p = outs[r].text.data() + outs[r].offsets[c];
+        len = (size_t)(outs[r].offsets[c + 1] - outs[r].offsets[c]);
+    };
+    for (;;) {
+        int best = -1;
+        const char* bp = nullptr;
+        size_t bl = 0;
+        for (int r = 0; r < P; ++r) {
+            if (pos[r] >= outs[r].sorted.size()) continue;
+            const char* p; size_t len;
+            line(r, pos[r], p, len);
+            if (best < 0) { best = r; bp = p; bl = len; continue; }
+            const int c = memcmp(p, bp, std::min(len, bl));
+            if (c < 0 || (c == 0 && len < bl)) { best = r; bp = p; bl = len; }
+        }
+        if (best < 0) break;
+        fwrite(bp, 1, bl, sol);
+        ++pos[best];
+    }
+    fclose(sol);
 }
 
 }  // namespace
@@ -126,7 +159,8 @@ int main(int argc, char** argv) {
         cluster.begin();
         cluster.insert(cdev, counts);                              // initialize_kmers (enqueued; the build completes inside assemble)
         const auto insert_time = clock::now();
-        std::vector<kh_sharded::RankOutput> outs = cluster.assemble();   // assemble_contigs
+        const char* solution_path = std::getenv("KH_SOLUTION");
+        std::vector<kh_sharded::RankOutput> outs = cluster.assemble(solution_path != nullptr);   // assemble_contigs
         const auto end_time = clock::now();
         for (void* p : dev) kh_device_free(p);
 
@@ -137,14 +171,21 @@ int main(int argc, char** argv) {
             BUtil::print("Finished inserting in %lf sec\n", insert_duration);
             BUtil::print("Assembled in %lf total\n", total_duration);
         } else {
-            for (int r = 0; r < n_ranks; ++r) {
-                const std::string out_name = test_prefix + "_" + std::to_string(r) + ".dat";
-                FILE* out = fopen(out_name.c_str(), "w");
-                if (out == nullptr) throw std::runtime_error("output_results: could not open " + out_name);
-                if (!outs[r].text.empty() && fwrite(outs[r].text.data(), 1, outs[r].text.size(), out) != outs[r].text.size())
-                    throw std::runtime_error("output_results: short write to " + out_name);
-                fclose(out);
-            }
+            // output_results (kmer_hash.cpp:60-67): every rank's file from its own writer thread
+            std::vector<std::string> werr(n_ranks);
+            std::vector<std::thread> writers;
+            for (int r = 0; r < n_ranks; ++r)
+                writers.emplace_back([&, r] {
+                    const std::string out_name = test_prefix + "_" + std::to_string(r) + ".dat";
+                    FILE* out = fopen(out_name.c_str(), "w");
+                    if (out == nullptr) { werr[r] = "output_results: could not open " + out_name; return; }
+                    if (!outs[r].text.empty() && fwrite(outs[r].text.data(), 1, outs[r].text.size(), out) != outs[r].text.size())
+                        werr[r] = "output_results: short write to " + out_name;
+                    fclose(out);
+                });
+            for (auto& w : writers) w.join();
+            for (const auto& e : werr) if (!e.empty()) throw std::runtime_error(e);
+            if (solution_path) write_merged_solution(solution_path, outs);
             BUtil::print("Rank %d reconstructed %d contigs with %d nodes from %d start nodes. "
                          "(%lf read, %lf insert, %lf total)\n",
                          0, (int)outs[0].n_contigs, (int)outs[0].n_nodes, 0, assembly_duration, insert_duration, total_duration);
@@ -196,6 +237,14 @@ int main(int argc, char** argv) {
         if (contig_bytes && fwrite(contig_text, 1, contig_bytes, out) != contig_bytes)
             throw std::runtime_error("output_results: short write to " + out_name);
         fclose(out);
+        if (const char* solution_path = std::getenv("KH_SOLUTION")) {       // the sorted contig set (check_it.sh:47-48), sorted on the GPU
+            std::vector<uint64_t> order(n_contigs);
+            must(kh_sorted_order(t, order.data(), nullptr), t, "sorted order");
+            FILE* sol = fopen(solution_path, "w");
+            if (sol == nullptr) throw std::runtime_error(std::string("could not open ") + solution_path);
+            for (uint64_t c : order) fwrite(contig_text + offsets[c], 1, offsets[c + 1] - offsets[c], sol);
+            fclose(sol);
+        }
         // same line as kmer_hash.cpp:71-78, including its quirks: "start nodes" is a literal 0
         // and the slot labelled "read" carries the assembly time
         BUtil::print("Rank %d reconstructed %d contigs with %d nodes from %d start nodes. "

@@ -19,14 +19,16 @@ def bins():
 
 
 @pytest.mark.parametrize("k,n,c", [(19, 200000, 300), (31, 100000, 900), (51, 150000, 1500)])
-def test_check_script_passes(bins, tmp_path, k, n, c):
+@pytest.mark.parametrize("gpu_sort", [False, True])
+def test_check_script_passes(bins, tmp_path, k, n, c, gpu_sort):
     """tools/check.sh = scripts/check_it.sh:32,47-59 around our binary: sorted output == solution."""
     gen = os.path.join(ROOT, "tools", "gen_kmers")
     if not os.path.exists(gen):
         kmergen.build()
     inp = tmp_path / "synth.txt"
     subprocess.run([gen, str(k), str(n), str(c), str(inp), "--seed", "11"], check=True, capture_output=True)
-    r = subprocess.run([os.path.join(ROOT, "tools", "check.sh"), str(inp)], cwd=tmp_path, capture_output=True, text=True)
+    env = dict(os.environ, KH_GPU_SORT="1") if gpu_sort else dict(os.environ)
+    r = subprocess.run([os.path.join(ROOT, "tools", "check.sh"), str(inp)], cwd=tmp_path, capture_output=True, text=True, env=env)
     assert r.returncode == 0, r.stdout + r.stderr
     assert f"PASSED: {inp}" in r.stdout
     # the metrics line of test mode, format of kmer_hash.cpp:71-78
@@ -129,3 +131,32 @@ def test_header_api_find_and_hashmap(tmp_path, k, case):
                     "-o", str(exe)], check=True, capture_output=True)
     r = subprocess.run([str(exe), os.path.join(ROOT, "tests", "golden", case + ".txt")], capture_output=True, text=True, timeout=600)
     assert r.returncode == 0 and r.stdout.startswith("OK"), r.stdout + r.stderr
+
+
+@pytest.mark.parametrize("k,ranks", [(19, 1), (51, 1), (51, 3), (19, 2)])
+def test_cli_writes_the_sorted_solution_itself(bins, tmp_path, k, ranks):
+    """Output side (scripts/check_it.sh:47-48, `cat test*.dat | sort`): with KH_SOLUTION the binary sorts every rank's
+    contigs on its GPU (kh_sorted_order), merges the per-rank lists and writes the file check_it.sh would diff."""
+    d = kmergen.Dataset(k, 120_000, 900, seed=40 + k + ranks)
+    inp = tmp_path / "in.txt"
+    d.text().tofile(inp)
+    env = dict(os.environ, KH_SOLUTION=str(tmp_path / "sol.txt"), KH_RANKS=str(ranks))
+    subprocess.run([bins[k], str(inp), "test", "so"], cwd=tmp_path, check=True, capture_output=True, env=env)
+    lines = b"".join((tmp_path / f"so_{r}.dat").read_bytes() for r in range(ranks)).splitlines(keepends=True)
+    assert (tmp_path / "sol.txt").read_bytes() == b"".join(sorted(lines)) == d.solution()      # the generator's sorted solution file
+
+
+def test_sorted_order_breaks_ties_behind_the_prefix_key(tmp_path):
+    """kh_sorted_order sorts a 21-character prefix key on the GPU; contigs that agree on it are finished on the host."""
+    from cs267_hw3_b200 import build as b
+    k = 23
+    exe = b.build_cli(ks=(k,))[0]
+    p = "ACGTTGCAAGGCTTACGATCGA"                                    # 22 bases shared by all three contigs
+    kmers = [p + "T", p + "C", p + "G", "T" * 22 + "A", "A" * 23]
+    text = "".join(f"{x} FF\n" for x in kmers)
+    inp = tmp_path / "ties.txt"
+    inp.write_text(text)
+    env = dict(os.environ, KH_SOLUTION=str(tmp_path / "sol.txt"))
+    subprocess.run([exe, str(inp), "test", "ti"], cwd=tmp_path, check=True, capture_output=True, env=env)
+    assert (tmp_path / "sol.txt").read_text().split() == sorted(kmers)
+    assert (tmp_path / "ti_0.dat").read_text().split() == kmers

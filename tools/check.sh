@@ -4,6 +4,9 @@
 # taken from the file instead of being hard-coded to 19.
 #
 #   tools/check.sh <input_file.txt>         expects <dir>/<root>_solution.txt next to the input
+#   KH_GPU_SORT=1 tools/check.sh <input>     the binary also writes the sorted contig set itself (KH_SOLUTION: contigs
+#                                            sorted on the GPU, per-rank lists merged on the host) -- no `sort` here
+#   KH_RANKS=N tools/check.sh <input>        N ranks (GPUs), N files test_0.dat .. test_<N-1>.dat, as `srun -n N` gives
 #
 # Steps kept verbatim: remove old test_*.dat (:32), run in `test` mode, `cat test_*.dat | sort`
 # into <root>_test.txt (:47-48), `diff -q` against the solution, print PASSED/FAILED (:55-59).
@@ -24,13 +27,16 @@ if [ ! -x "$BIN" ]; then
     exit 1
 fi
 rm -f test_*.dat
+if [ -n "$KH_GPU_SORT" ]; then export KH_SOLUTION="$OUTPUT_FILE"; fi
 CMD="$BIN $INPUT_FILE test"
 echo "Running command: $CMD"
 if ! eval "$CMD"; then
     echo "ERROR: Execution failed."
     exit 1
 fi
-if ls test_*.dat 1> /dev/null 2>&1; then
+if [ -n "$KH_GPU_SORT" ] && [ -f "$OUTPUT_FILE" ]; then
+    :                                        # already sorted by the binary
+elif ls test_*.dat 1> /dev/null 2>&1; then
     cat test_*.dat | LC_ALL=C sort > "$OUTPUT_FILE"
 else
     echo "ERROR: Missing output files from ranks"
