@@ -1,7 +1,7 @@
 # Build without Python: the CUDA library, the reference's CLI per K, the generator.  Same flags as
 # cs267_hw3_b200/build.py and tools/kmergen.py (those are what __graft_entry__.build() and the tests use).
 #
-#   make                 libkh_b200.so + kmer_hash_19 kmer_hash_31 kmer_hash_51 + tools/gen_kmers
+#   make                 libkh_b200.so + kmer_hash_19 kmer_hash_31 kmer_hash_51 + kmer_count + tools/gen_kmers
 #   make KS="21 27"      other k-mer lengths (2..61)
 #   make check           CPU test suite;  make check-gpu  the GPU parity suite (needs a B200)
 NVCC      ?= nvcc
@@ -16,13 +16,16 @@ CSRC := $(wildcard $(PKG)/csrc/*.cu $(PKG)/csrc/*.cuh)
 HDRS := $(wildcard include/*.h include/*.hpp include/kh/*.hpp)
 CLIS := $(addprefix kmer_hash_,$(KS))
 
-all: $(LIB) $(CLIS) tools/gen_kmers tools/libkmergen.so
+all: $(LIB) $(CLIS) kmer_count tools/gen_kmers tools/libkmergen.so
 
 $(LIB): $(CSRC) include/kh_capi.h
-	$(NVCC) $(NVCCFLAGS) -Xcompiler -fPIC -shared $(PKG)/csrc/capi.cu -o $@
+	$(NVCC) $(NVCCFLAGS) -Xcompiler -fPIC -shared $(PKG)/csrc/capi.cu $(PKG)/csrc/count.cu -o $@
 
 kmer_hash_%: src/kmer_hash.cpp $(HDRS) $(LIB)
 	$(CXX) $(CXXFLAGS) -DKMER_LEN=$* -Iinclude $< -L$(PKG) -lkh_b200 -Wl,-rpath,$(abspath $(PKG)) -o $@
+
+kmer_count: src/kmer_count.cpp include/kh_capi.h include/kh/kmer_counter.hpp $(LIB)
+	$(CXX) $(CXXFLAGS) -Iinclude $< -L$(PKG) -lkh_b200 -Wl,-rpath,$(abspath $(PKG)) -o $@
 
 tools/gen_kmers: tools/kmer_gen.cpp
 	$(CXX) $(CXXFLAGS) -DKG_MAIN $< -o $@
@@ -37,6 +40,6 @@ check-gpu:
 	python -m pytest tests -q -m gpu
 
 clean:
-	rm -f $(LIB) $(CLIS) tools/gen_kmers tools/libkmergen.so
+	rm -f $(LIB) $(CLIS) kmer_count tools/gen_kmers tools/libkmergen.so
 
 .PHONY: all check check-gpu clean

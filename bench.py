@@ -467,6 +467,14 @@ def run_b200_arm(args, workload: str) -> dict | None:
             s2 = measure_shape_n1(args, w, max(3, min(args.steps, 5)), 3, local_rank, full=False)
             line["shapes"][w] = {k2: s2[k2] for k2 in ("value", "ms_per_step", "stages_ms", "e2e", "verified", "roofline", "config",
                                                        "n_segments", "rank_rounds", "gpu_launches")}
+    if args.workload is None and not args.n and not args.no_count:
+        # SURVEY.md 8(f)-4, a secondary record: the stage BEFORE the timed one (reads -> unique k-mers with extensions,
+        # csrc/count.cu) on a bounded sample of the same contig shape; never fail the bench line over it
+        try:
+            from tools import count_bench
+            line["kmer_analysis"] = count_bench.run(k=k, n=4_000_000, coverage=8, read_len=150)
+        except Exception as e:
+            line["kmer_analysis"] = {"error": str(e)}
     if not args.no_cpu_baseline:
         line["cpu_baseline"] = cpu_baseline_leg(k, workload)
     else:
@@ -495,6 +503,7 @@ def main():
     ap.add_argument("--load-factor", type=float, default=0.5)
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-e2e", action="store_true", help="skip the host-buffer leg (profiling runs)")
+    ap.add_argument("--no-count", action="store_true", help="skip the k-mer analysis sub-record (reads -> k-mers)")
     ap.add_argument("--also", nargs="*", default=None, choices=sorted(WORKLOADS),
                     help="further workloads measured in the same run and reported under \"shapes\" (default: chr14_k19)")
     ap.add_argument("--scaling", default="strong", choices=["strong", "weak"],

@@ -33,6 +33,9 @@ ABI_SYMBOLS = [
     "kh_shard_begin", "kh_shard_insert", "kh_shard_assemble", "kh_shard_assemble_parts", "kh_shard_assemble_part",
     "kh_shard_finish", "kh_shard_result", "kh_debug_buffer", "kh_get_device_view", "kh_sorted_order",
     "kh_device_alloc", "kh_device_alloc_on", "kh_device_free", "kh_copy_to_host", "kh_copy_device",
+    # k-mer analysis (reads -> k-mers with extensions), the stage before this one
+    "kh_count_create", "kh_count_destroy", "kh_count_clear", "kh_count_reads", "kh_count_reads_device",
+    "kh_count_extract", "kh_count_extract_device", "kh_count_extract_lines", "kh_count_lookup", "kh_count_get_stats", "kh_count_last_error",
 ]
 
 
@@ -51,6 +54,17 @@ class Stats(C.Structure):
         ("ms_insert", C.c_float), ("ms_assemble", C.c_float), ("ms_walk", C.c_float),
         ("ms_rank", C.c_float), ("ms_emit", C.c_float), ("ms_pack", C.c_float), ("ms_clear", C.c_float),
         ("ms_build", C.c_float), ("ms_stage", C.c_float), ("n_launches", C.c_uint64),
+    ]
+
+    def as_dict(self) -> dict:
+        return {n: getattr(self, n) for n, _ in self._fields_}
+
+
+class CountStats(C.Structure):
+    _fields_ = [
+        ("n_slots", C.c_uint64), ("n_distinct", C.c_uint64), ("n_occurrences", C.c_uint64), ("n_bytes", C.c_uint64),
+        ("n_reported", C.c_uint64), ("slot_bytes", C.c_uint32), ("n_launches", C.c_uint32),
+        ("ms_count", C.c_float), ("ms_extract", C.c_float),
     ]
 
     def as_dict(self) -> dict:
@@ -99,6 +113,24 @@ def lib() -> C.CDLL:
     L.kh_host_alloc.argtypes = [C.POINTER(vp), u64]
     L.kh_host_free.argtypes = [vp]
     L.kh_measure_random_sector_rate.argtypes = [i32, u64, u64, C.POINTER(C.c_double)]
+    L.kh_device_alloc.argtypes = [C.POINTER(vp), u64]
+    L.kh_device_alloc_on.argtypes = [i32, C.POINTER(vp), u64]
+    L.kh_device_free.argtypes = [vp]
+    L.kh_copy_to_host.argtypes = [vp, vp, vp, u64]
+    L.kh_copy_device.argtypes = [vp, vp, vp, u64]
+    u32 = C.c_uint32
+    L.kh_count_create.argtypes = [i32, u64, C.c_double, i32, C.POINTER(vp)]
+    L.kh_count_destroy.argtypes = [vp]
+    L.kh_count_clear.argtypes = [vp]
+    L.kh_count_reads.argtypes = [vp, vp, u64]
+    L.kh_count_reads_device.argtypes = [vp, vp, u64]
+    L.kh_count_extract.argtypes = [vp, u32, u32, vp, u64, pu64]
+    L.kh_count_extract_device.argtypes = [vp, u32, u32, C.POINTER(vp), pu64]
+    L.kh_count_extract_lines.argtypes = [vp, u32, u32, vp, u64, pu64]
+    L.kh_count_lookup.argtypes = [vp, vp, u64, vp]
+    L.kh_count_get_stats.argtypes = [vp, C.POINTER(CountStats)]
+    L.kh_count_last_error.argtypes = [vp]
+    L.kh_count_last_error.restype = C.c_char_p
     _lib = L
     return L
 
@@ -269,3 +301,85 @@ class KmerHashTable:
         nc, nb, nn = C.c_uint64(), C.c_uint64(), C.c_uint64()
         self._check(lib().kh_assemble_device(self._h, C.byref(cp), C.byref(op), C.byref(nc), C.byref(nb), C.byref(nn)))
         return cp.value, op.value, nc.value, nb.value, nn.value
+
+
+class KmerCounter:
+    """k-mer analysis on one GPU (a `kh_counter*`): reads -> unique k-mers with their backward / forward extensions,
+    the stage whose output the reference reads from text (README.md:19-21, read_kmers.hpp:54-79)."""
+
+    def __init__(self, k: int, n_distinct_expected: int, load_factor: float = 0.5, device: int = 0):
+        self.k = k
+        self._h = C.c_void_p()
+        rc = lib().kh_count_create(k, n_distinct_expected, load_factor, device, C.byref(self._h))
+        if rc != KH_OK:
+            raise KhError(rc, "kh_count_create: " + lib().kh_status_string(rc).decode())
+
+    def _check(self, rc: int) -> None:
+        if rc != KH_OK:
+            msg = lib().kh_count_last_error(self._h).decode() or lib().kh_status_string(rc).decode()
+            raise KhError(rc, msg)
+
+    def close(self) -> None:
+        if self._h:
+            lib().kh_count_destroy(self._h)
+            self._h = C.c_void_p()
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    def __enter__(self):
+        return self
+
+    def __exit__(self, *a):
+        self.close()
+
+    def clear(self) -> None:
+        self._check(lib().kh_count_clear(self._h))
+
+    def count_reads(self, reads) -> None:
+        r = np.frombuffer(reads, dtype=np.uint8) if not isinstance(reads, np.ndarray) else np.ascontiguousarray(reads)
+        self._check(lib().kh_count_reads(self._h, r.ctypes.data, r.size))
+
+    def count_reads_ptr(self, host_ptr: int, n_bytes: int) -> None:
+        self._check(lib().kh_count_reads(self._h, host_ptr, n_bytes))
+
+    def count_reads_device(self, dev_ptr: int, n_bytes: int) -> None:
+        self._check(lib().kh_count_reads_device(self._h, dev_ptr, n_bytes))
+
+    def extract(self, min_count: int = 2, min_ext: int = 2) -> np.ndarray:
+        """kmer_pair records of the reported k-mers, shape (n, pair_bytes), in table order."""
+        n = C.c_uint64()
+        self._check(lib().kh_count_extract(self._h, min_count, min_ext, None, 0, C.byref(n)))
+        out = np.empty((n.value, pair_bytes(self.k)), dtype=np.uint8)
+        self._check(lib().kh_count_extract(self._h, min_count, min_ext, out.ctypes.data, n.value, C.byref(n)))
+        return out
+
+    def extract_device(self, min_count: int = 2, min_ext: int = 2) -> tuple[int, int]:
+        """(device pointer to the records, number of records); the buffer belongs to the counter."""
+        p, n = C.c_void_p(), C.c_uint64()
+        self._check(lib().kh_count_extract_device(self._h, min_count, min_ext, C.byref(p), C.byref(n)))
+        return p.value or 0, n.value
+
+    def extract_lines(self, min_count: int = 2, min_ext: int = 2) -> np.ndarray:
+        """The reported k-mers in the reference's k-mer file format (uint8 buffer of (K+4)-byte lines)."""
+        n = C.c_uint64()
+        self._check(lib().kh_count_extract_lines(self._h, min_count, min_ext, None, 0, C.byref(n)))
+        out = np.empty(n.value * (self.k + 4), dtype=np.uint8)
+        self._check(lib().kh_count_extract_lines(self._h, min_count, min_ext, out.ctypes.data, n.value, C.byref(n)))
+        return out
+
+    def lookup(self, pkmers) -> np.ndarray:
+        """uint32 (n, 9): occurrences, backward A C G T, forward A C G T of the given packed k-mers."""
+        q = np.ascontiguousarray(pkmers, dtype=np.uint8)
+        n = q.size // packed_bytes(self.k)
+        out = np.zeros((n, 9), dtype=np.uint32)
+        self._check(lib().kh_count_lookup(self._h, q.ctypes.data, n, out.ctypes.data))
+        return out
+
+    def stats(self) -> dict:
+        s = CountStats()
+        self._check(lib().kh_count_get_stats(self._h, C.byref(s)))
+        return s.as_dict()

@@ -38,7 +38,9 @@ def lib_sources() -> list[str]:
 
 def build_lib(force: bool = False) -> str:
     if force or _stale(LIB, lib_sources()):
-        _run([_nvcc(), *NVCC_FLAGS, "-Xcompiler", "-fPIC", "-shared", os.path.join(CSRC, "capi.cu"), "-o", LIB])
+        # two translation units: capi.cu (tables, traversal, multi-GPU) and count.cu (k-mer analysis)
+        _run([_nvcc(), *NVCC_FLAGS, "-Xcompiler", "-fPIC", "-shared", os.path.join(CSRC, "capi.cu"),
+              os.path.join(CSRC, "count.cu"), "-o", LIB])
     return LIB
 
 
@@ -57,7 +59,20 @@ def build_cli(ks=(19, 31, 51), force: bool = False) -> list[str]:
     return outs
 
 
+def build_count_cli(force: bool = False) -> str:
+    """kmer_count: reads -> the reference's k-mer file (or straight to contigs); K is a run-time argument."""
+    build_lib(force)
+    src = os.path.join(ROOT, "src", "kmer_count.cpp")
+    hdrs = [os.path.join(ROOT, "include", "kh_capi.h"), os.path.join(ROOT, "include", "kh", "kmer_counter.hpp")]
+    out = os.path.join(ROOT, "kmer_count")
+    if force or _stale(out, [src, LIB, *hdrs]):
+        _run(["g++", "-O2", "-std=c++17", "-pthread", "-I" + os.path.join(ROOT, "include"), src,
+              "-L" + PKG, "-lkh_b200", "-Wl,-rpath," + PKG, "-o", out])
+    return out
+
+
 if __name__ == "__main__":
     print(build_lib(force=True))
     if os.path.exists(os.path.join(ROOT, "src", "kmer_hash.cpp")):
         print("\n".join(build_cli(force=True)))
+        print(build_count_cli(force=True))

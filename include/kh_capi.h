@@ -207,6 +207,57 @@ int kh_shard_finish(kh_table* t, int* error_bits_out);
 int kh_shard_result(kh_table* t, const char** contigs_dev, const uint64_t** offsets_dev,
                     uint64_t* n_contigs, uint64_t* contig_bytes, uint64_t* n_nodes);
 
+/* ---------------------------------------------------------------------------------------------
+ * k-mer analysis -- the stage BEFORE this one: reads -> unique k-mers with their backward / forward
+ * extensions (README.md:19-21: "the output of this first preprocessing stage ... is a set of unique DNA
+ * sequence fragments of length k", each "associated with a forward and backward extension").  The
+ * reference only ever reads that output from a text file (read_kmers.hpp:54-79); here it is produced on
+ * the GPU, in the reference's kmer_pair bytes, so it can go straight into kh_insert_pairs_device.
+ *
+ * Input: a byte buffer of reads.  'A' 'C' 'G' 'T' are bases, every other byte ('\n', 'N', ...) separates
+ * reads; each call's buffer is taken to begin and end at a read boundary.  Every position whose K bytes are
+ * bases is one occurrence of that k-mer; the byte before / after it, when it is a base, is its backward /
+ * forward observation.  Per distinct k-mer the table keeps saturating counters: occurrences (<= 255) and, per
+ * side and base, observations (<= 127).  kh_count_extract reports the k-mers with occurrences >= min_count
+ * (1..255); an extension is the base that alone reaches min_ext (1..127) on its side, 'F' when none does
+ * (a contig begins / ends: README.md:37) or several do (a fork).  No reverse complements, like the reference
+ * (kmer_t.hpp:51-57).  Records come out in table order (arbitrary, as k-mer counters' output is).
+ * One GPU per counter; supported K: 2..61.
+ * ------------------------------------------------------------------------------------------- */
+typedef struct kh_counter kh_counter;
+typedef struct kh_count_stats {
+    uint64_t n_slots;          /* table capacity (one k-mer per slot)                              */
+    uint64_t n_distinct;       /* distinct k-mers seen since create / clear                        */
+    uint64_t n_occurrences;    /* k-mer occurrences counted since create / clear                   */
+    uint64_t n_bytes;          /* read bytes consumed since create / clear                         */
+    uint64_t n_reported;       /* records of the last kh_count_extract*                            */
+    uint32_t slot_bytes;       /* 16 (K <= 31) or 32 (one DRAM sector)                             */
+    uint32_t n_launches;       /* kernels launched since create                                    */
+    float ms_count;            /* last kh_count_reads*: first byte in .. last kernel out (CUDA events) */
+    float ms_extract;          /* last kh_count_extract*: the extract kernel                       */
+} kh_count_stats;
+/* n_distinct_expected counts EVERY distinct k-mer of the reads, erroneous ones included; the table holds
+ * n_distinct_expected / load_factor slots and does not grow (KH_ERR_TABLE_FULL from the next call on). */
+int kh_count_create(int k, uint64_t n_distinct_expected, double load_factor, int device, kh_counter** out);
+int kh_count_destroy(kh_counter* c);
+int kh_count_clear(kh_counter* c);
+int kh_count_reads(kh_counter* c, const char* reads_host, uint64_t n_bytes);         /* may be called repeatedly */
+int kh_count_reads_device(kh_counter* c, const char* reads_dev, uint64_t n_bytes);  /* enqueues on the counter's stream */
+/* kmer_pair records (kh_pair_bytes(k) each) of the reported k-mers.  _device: *pairs_dev_out is owned by the
+ * counter and valid until its next extract, clear or destroy.  Host variant: pairs_host_out may be NULL to
+ * learn *n_out only; with capacity < *n_out nothing is copied and KH_ERR_ARG is returned (*n_out is set). */
+int kh_count_extract_device(kh_counter* c, uint32_t min_count, uint32_t min_ext, const void** pairs_dev_out, uint64_t* n_out);
+int kh_count_extract(kh_counter* c, uint32_t min_count, uint32_t min_ext, void* pairs_host_out, uint64_t capacity, uint64_t* n_out);
+/* The same k-mers as lines of the reference's k-mer file -- K bases, a blank, backward and forward extension, '\n'
+ * (K + 4 bytes each; what read_kmers parses, read_kmers.hpp:64-76): the reference's input file, written from reads.
+ * lines_host_out may be NULL to learn *n_out; capacity_lines counts lines. */
+int kh_count_extract_lines(kh_counter* c, uint32_t min_count, uint32_t min_ext, char* lines_host_out, uint64_t capacity_lines, uint64_t* n_out);
+/* The counters of n given k-mers (pkmer_t bytes): 9 x uint32 each -- occurrences, backward A C G T, forward A C G T;
+ * all zero for a k-mer that was never seen. */
+int kh_count_lookup(kh_counter* c, const void* pkmers_host, uint64_t n, uint32_t* counts_host_out);
+int kh_count_get_stats(kh_counter* c, kh_count_stats* out);
+const char* kh_count_last_error(kh_counter* c);
+
 /* Introspection for tests and debugging: device pointer and capacity of an internal buffer of a chunk table
  * ("link", "meta", "chunk_base", "seg_base", "chunk_cursor", "counters", ...; "caps" returns HOST numbers). */
 int kh_debug_buffer(kh_table* t, const char* name, void** ptr_out, uint64_t* bytes_out);

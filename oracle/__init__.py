@@ -17,7 +17,7 @@ HERE = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.path.join(HERE, "libkmer_oracle.so")
 REF_DIR = os.path.join(HERE, "_ref")
 
-ERRORS = {1: "bad argument", 2: "k-mer not found", 3: "allocation", 4: "cycle", 5: "bad base"}
+ERRORS = {1: "bad argument", 2: "k-mer not found", 3: "allocation", 4: "cycle", 5: "bad base", 6: "capacity"}
 
 
 def build(verbose: bool = False) -> None:
@@ -35,7 +35,8 @@ _lib = None
 def lib() -> C.CDLL:
     global _lib
     if _lib is None:
-        if not os.path.exists(LIB_PATH):
+        srcs = [os.path.join(HERE, f) for f in ("kmer_oracle.c", "kmer_count_oracle.c")]
+        if not os.path.exists(LIB_PATH) or any(os.path.getmtime(f) > os.path.getmtime(LIB_PATH) for f in srcs):
             build()
         L = C.CDLL(LIB_PATH)
         u8p, u64, vp = C.POINTER(C.c_uint8), C.c_uint64, C.c_void_p
@@ -53,6 +54,9 @@ def lib() -> C.CDLL:
         L.ko_insert_pairs.argtypes = [vp, vp, u64]
         L.ko_find.argtypes = [vp, u8p, u8p]
         L.ko_assemble.argtypes = [vp, vp, u64, vp, u64, C.POINTER(u64), C.POINTER(u64), C.POINTER(u64)]
+        L.kco_count_occurrences.argtypes = [vp, u64, C.c_int]
+        L.kco_count_occurrences.restype = u64
+        L.kco_analyse.argtypes = [vp, u64, C.c_int, C.c_uint32, C.c_uint32, vp, u64, C.POINTER(u64), vp]
         _lib = L
     return _lib
 
@@ -159,6 +163,22 @@ def assemble_text(text: bytes | np.ndarray, k: int, nranks: int = 1):
         outs.append(tab.assemble(pairs[lo:hi])[0])
     tab.close()
     return outs
+
+
+# ---- the k-mer analysis stage that precedes the reference's path (oracle/kmer_count_oracle.c) ----------
+
+def analyse_reads(reads: bytes | np.ndarray, k: int, min_count: int = 2, min_ext: int = 2):
+    """reads (any byte outside ACGT separates them) -> (records sorted by k-mer, shape (n, pair_bytes);
+    counters uint32 (n, 9): occurrences, backward A C G T, forward A C G T; number of occurrences in the reads)."""
+    r = np.frombuffer(reads, dtype=np.uint8) if not isinstance(reads, np.ndarray) else np.ascontiguousarray(reads)
+    n_occ = int(lib().kco_count_occurrences(r.ctypes.data, r.size, k))
+    n = C.c_uint64()
+    _check(lib().kco_analyse(r.ctypes.data, r.size, k, min_count, min_ext, None, 0, C.byref(n), None), "analyse(size)")
+    pairs = np.empty((n.value, pair_bytes(k)), dtype=np.uint8)
+    counts = np.empty((n.value, 9), dtype=np.uint32)
+    _check(lib().kco_analyse(r.ctypes.data, r.size, k, min_count, min_ext, pairs.ctypes.data, n.value, C.byref(n),
+                             counts.ctypes.data), "analyse")
+    return pairs, counts, n_occ
 
 
 # ---- the unmodified reference, compiled (oracle/_ref) -------------------------------------
