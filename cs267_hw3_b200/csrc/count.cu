@@ -2,9 +2,10 @@
 // backward / forward extensions, as kmer_pair records in device memory.  The algorithm and the table format are in
 // count_core.cuh; this file holds the three kernels and the host runtime.
 //
-//   kc_count_kernel    a block packs a tile of 2048 read characters (+ halo) to 2 bits each in shared memory; every thread
-//                      cuts 8 k-mers with their two neighbour characters out of the packed stream (five LDS + funnel
-//                      shifts each, whatever K is) and counts them: one sector read + one CAS on the counter word
+//   kc_count_kernel    a block packs a tile of 2048 read characters (+ halo) to 2 bits each in shared memory, lists the
+//                      positions that hold a k-mer, and its threads cut the k-mers with their two neighbour characters
+//                      out of the packed stream (five LDS + funnel shifts each, whatever K is) and count them: one
+//                      sector read + one CAS on the counter word
 //   kc_extract_kernel  table scan -> kmer_pair records of the k-mers with enough occurrences (block-wise compaction)
 //   kc_lookup_kernel   counters of given k-mers
 //
@@ -12,6 +13,7 @@
 // read and written back.  Algorithmic bytes per occurrence = 1 (the character) + 64.
 #include <algorithm>
 #include <cstdio>
+#include <cstdlib>
 #include <cstring>
 #include <string>
 
@@ -26,44 +28,82 @@ constexpr u64 kKcChunk = 64ull << 20;                       // positions per hos
 constexpr u64 kKcHalo = 16 + 64;                            // bytes around a chunk: 16 before (keeps the alignment), 64 behind
 }  // namespace
 
-template <int W>
-__global__ void __launch_bounds__(kKcThreads)
+// Pass 1 compacts the tile's positions that hold a k-mer into a list (reads end every ~150 characters and K - 1
+// positions before every end hold none: a third of the lanes would idle through the table code otherwise); pass 2 runs
+// over the list with full warps (2.22 -> 1.69 ms for 52.7 M occurrences of 51-mers).  PF (off by default): the slot of a
+// thread's next occurrence is prefetched into L2 one iteration ahead -- measured, no gain: the kernel is issue-bound.
+template <int W, bool PF, int MINB>
+__global__ void __launch_bounds__(kKcThreads, MINB)
 kc_count_kernel(const unsigned char* __restrict__ buf, u64 n, u64 p_begin, u64 p_end, u64* __restrict__ table, u64 n_slots, int k,
                 KcCounters* ctr) {
     __shared__ u32 s_code[kKcWords], s_inv[kKcWords];
-    __shared__ u32 s_occ, s_fresh, s_err;
+    __shared__ unsigned short s_list[kKcTile];
+    __shared__ u32 s_n, s_fresh, s_fail;
     const u64 t0 = (p_begin & ~15ull) + (u64)blockIdx.x * kKcTile;
-    if (threadIdx.x == 0) { s_occ = 0; s_fresh = 0; s_err = 0; }
+    if (threadIdx.x == 0) { s_n = 0; s_fresh = 0; s_fail = 0; }
     for (u32 i = threadIdx.x; i < kKcWords; i += kKcThreads)
         kc_pack_word(buf, n, (long long)t0 - 16 + 16ll * (long long)i, s_code[i], s_inv[i]);
     __syncthreads();
-    u32 occ = 0, fresh = 0, err = 0;
-#pragma unroll 1
+    const u32 lane = threadIdx.x & 31u;
+#pragma unroll
     for (int r = 0; r < kKcPer; ++r) {
         const u32 local = threadIdx.x + (u32)r * kKcThreads;
         const u64 p = t0 + local;
-        if (p < p_begin || p >= p_end) continue;
-        const KcOcc o = kc_position(s_code, s_inv, local, k);
-        if (!o.valid) continue;
-        bool f;
-        if (!kc_upsert<W>(table, n_slots, o, f)) { err |= kKcErrFull; continue; }
-        ++occ;
-        fresh += f ? 1u : 0u;
+        const bool ok = p >= p_begin && p < p_end && kc_kmer_valid(s_inv, local, k);
+        const u32 bal = __ballot_sync(kFull, ok);
+        u32 base = 0;
+        if (lane == 0 && bal) base = atomicAdd(&s_n, (u32)__popc(bal));
+        base = __shfl_sync(kFull, base, 0);
+        if (ok) s_list[base + (u32)__popc(bal & ((1u << lane) - 1u))] = (unsigned short)local;
+    }
+    __syncthreads();
+    const u32 cnt = s_n;
+    u32 fresh = 0, fail = 0;
+    if (!PF) {
+#pragma unroll 1
+        for (u32 i = threadIdx.x; i < cnt; i += kKcThreads) {
+            const KcOcc o = kc_position(s_code, s_inv, s_list[i], k);
+            bool f;
+            if (kc_upsert<W>(table, n_slots, o, kc_home(o.key_hi, o.key_lo, n_slots), f)) fresh += f ? 1u : 0u;
+            else ++fail;
+        }
+    } else {
+        u32 i = threadIdx.x;
+        KcOcc o = {};
+        u64 home = 0;
+        if (i < cnt) {
+            o = kc_position(s_code, s_inv, s_list[i], k);
+            home = kc_home(o.key_hi, o.key_lo, n_slots);
+            asm volatile("prefetch.global.L2 [%0];" ::"l"(table + home * (u64)KcSlot<W>::kWords));
+        }
+#pragma unroll 1
+        while (i < cnt) {
+            const u32 i2 = i + kKcThreads;
+            KcOcc o2 = {};
+            u64 home2 = 0;
+            if (i2 < cnt) {
+                o2 = kc_position(s_code, s_inv, s_list[i2], k);
+                home2 = kc_home(o2.key_hi, o2.key_lo, n_slots);
+                asm volatile("prefetch.global.L2 [%0];" ::"l"(table + home2 * (u64)KcSlot<W>::kWords));
+            }
+            bool f;
+            if (kc_upsert<W>(table, n_slots, o, home, f)) fresh += f ? 1u : 0u;
+            else ++fail;
+            o = o2; home = home2; i = i2;
+        }
     }
     __syncwarp();
-    occ = __reduce_add_sync(kFull, occ);
     fresh = __reduce_add_sync(kFull, fresh);
-    err = __reduce_or_sync(kFull, err);
-    if ((threadIdx.x & 31u) == 0) {
-        if (occ) atomicAdd(&s_occ, occ);
+    fail = __reduce_add_sync(kFull, fail);
+    if (lane == 0) {
         if (fresh) atomicAdd(&s_fresh, fresh);
-        if (err) atomicOr(&s_err, err);
+        if (fail) atomicAdd(&s_fail, fail);
     }
     __syncthreads();
     if (threadIdx.x == 0) {
-        if (s_occ) atomicAdd(&ctr->n_occurrences, (u64)s_occ);
+        if (cnt > s_fail) atomicAdd(&ctr->n_occurrences, (u64)(cnt - s_fail));
         if (s_fresh) atomicAdd(&ctr->n_distinct, (u64)s_fresh);
-        if (s_err) atomicOr(&ctr->errors, s_err);
+        if (s_fail) atomicOr(&ctr->errors, kKcErrFull);
     }
 }
 
@@ -166,6 +206,8 @@ struct kh_counter {
     u32 n_launches = 0;
     float ms_count = 0.f, ms_extract = 0.f;
     bool have_count = false;
+    bool prefetch = false;            // KH_COUNT_PREFETCH=1: software prefetch of the next occurrence's slot (measured: no gain, the kernel is issue-bound)
+    int min_blocks = 8;               // KH_COUNT_BLOCKS=6: 128-bit keys at 40 registers / 6 blocks per SM instead of 32 / 8
     std::string err;
 };
 
@@ -212,10 +254,16 @@ int kc_launch_count(kh_counter* c, const unsigned char* buf, u64 n, u64 p_begin,
     const u64 span = p_end - (p_begin & ~15ull);
     const u64 blocks = (span + kKcTile - 1) / kKcTile;
     if (blocks > 0x7FFFFFFFull) return kc_fail(c, KH_ERR_ARG, "kh_count_reads_device: at most 2^42 bytes per call");
-    if (c->W == 1)
-        kc_count_kernel<1><<<(unsigned)blocks, kKcThreads, 0, c->stream>>>(buf, n, p_begin, p_end, c->table, c->n_slots, c->k, c->d_ctr);
-    else
-        kc_count_kernel<2><<<(unsigned)blocks, kKcThreads, 0, c->stream>>>(buf, n, p_begin, p_end, c->table, c->n_slots, c->k, c->d_ctr);
+    const unsigned g = (unsigned)blocks;
+#define KC_LAUNCH(W_, PF_, MB_) kc_count_kernel<W_, PF_, MB_><<<g, kKcThreads, 0, c->stream>>>(buf, n, p_begin, p_end, c->table, c->n_slots, c->k, c->d_ctr)
+    if (c->W == 1) {
+        if (c->prefetch) KC_LAUNCH(1, true, 8); else KC_LAUNCH(1, false, 8);
+    } else if (c->min_blocks == 8) {                        // 32 registers (a few spilled bytes), 8 blocks per SM
+        if (c->prefetch) KC_LAUNCH(2, true, 8); else KC_LAUNCH(2, false, 8);
+    } else {                                                // 40 registers, 6 blocks per SM
+        if (c->prefetch) KC_LAUNCH(2, true, 6); else KC_LAUNCH(2, false, 6);
+    }
+#undef KC_LAUNCH
     KC_CUDA(c, cudaGetLastError());
     ++c->n_launches;
     return KH_OK;
@@ -236,6 +284,8 @@ int kh_count_create(int k, uint64_t n_distinct_expected, double load_factor, int
     }
     kh_counter* c = new kh_counter();
     c->k = k; c->W = kc_slot_words(k); c->device = device; c->pb = (k + 3) / 4 + 2;
+    if (const char* e = getenv("KH_COUNT_PREFETCH")) c->prefetch = atoi(e) != 0;
+    if (const char* e = getenv("KH_COUNT_BLOCKS")) c->min_blocks = atoi(e) == 6 ? 6 : 8;
     const double want = (double)std::max<uint64_t>(n_distinct_expected, 1) / load_factor;
     c->n_slots = std::max<u64>(1024, (u64)want + 1);
     c->table_bytes = (size_t)c->n_slots * (c->W == 1 ? 16 : 32);

@@ -165,34 +165,38 @@ __host__ __device__ __forceinline__ KcWin kc_window(const u32* w, u32 s) {
 struct KcOcc {
     u64 key_hi, key_lo;      // the k-mer as a right-justified base-4 number, first base most significant (slot.cuh)
     u32 back, fwd;           // 0..3 = A C G T, 4 = none
-    bool valid;              // all K bytes are bases
 };
+__host__ __device__ __forceinline__ u32 kc_char_bad(const u32* s_inv, u32 c) { return (s_inv[c >> 4] >> (30u - 2u * (c & 15u))) & 3u; }
+// (pass 2; the position is known to hold a k-mer, kc_kmer_valid)
 __host__ __device__ __forceinline__ KcOcc kc_position(const u32* s_code, const u32* s_inv, u32 local, int k) {
     const u32 s = 15u + local;
-    const KcWin y = kc_window(s_code, s), v = kc_window(s_inv, s);
+    const KcWin y = kc_window(s_code, s);
     // drop character 0 (the backward observation): the k-mer is on top
     const u64 zh = (y.hi << 2) | (y.lo >> 62), zl = y.lo << 2;
-    const u64 vh = (v.hi << 2) | (v.lo >> 62), vl = v.lo << 2;
     const int kb = 2 * k;                                   // 4 .. 122
     KcOcc o;
-    bool bad;
-    u32 f, fbad;
+    u32 f;
     if (kb <= 64) {
         o.key_hi = 0ull;
         o.key_lo = zh >> (64 - kb);
-        bad = (vh >> (64 - kb)) != 0ull;
     } else {
         const int s2 = 128 - kb;                            // 6 .. 62
         o.key_hi = zh >> s2;
         o.key_lo = (zh << (64 - s2)) | (zl >> s2);
-        bad = vh != 0ull || (vl >> s2) != 0ull;
     }
-    if (kb <= 62) { f = (u32)(zh >> (62 - kb)) & 3u; fbad = (u32)(vh >> (62 - kb)) & 3u; }
-    else          { f = (u32)(zl >> (126 - kb)) & 3u; fbad = (u32)(vl >> (126 - kb)) & 3u; }
-    o.valid = !bad;
-    o.back = (v.hi >> 62) ? 4u : (u32)(y.hi >> 62);
-    o.fwd = fbad ? 4u : f;
+    if (kb <= 62) f = (u32)(zh >> (62 - kb)) & 3u;
+    else          f = (u32)(zl >> (126 - kb)) & 3u;
+    o.back = kc_char_bad(s_inv, s) ? 4u : (u32)(y.hi >> 62);
+    o.fwd = kc_char_bad(s_inv, s + (u32)k + 1u) ? 4u : f;
     return o;
+}
+
+// pass 1 of a tile: does position `local` hold a k-mer (all K bytes are bases)?  Only the mask stream is looked at.
+__host__ __device__ __forceinline__ bool kc_kmer_valid(const u32* s_inv, u32 local, int k) {
+    const KcWin v = kc_window(s_inv, 15u + local);
+    const u64 vh = (v.hi << 2) | (v.lo >> 62), vl = v.lo << 2;
+    const int kb = 2 * k;
+    return kb <= 64 ? (vh >> (64 - kb)) == 0ull : (vh == 0ull && (vl >> (128 - kb)) == 0ull);
 }
 
 // ---- the counter word -------------------------------------------------------------------------------------------
@@ -230,7 +234,7 @@ __host__ __device__ __forceinline__ unsigned char kc_pick(u64 c, u32 shift, u32 
 
 // ---- the table --------------------------------------------------------------------------------------------------
 __host__ __device__ __forceinline__ u64 kc_hash(u64 key_hi, u64 key_lo) {
-    return fmix64(key_lo ^ fmix64(key_hi + 0x9E3779B97F4A7C15ull));
+    return fmix64(key_lo ^ (key_hi * 0x9E3779B97F4A7C15ull));          // K <= 32: key_hi = 0, the plain finaliser
 }
 template <int W> __host__ __device__ __forceinline__ void kc_tag(u64 key_hi, u64 key_lo, u64& t0, u64& t1);
 template <> __host__ __device__ __forceinline__ void kc_tag<1>(u64, u64 key_lo, u64& t0, u64& t1) { t0 = (key_lo << 1) | 1ull; t1 = 0ull; }
@@ -241,12 +245,13 @@ template <int W> __host__ __device__ __forceinline__ bool kc_slot_is(const u64 (
 }
 template <int W> __host__ __device__ __forceinline__ u64 kc_slot_counters(const u64 (&q)[4]) { return W == 1 ? q[1] : q[2]; }
 
-// one occurrence: find or claim the k-mer's slot, count.  Returns false when the table is full.
+// the slot a k-mer's probe sequence starts at
+__host__ __device__ __forceinline__ u64 kc_home(u64 key_hi, u64 key_lo, u64 n_slots) { return kc_mulhi64(kc_hash(key_hi, key_lo), n_slots); }
+// one occurrence: find or claim the k-mer's slot (probing from its home slot s), count.  Returns false when the table is full.
 template <int W>
-__host__ __device__ __forceinline__ bool kc_upsert(u64* table, u64 n_slots, const KcOcc& o, bool& fresh) {
+__host__ __device__ __forceinline__ bool kc_upsert(u64* table, u64 n_slots, const KcOcc& o, u64 s, bool& fresh) {
     u64 t0, t1;
     kc_tag<W>(o.key_hi, o.key_lo, t0, t1);
-    u64 s = kc_mulhi64(kc_hash(o.key_hi, o.key_lo), n_slots);
     fresh = false;
     for (u64 tries = 0; tries < n_slots; ++tries) {
         u64* p = table + s * (u64)KcSlot<W>::kWords;
@@ -275,7 +280,7 @@ template <int W>
 __host__ __device__ __forceinline__ u64 kc_find(const u64* table, u64 n_slots, u64 key_hi, u64 key_lo) {
     u64 t0, t1;
     kc_tag<W>(key_hi, key_lo, t0, t1);
-    u64 s = kc_mulhi64(kc_hash(key_hi, key_lo), n_slots);
+    u64 s = kc_home(key_hi, key_lo, n_slots);
     for (u64 tries = 0; tries < n_slots; ++tries) {
         const u64* p = table + s * (u64)KcSlot<W>::kWords;
         u64 q[4] = {p[0], p[1], W == 1 ? 0ull : p[2], 0ull};

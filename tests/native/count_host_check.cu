@@ -24,18 +24,21 @@ static void count_piece(const unsigned char* buf, u64 n, u64 p_begin, u64 p_end,
     for (u64 block = 0; block < blocks; ++block) {
         const u64 t0 = (p_begin & ~15ull) + block * kKcTile;
         for (u32 i = 0; i < kKcWords; ++i) kc_pack_word(buf, n, (long long)t0 - 16 + 16ll * (long long)i, s_code[i], s_inv[i]);
-        for (u32 thread = 0; thread < (u32)kKcThreads; ++thread) {
-            for (int r = 0; r < kKcPer; ++r) {
+        // pass 1: the positions that hold a k-mer; pass 2: count them (the kernel's two passes, serially)
+        std::vector<unsigned short> list;
+        for (int r = 0; r < kKcPer; ++r) {
+            for (u32 thread = 0; thread < (u32)kKcThreads; ++thread) {
                 const u32 local = thread + (u32)r * kKcThreads;
                 const u64 p = t0 + local;
-                if (p < p_begin || p >= p_end) continue;
-                const KcOcc o = kc_position(s_code.data(), s_inv.data(), local, k);
-                if (!o.valid) continue;
-                bool f;
-                if (!kc_upsert<W>(table, n_slots, o, f)) { ctr.errors |= kKcErrFull; continue; }
-                ++ctr.n_occurrences;
-                ctr.n_distinct += f ? 1 : 0;
+                if (p >= p_begin && p < p_end && kc_kmer_valid(s_inv.data(), local, k)) list.push_back((unsigned short)local);
             }
+        }
+        for (unsigned short local : list) {
+            const KcOcc o = kc_position(s_code.data(), s_inv.data(), local, k);
+            bool f;
+            if (!kc_upsert<W>(table, n_slots, o, kc_home(o.key_hi, o.key_lo, n_slots), f)) { ctr.errors |= kKcErrFull; continue; }
+            ++ctr.n_occurrences;
+            ctr.n_distinct += f ? 1 : 0;
         }
     }
 }

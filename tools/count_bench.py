@@ -20,7 +20,7 @@ import cs267_hw3_b200 as kh  # noqa: E402
 from tools import kmergen, readgen  # noqa: E402
 
 
-def run(k=51, n=4_000_000, coverage=8, read_len=150, reps=5, seed=267):
+def run(k=51, n=4_000_000, coverage=8, read_len=150, reps=5, seed=267, sweep=False):
     c = max(1, round(n * 860329 / 89710742))
     d = kmergen.Dataset(k, n, c, seed=seed)
     t0 = time.time()
@@ -49,6 +49,19 @@ def run(k=51, n=4_000_000, coverage=8, read_len=150, reps=5, seed=267):
         ts = tab.stats()
         lines = sorted(buf.tobytes().split(b"\n")[:-1])
         verified = nodes == n and b"\n".join(lines) + b"\n" == d.solution()
+        variants = {}
+        if sweep:                                          # the kernel's two switches, same reads, same table size
+            for pf in (0, 1):
+                for mb in ((8,) if k <= 31 else (6, 8)):
+                    os.environ["KH_COUNT_PREFETCH"], os.environ["KH_COUNT_BLOCKS"] = str(pf), str(mb)
+                    with kh.KmerCounter(k, n, 0.5, device=0) as kv:
+                        t = []
+                        for _ in range(4):
+                            kv.clear()
+                            kv.count_reads_device(p.value, reads.size)
+                            t.append(kv.stats()["ms_count"])
+                        variants[f"prefetch{pf}_blocks{mb}"] = round(float(np.median(t[1:])), 4)
+            os.environ.pop("KH_COUNT_PREFETCH"); os.environ.pop("KH_COUNT_BLOCKS")
         pin = kh.PinnedBuffer(reads.size)
         pin.array[:] = reads
         ms_host = []
@@ -77,11 +90,12 @@ def run(k=51, n=4_000_000, coverage=8, read_len=150, reps=5, seed=267):
                      "frac": alg / ms / 1e6 / peak, "alg_bytes_per_occurrence": 65, "traffic": None},
         "ms_extract": float(np.median(ms_ext[1:])), "ms_count_host_buffers": float(np.median(ms_host[1:])),
         "host_gbs": reads.size / float(np.median(ms_host[1:])) / 1e6,
-        "then_insert_ms": ts["ms_insert"], "then_assemble_ms": ts["ms_assemble"], "verified": bool(verified),
+        "then_insert_ms_first_call": ts["ms_insert"], "then_assemble_ms_first_call": ts["ms_assemble"], "verified": bool(verified),
+        "variants_ms": variants or None,
     })
     return out
 
 
 if __name__ == "__main__":
-    a = [int(x) for x in sys.argv[1:]]
-    print(json.dumps(run(*a)))
+    a = [int(x) for x in sys.argv[1:] if x != "--sweep"]
+    print(json.dumps(run(*a, sweep="--sweep" in sys.argv)))
