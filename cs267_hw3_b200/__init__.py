@@ -16,7 +16,8 @@ import numpy as np
 from . import build as _build
 
 PKG = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(PKG, "libkh_b200.so")
+# KH_LIB_PATH: load another build of the library (tuning runs with other compile-time geometry, tools/probes/build_variants.sh)
+LIB_PATH = os.environ.get("KH_LIB_PATH") or os.path.join(PKG, "libkh_b200.so")
 
 KH_OK, KH_ERR_ARG, KH_ERR_CUDA, KH_ERR_NOT_FOUND, KH_ERR_TABLE_FULL = 0, 1, 2, 3, 4
 KH_ERR_CYCLE, KH_ERR_BAD_INPUT, KH_ERR_CONVERGE, KH_ERR_NOMEM = 5, 6, 7, 8
@@ -79,7 +80,7 @@ def lib() -> C.CDLL:
     global _lib
     if _lib is not None:
         return _lib
-    if not os.path.exists(LIB_PATH) or _build._stale(LIB_PATH, _build.lib_sources()):
+    if not os.environ.get("KH_LIB_PATH") and (not os.path.exists(LIB_PATH) or _build._stale(LIB_PATH, _build.lib_sources())):
         _build.build_lib()
     L = C.CDLL(LIB_PATH)
     u64, vp, i32 = C.c_uint64, C.c_void_p, C.c_int

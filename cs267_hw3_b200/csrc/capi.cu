@@ -608,6 +608,7 @@ int ct_setup(kh_table* t, int rank, int world, u64 n_local_max, u64 n_total, u64
     KH_CUDA(t, cudaStreamSynchronize(t->stream));
     if (!c.attr_set) {
         KH_CUDA(t, cudaFuncSetAttribute(ct_build_kernel<W>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)CtBuild<W>::kSmem));
+        KH_CUDA(t, cudaFuncSetAttribute(ct_build_kernel<W>, cudaFuncAttributePreferredSharedMemoryCarveout, (int)cudaSharedmemCarveoutMaxShared));
         KH_CUDA(t, cudaFuncSetAttribute(ct_stage_kernel<W>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)ct_stage_smem(W, 8)));
         c.attr_set = true;
     }

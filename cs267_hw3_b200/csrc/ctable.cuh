@@ -39,11 +39,22 @@
 
 namespace kh {
 
+// Build-kernel geometry, overridable at compile time for tuning runs (tools/probes/build_variants.sh): buckets per chunk
+// for 128-bit slots, threads per block, blocks per SM.
+#ifndef KH_CT_BUCKETS2
+#define KH_CT_BUCKETS2 2176
+#endif
+#ifndef KH_CT_THREADS
+#define KH_CT_THREADS 512
+#endif
+#ifndef KH_CT_MINBLOCKS
+#define KH_CT_MINBLOCKS 2
+#endif
 template <int W> struct CtBuild {
     // A chunk = one run of buckets that a thread block builds in shared memory.  Shared memory per block:
     //   table | succ u16[node] (later the characters) | (ancestor, distance) u32[node] | ext code + flags u8[node] | pool offset u16[node]
     // = 104 448 B (64-bit slots) / 108 800 B (128-bit slots): two blocks of 512 threads per SM.
-    static constexpr u32 kMaxBuckets = (W == 1) ? 1536u : 2176u;                 // 48 / 68 KB of table per chunk
+    static constexpr u32 kMaxBuckets = (W == 1) ? 1536u : (u32)KH_CT_BUCKETS2;                 // 48 / 68 KB of table per chunk
     static constexpr u32 kMaxSlots = kMaxBuckets * (u32)Slot<W>::kPerBucket;      // 6144 / 4352: also the most records a chunk can take
     static constexpr u32 kOffSucc = kMaxBuckets * 32u;
     static constexpr u32 kOffPd = kOffSucc + kMaxSlots * 2u;
@@ -51,7 +62,7 @@ template <int W> struct CtBuild {
     static constexpr u32 kOffCode = kOffOff + kMaxSlots * 2u;
     static constexpr u32 kSmem = kOffCode + kMaxSlots;
 };
-constexpr int kCtBuildThreads = 512;
+constexpr int kCtBuildThreads = KH_CT_THREADS;
 // Where record number `at` of chunk `chunk` lives in the chunk buffers: position-major, in groups of one 128-byte
 // line (8 or 16 records).  All chunks fill at about the same rate, so at any moment the appends of the staging pass
 // land in a window of a few hundred MB instead of being spread over every chunk's own multi-KB buffer (3.7 GB in
@@ -540,7 +551,7 @@ template <> __device__ __forceinline__ int ct_find_step<2>(unsigned saddr, u128 
 }
 
 template <int W>
-__global__ void __launch_bounds__(kCtBuildThreads, 2)
+__global__ void __launch_bounds__(kCtBuildThreads, KH_CT_MINBLOCKS)
 ct_build_kernel(const typename Slot<W>::value_t* __restrict__ fine, const u32* __restrict__ chunk_cursor,
                 const u32* __restrict__ chunk_base, const u32* __restrict__ pool_off,
                 typename Slot<W>::value_t* __restrict__ table, u32* __restrict__ seg_base,
