@@ -20,8 +20,18 @@ from tools import kmergen  # noqa: E402
 
 def main():
     rank, world, local = int(os.environ["RANK"]), int(os.environ["WORLD_SIZE"]), int(os.environ["LOCAL_RANK"])
+    # KH_TEST_ONE_DEVICE=1: every process on GPU 0 (a one-GPU box): the same CUDA IPC mappings, peer stores and in-stream
+    # barriers between PROCESSES, the contexts time-sliced by the driver; NCCL refuses two ranks on one device, so the
+    # start-up exchange and the error-bit reduction go over gloo
+    one_device = os.environ.get("KH_TEST_ONE_DEVICE") == "1"
+    if one_device:
+        local = 0
     torch.cuda.set_device(local)
-    dist.init_process_group("nccl", device_id=torch.device("cuda", local))
+    if one_device:
+        dist.init_process_group("gloo")
+    else:
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local))
+    red_dev = "cpu" if one_device else "cuda"
     failures = 0
     for k, n, c, longn in ((19, 400_000, 3_000, 0), (51, 300_000, 2_500, 0), (31, 200_000, 40, 150_000)):
         d = kmergen.Dataset(k, n, c, seed=500 + k, long_nodes=longn)
@@ -42,14 +52,14 @@ def main():
             ok = nc == want_nc and got.tobytes() == want
             failures += 0 if ok else 1
         st = shard.tab.stats()
-        tot = torch.tensor([float(st["n_inserted"]), float(nn)], device="cuda", dtype=torch.float64)
+        tot = torch.tensor([float(st["n_inserted"]), float(nn)], device=red_dev, dtype=torch.float64)
         dist.all_reduce(tot)
         if int(tot[0]) != n or int(tot[1]) != n:
             failures += 1
         print(f"rank {rank}/{world} k={k}: {st['n_inserted']} k-mers held, {nc} contigs, {'OK' if ok else 'MISMATCH'}", flush=True)
         shard.close()
         dist.barrier()
-    t = torch.tensor([float(failures)], device="cuda")
+    t = torch.tensor([float(failures)], device=red_dev)
     dist.all_reduce(t)
     dist.destroy_process_group()
     sys.exit(1 if t.item() else 0)

@@ -33,6 +33,18 @@ def test_one_process_per_gpu_matches_the_reference_per_rank_files(world):
     assert r.stdout.count("OK") == 3 * world and "MISMATCH" not in r.stdout
 
 
+def test_one_process_per_rank_on_one_gpu():
+    """Two PROCESSES on GPU 0: the transport of the multi-process path (CUDA IPC peer mappings opened by
+    kh_shard_connect, peer stores, barrier kernels that wait for another process's kernel) on a one-GPU box, where the
+    tests above skip.  The driver time-slices the two contexts, so this is slow per step but exact."""
+    env = dict(os.environ, KH_TEST_ONE_DEVICE="1")
+    r = subprocess.run([sys.executable, "-m", "torch.distributed.run", "--nnodes=1", "--nproc-per-node=2",
+                        "--master-addr", "127.0.0.1", "--master-port", "29631",
+                        os.path.join(ROOT, "tests", "multi_gpu_worker.py")], capture_output=True, text=True, timeout=600, env=env)
+    assert r.returncode == 0, r.stdout[-4000:] + r.stderr[-4000:]
+    assert r.stdout.count("OK") == 6 and "MISMATCH" not in r.stdout
+
+
 @pytest.mark.parametrize("world,k", [(2, 51), (2, 19), (4, 31), (8, 51)])
 def test_one_thread_per_gpu_cli(tmp_path, world, k):
     if _ngpu() < world:
