@@ -65,7 +65,7 @@ class CountStats(C.Structure):
     _fields_ = [
         ("n_slots", C.c_uint64), ("n_distinct", C.c_uint64), ("n_occurrences", C.c_uint64), ("n_bytes", C.c_uint64),
         ("n_reported", C.c_uint64), ("slot_bytes", C.c_uint32), ("n_launches", C.c_uint32),
-        ("ms_count", C.c_float), ("ms_extract", C.c_float),
+        ("n_grows", C.c_uint32), ("reserved", C.c_uint32), ("ms_count", C.c_float), ("ms_extract", C.c_float),
     ]
 
     def as_dict(self) -> dict:

@@ -26,6 +26,8 @@ namespace {
 constexpr u32 kFull = 0xFFFFFFFFu;
 constexpr u64 kKcChunk = 64ull << 20;                       // positions per host chunk (multiple of the tile and of 16)
 constexpr u64 kKcHalo = 16 + 64;                            // bytes around a chunk: 16 before (keeps the alignment), 64 behind
+constexpr double kKcMaxLoad = 0.9;                          // a launch never takes the table past this load
+constexpr u64 kKcMinLaunch = 4ull << 20;                    // grow rather than count in launches smaller than this
 }  // namespace
 
 // Pass 1 compacts the tile's positions that hold a k-mer into a list (reads end every ~150 characters and K - 1
@@ -57,7 +59,8 @@ kc_count_kernel(const unsigned char* __restrict__ buf, u64 n, u64 p_begin, u64 p
         if (ok) s_list[base + (u32)__popc(bal & ((1u << lane) - 1u))] = (unsigned short)local;
     }
     __syncthreads();
-    const u32 cnt = s_n;
+    // a table that has overflowed stays wrong whatever follows: later blocks do not probe it slot by slot any more
+    const u32 cnt = *reinterpret_cast<volatile u32*>(&ctr->errors) ? 0u : s_n;
     u32 fresh = 0, fail = 0;
     if (!PF) {
 #pragma unroll 1
@@ -105,6 +108,14 @@ kc_count_kernel(const unsigned char* __restrict__ buf, u64 n, u64 p_begin, u64 p
         if (s_fresh) atomicAdd(&ctr->n_distinct, (u64)s_fresh);
         if (s_fail) atomicOr(&ctr->errors, kKcErrFull);
     }
+}
+
+// table growth: every occupied slot of the old table moves to its place in the new one
+template <int W>
+__global__ void __launch_bounds__(256)
+kc_rehash_kernel(const u64* __restrict__ old_table, u64 old_slots, u64* __restrict__ table, u64 n_slots, KcCounters* ctr) {
+    const u64 i = (u64)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < old_slots && !kc_move_slot<W>(old_table, i, table, n_slots)) atomicOr(&ctr->errors, kKcErrFull);
 }
 
 constexpr int kKcExtThreads = 256;
@@ -207,6 +218,10 @@ struct kh_counter {
     float ms_count = 0.f, ms_extract = 0.f;
     bool have_count = false;
     bool prefetch = false;            // KH_COUNT_PREFETCH=1: software prefetch of the next occurrence's slot (measured: no gain, the kernel is issue-bound)
+    bool may_grow = true;             // KH_COUNT_GROW=0: a full table is an error instead of a reason to grow
+    double lf = 0.5;
+    u32 n_grows = 0;
+    u64 distinct_ub = 0;              // host-side upper bound of the distinct count: every launched position counted as new
     int min_blocks = 8;               // KH_COUNT_BLOCKS=6: 128-bit keys at 40 registers / 6 blocks per SM instead of 32 / 8
     std::string err;
 };
@@ -249,6 +264,48 @@ int kc_settle(kh_counter* c) {
     return KH_OK;
 }
 
+// How many of the next `want` positions may be counted right now without any risk of running out of slots: every position
+// could be a new k-mer, so a launch never gets more positions than the table has room for below kKcMaxLoad.  When that
+// room falls under kKcMinLaunch positions the table grows (x2, rehashed on the GPU) -- no occurrence is ever dropped and
+// nobody has to know the number of distinct k-mers in advance.  Waits for the stream only when the host-side upper
+// bound of the distinct count (every launched position counted as new) says the table might be short.
+int kc_grow(kh_counter* c) {
+    const u64 new_slots = 2 * c->n_slots;
+    const size_t new_bytes = (size_t)new_slots * (c->W == 1 ? 16 : 32);
+    u64* fresh = nullptr;
+    KC_CUDA(c, cudaMalloc(reinterpret_cast<void**>(&fresh), new_bytes));
+    KC_CUDA(c, cudaMemsetAsync(fresh, 0, new_bytes, c->stream));
+    const u64 blocks = (c->n_slots + 255) / 256;
+    if (c->W == 1) kc_rehash_kernel<1><<<(unsigned)blocks, 256, 0, c->stream>>>(c->table, c->n_slots, fresh, new_slots, c->d_ctr);
+    else kc_rehash_kernel<2><<<(unsigned)blocks, 256, 0, c->stream>>>(c->table, c->n_slots, fresh, new_slots, c->d_ctr);
+    KC_CUDA(c, cudaGetLastError());
+    ++c->n_launches;
+    ++c->n_grows;
+    KC_CUDA(c, cudaStreamSynchronize(c->stream));
+    KC_CUDA(c, cudaFree(c->table));
+    c->table = fresh; c->n_slots = new_slots; c->table_bytes = new_bytes;
+    return KH_OK;
+}
+int kc_reserve(kh_counter* c, u64 want, u64* granted) {
+    auto room = [&](u64 distinct) {
+        const u64 limit = (u64)(kKcMaxLoad * (double)c->n_slots);
+        return limit > distinct ? limit - distinct : 0ull;
+    };
+    if (room(c->distinct_ub) >= want) { *granted = want; return KH_OK; }
+    KC_TRY(kc_settle(c));
+    c->distinct_ub = c->h_ctr.n_distinct;
+    const u64 floor = std::min<u64>(want, kKcMinLaunch);
+    while (room(c->distinct_ub) < floor) {
+        if (!c->may_grow) {
+            if (room(c->distinct_ub) >= 16) break;
+            return kc_fail(c, KH_ERR_TABLE_FULL, "k-mer counter: the table is full and growing is disabled (KH_COUNT_GROW=0)");
+        }
+        KC_TRY(kc_grow(c));
+    }
+    *granted = std::min<u64>(want, room(c->distinct_ub));
+    return KH_OK;
+}
+
 int kc_launch_count(kh_counter* c, const unsigned char* buf, u64 n, u64 p_begin, u64 p_end) {
     if (p_end <= p_begin) return KH_OK;
     const u64 span = p_end - (p_begin & ~15ull);
@@ -286,6 +343,8 @@ int kh_count_create(int k, uint64_t n_distinct_expected, double load_factor, int
     c->k = k; c->W = kc_slot_words(k); c->device = device; c->pb = (k + 3) / 4 + 2;
     if (const char* e = getenv("KH_COUNT_PREFETCH")) c->prefetch = atoi(e) != 0;
     if (const char* e = getenv("KH_COUNT_BLOCKS")) c->min_blocks = atoi(e) == 6 ? 6 : 8;
+    if (const char* e = getenv("KH_COUNT_GROW")) c->may_grow = atoi(e) != 0;
+    c->lf = load_factor;
     const double want = (double)std::max<uint64_t>(n_distinct_expected, 1) / load_factor;
     c->n_slots = std::max<u64>(1024, (u64)want + 1);
     c->table_bytes = (size_t)c->n_slots * (c->W == 1 ? 16 : 32);
@@ -343,6 +402,7 @@ int kh_count_clear(kh_counter* c) {
     KC_CUDA(c, cudaMemsetAsync(c->table, 0, c->table_bytes, c->stream));
     KC_CUDA(c, cudaMemsetAsync(c->d_ctr, 0, sizeof(KcCounters), c->stream));
     c->n_bytes = 0;
+    c->distinct_ub = 0;
     c->h_ctr = KcCounters{};
     c->err.clear();
     return KH_OK;
@@ -354,6 +414,7 @@ int kh_count_reads_device(kh_counter* c, const char* reads_dev, uint64_t n_bytes
     KC_CUDA(c, cudaSetDevice(c->device));
     KC_CUDA(c, cudaEventRecord(c->ev0, c->stream));
     KC_TRY(kc_launch_count(c, reinterpret_cast<const unsigned char*>(reads_dev), n_bytes, 0, n_bytes));
+    c->distinct_ub += n_bytes;
     KC_CUDA(c, cudaEventRecord(c->ev1, c->stream));
     c->have_count = true;
     c->n_bytes += n_bytes;
@@ -399,7 +460,14 @@ int kh_count_reads(kh_counter* c, const char* reads_host, uint64_t n_bytes) {
         u64 a, b, off, len;
         range(ci, a, b, off, len);
         KC_CUDA(c, cudaStreamWaitEvent(c->stream, c->ev_copied[ci & 1], 0));
-        KC_TRY(kc_launch_count(c, c->stage[ci & 1], b - a, off - a, off - a + len));
+        for (u64 done = 0; done < len;) {                  // normally one launch; several when the table is nearly full
+            u64 take = 0;
+            KC_TRY(kc_reserve(c, len - done, &take));
+            if (take < len - done) take &= ~15ull;         // pieces start on a 16-character boundary
+            KC_TRY(kc_launch_count(c, c->stage[ci & 1], b - a, off - a + done, off - a + done + take));
+            c->distinct_ub += take;
+            done += take;
+        }
         KC_CUDA(c, cudaEventRecord(c->ev_consumed[ci & 1], c->stream));
     }
     KC_CUDA(c, cudaEventRecord(c->ev1, c->stream));
@@ -507,6 +575,8 @@ int kh_count_get_stats(kh_counter* c, kh_count_stats* out) {
     out->n_reported = c->h_ctr.n_reported;
     out->slot_bytes = c->W == 1 ? 16u : 32u;
     out->n_launches = c->n_launches;
+    out->n_grows = c->n_grows;
+    out->reserved = 0;
     out->ms_count = c->ms_count;
     out->ms_extract = c->ms_extract;
     return rc;

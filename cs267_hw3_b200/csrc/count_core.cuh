@@ -40,6 +40,7 @@ constexpr u32 kKcWords = kKcTile / 16 + 5;
 
 constexpr u32 kKcCountCap = 255, kKcExtCap = 127;
 constexpr u32 kKcErrFull = 1u;
+constexpr u64 kKcMaxProbes = 1ull << 16;                     // a probe sequence this long means the table is (as good as) full
 
 struct KcCounters {
     u64 n_occurrences;       // positions counted so far
@@ -253,7 +254,7 @@ __host__ __device__ __forceinline__ bool kc_upsert(u64* table, u64 n_slots, cons
     u64 t0, t1;
     kc_tag<W>(o.key_hi, o.key_lo, t0, t1);
     fresh = false;
-    for (u64 tries = 0; tries < n_slots; ++tries) {
+    for (u64 tries = 0, lim = n_slots < kKcMaxProbes ? n_slots : kKcMaxProbes; tries < lim; ++tries) {
         u64* p = table + s * (u64)KcSlot<W>::kWords;
         u64 q[4];
         kc_load_slot<W>(p, q);
@@ -281,7 +282,7 @@ __host__ __device__ __forceinline__ u64 kc_find(const u64* table, u64 n_slots, u
     u64 t0, t1;
     kc_tag<W>(key_hi, key_lo, t0, t1);
     u64 s = kc_home(key_hi, key_lo, n_slots);
-    for (u64 tries = 0; tries < n_slots; ++tries) {
+    for (u64 tries = 0, lim = n_slots < kKcMaxProbes ? n_slots : kKcMaxProbes; tries < lim; ++tries) {
         const u64* p = table + s * (u64)KcSlot<W>::kWords;
         u64 q[4] = {p[0], p[1], W == 1 ? 0ull : p[2], 0ull};
         if (kc_slot_empty<W>(q)) return 0ull;
@@ -289,6 +290,32 @@ __host__ __device__ __forceinline__ u64 kc_find(const u64* table, u64 n_slots, u
         s = (s + 1 == n_slots) ? 0ull : s + 1;
     }
     return 0ull;
+}
+
+// growing the table: slot i of the old table (if occupied) moves to the new one -- its key claims a slot by CAS (other
+// keys are moving in at the same time), its counter word is stored (keys are unique: nobody else touches that word).
+// Returns false when the new table is full (it is sized so that it cannot be).
+template <int W>
+__host__ __device__ __forceinline__ bool kc_move_slot(const u64* old_table, u64 i, u64* table, u64 n_slots) {
+    const u64* src = old_table + i * (u64)KcSlot<W>::kWords;
+    const u64 q0[4] = {src[0], src[1], W == 1 ? 0ull : src[2], 0ull};
+    if (kc_slot_empty<W>(q0)) return true;
+    const u64 t0 = q0[0], t1 = W == 1 ? 0ull : q0[1], counters = kc_slot_counters<W>(q0);
+    const u64 key_lo = W == 1 ? t0 >> 1 : t0, key_hi = W == 1 ? 0ull : t1 & ~(1ull << 63);
+    u64 s = kc_home(key_hi, key_lo, n_slots);
+    for (u64 tries = 0, lim = n_slots < kKcMaxProbes ? n_slots : kKcMaxProbes; tries < lim; ++tries) {
+        u64* p = table + s * (u64)KcSlot<W>::kWords;
+        u64 q[4];
+        kc_load_slot<W>(p, q);
+        if (kc_slot_empty<W>(q)) {
+            bool mine;
+            if (W == 1) mine = kc_cas64(p, 0ull, t0) == 0ull;
+            else { const u128 old = kc_cas128(p, u128{0ull, 0ull}, u128{t0, t1}); mine = old.lo == 0ull && old.hi == 0ull; }
+            if (mine) { p[W == 1 ? 1 : 2] = counters; return true; }
+        }
+        s = (s + 1 == n_slots) ? 0ull : s + 1;
+    }
+    return false;
 }
 
 // ---- k-mer <-> the reference's packed bytes (packing.hpp:77-92: first base in bits 7..6 of byte 0, A-padded tail) ---

@@ -233,11 +233,16 @@ typedef struct kh_count_stats {
     uint64_t n_reported;       /* records of the last kh_count_extract*                            */
     uint32_t slot_bytes;       /* 16 (K <= 31) or 32 (one DRAM sector)                             */
     uint32_t n_launches;       /* kernels launched since create                                    */
+    uint32_t n_grows;          /* times the table was doubled and rehashed since create            */
+    uint32_t reserved;
     float ms_count;            /* last kh_count_reads*: first byte in .. last kernel out (CUDA events) */
     float ms_extract;          /* last kh_count_extract*: the extract kernel                       */
 } kh_count_stats;
-/* n_distinct_expected counts EVERY distinct k-mer of the reads, erroneous ones included; the table holds
- * n_distinct_expected / load_factor slots and does not grow (KH_ERR_TABLE_FULL from the next call on). */
+/* The table starts with n_distinct_expected / load_factor slots (distinct k-mers of the reads, erroneous ones
+ * included).  kh_count_reads never runs out of slots: it hands the kernel no more positions than the table has room
+ * for and doubles the table (rehashed on the GPU) when that room gets small -- a good estimate only saves the
+ * rehashes (KH_COUNT_GROW=0 turns growing off).  kh_count_reads_device only enqueues and therefore cannot grow:
+ * if the table fills up, the next synchronising call returns KH_ERR_TABLE_FULL (until kh_count_clear). */
 int kh_count_create(int k, uint64_t n_distinct_expected, double load_factor, int device, kh_counter** out);
 int kh_count_destroy(kh_counter* c);
 int kh_count_clear(kh_counter* c);

@@ -3,7 +3,8 @@
 // and thread by thread, with the host chunking of kh_count_reads (kc_chunk_range) at a small chunk size so that chunk and
 // tile boundaries fall inside the reads.  tests/test_count.py compares the output with the oracle.
 //
-//   count_host_check K chunk n_slots min_count min_ext misalign reads_file
+//   count_host_check K chunk n_slots min_count min_ext misalign reads_file [grow_after_chunk]
+// (grow_after_chunk: after that chunk the table is doubled and rehashed with kc_move_slot, as kc_grow does on the GPU)
 // prints "n_occurrences n_distinct n_reported full" and then one line per reported k-mer:
 //   record(hex)  occurrences backA backC backG backT fwdA fwdC fwdG fwdT  line       (the counters through kc_find;
 //   the record as a k-mer file line through kc_record_to_line, its blank shown as '_')
@@ -44,7 +45,7 @@ static void count_piece(const unsigned char* buf, u64 n, u64 p_begin, u64 p_end,
 }
 
 template <int W>
-static int run(int k, u64 chunk, u64 n_slots, u32 min_count, u32 min_ext, const unsigned char* reads, u64 n_bytes, bool one_piece) {
+static int run(int k, u64 chunk, u64 n_slots, u32 min_count, u32 min_ext, const unsigned char* reads, u64 n_bytes, bool one_piece, long grow_after) {
     std::vector<u64> table(n_slots * KcSlot<W>::kWords, 0ull);
     KcCounters ctr = {};
     const u64 nchunks = one_piece ? 0 : (n_bytes + chunk - 1) / chunk;
@@ -57,6 +58,13 @@ static int run(int k, u64 chunk, u64 n_slots, u32 min_count, u32 min_ext, const 
         memcpy(piece, reads + a, b - a);
         count_piece<W>(piece, b - a, off - a, off - a + len, table.data(), n_slots, k, ctr);
         free(piece);
+        if (grow_after >= 0 && ci == (u64)grow_after) {       // kc_grow: every slot moves into a table twice the size
+            std::vector<u64> bigger(2 * n_slots * KcSlot<W>::kWords, 0ull);
+            for (u64 i = 0; i < n_slots; ++i)
+                if (!kc_move_slot<W>(table.data(), i, bigger.data(), 2 * n_slots)) ctr.errors |= kKcErrFull;
+            table.swap(bigger);
+            n_slots *= 2;
+        }
     }
     const int pl = (k + 3) / 4, pb = pl + 2;
     std::vector<unsigned char> out;
@@ -87,7 +95,8 @@ static int run(int k, u64 chunk, u64 n_slots, u32 min_count, u32 min_ext, const 
 }
 
 int main(int argc, char** argv) {
-    if (argc != 8) { fprintf(stderr, "usage: count_host_check K chunk n_slots min_count min_ext misalign reads_file\n"); return 2; }
+    if (argc != 8 && argc != 9) { fprintf(stderr, "usage: count_host_check K chunk n_slots min_count min_ext misalign reads_file [grow_after_chunk]\n"); return 2; }
+    const long grow_after = argc == 9 ? atol(argv[8]) : -1;
     const int k = atoi(argv[1]);
     const u64 chunk = strtoull(argv[2], nullptr, 10), n_slots = strtoull(argv[3], nullptr, 10);
     const u32 min_count = (u32)atoi(argv[4]), min_ext = (u32)atoi(argv[5]);
@@ -105,6 +114,6 @@ int main(int argc, char** argv) {
     if (fread(base, 1, (size_t)n, f) != (size_t)n) return 2;
     fclose(f);
     if (chunk % kKcTile) return 2;
-    return kc_slot_words(k) == 1 ? run<1>(k, chunk, n_slots, min_count, min_ext, base, (u64)n, misalign != 0)
-                                 : run<2>(k, chunk, n_slots, min_count, min_ext, base, (u64)n, misalign != 0);
+    return kc_slot_words(k) == 1 ? run<1>(k, chunk, n_slots, min_count, min_ext, base, (u64)n, misalign != 0, grow_after)
+                                 : run<2>(k, chunk, n_slots, min_count, min_ext, base, (u64)n, misalign != 0, grow_after);
 }

@@ -77,10 +77,11 @@ def host_check(tmp_path_factory):
     return exe
 
 
-def _run_host(exe, tmp_path, reads, k, chunk, n_slots, min_count, min_ext, misalign=0):
+def _run_host(exe, tmp_path, reads, k, chunk, n_slots, min_count, min_ext, misalign=0, grow_after=None):
     f = tmp_path / "reads.txt"
     np.asarray(reads, dtype=np.uint8).tofile(f)
-    out = subprocess.run([exe, str(k), str(chunk), str(n_slots), str(min_count), str(min_ext), str(misalign), str(f)],
+    out = subprocess.run([exe, str(k), str(chunk), str(n_slots), str(min_count), str(min_ext), str(misalign), str(f)]
+                         + ([str(grow_after)] if grow_after is not None else []),
                          capture_output=True, text=True, check=True).stdout.splitlines()
     head = [int(x) for x in out[0].split()]
     pb = (k + 3) // 4 + 2
@@ -129,6 +130,17 @@ def test_kernel_functions_saturate_like_the_oracle(host_check, tmp_path):
     head, recs, cnts = _run_host(host_check, tmp_path, reads, 5, chunk=2048, n_slots=1024, min_count=1, min_ext=1)
     assert head[0] == n_occ and (recs == want_p).all() and (cnts == want_c).all()
     assert cnts[:, 0].max() == 255 and cnts[:, 1:].max() == 127
+
+
+@pytest.mark.parametrize("k", [19, 51])
+def test_kernel_functions_table_growth(host_check, tmp_path, k):
+    """kc_move_slot: the table doubled and rehashed in the middle of the input (twice) gives the same k-mers and counters."""
+    _, reads = _reads(k, 12000, 30, seed=40 + k, coverage=3, with_n=True)
+    want_p, want_c, n_occ = oracle.analyse_reads(reads, k, 1, 1)
+    n_slots = 1 << 15
+    for grow_after in (0, 5):
+        head, recs, cnts = _run_host(host_check, tmp_path, reads, k, chunk=4096, n_slots=n_slots, min_count=1, min_ext=1, grow_after=grow_after)
+        assert head[0] == n_occ and head[3] == 0 and (recs == want_p).all() and (cnts == want_c).all()
 
 
 def test_kernel_functions_report_a_full_table(host_check, tmp_path):
@@ -230,13 +242,48 @@ def test_gpu_count_device_buffer_any_alignment_and_long_input():
 
 
 @pytest.mark.gpu
+@pytest.mark.parametrize("k", [19, 51])
+def test_gpu_count_table_grows_instead_of_filling_up(k):
+    """A counter created far too small (1024 slots) for 150 000 distinct k-mers: kh_count_reads hands the kernel only as many
+    positions as the table has room for and doubles it when that gets small -- same records and counters as the oracle."""
+    import ctypes as C
+
+    import cs267_hw3_b200 as kh
+    _, reads = _reads(k, 150000, 200, seed=600 + k, coverage=3, error_rate=0.002)
+    want_p, want_c, n_occ = oracle.analyse_reads(reads, k, 2, 2)
+    with _counter(k, 100) as kc:
+        kc.count_reads(reads)
+        st = kc.stats()
+        assert st["n_grows"] >= 7 and st["n_occurrences"] == n_occ and st["n_distinct"] <= 0.9 * st["n_slots"]
+        assert (_sorted_rows(kc.extract(2, 2)) == want_p).all()
+        assert (kc.lookup(want_p[:, : (k + 3) // 4]) == want_c).all()
+    # the device entry point only enqueues, so it cannot grow: the overflow is reported by the next synchronising call
+    L = kh.lib()
+    with _counter(k, 100) as kc:
+        p = C.c_void_p()
+        assert L.kh_device_alloc(C.byref(p), reads.size) == 0
+        with kh.KmerHashTable(k, 1024) as tab:
+            tab._check(L.kh_copy_device(tab._h, p, reads.ctypes.data, reads.size))
+            tab.sync()
+        kc.count_reads_device(p.value, reads.size)
+        with pytest.raises(kh.KhError) as e:
+            kc.stats()
+        assert e.value.status == kh.KH_ERR_TABLE_FULL
+        L.kh_device_free(p)
+
+
+@pytest.mark.gpu
 def test_gpu_count_errors():
     import cs267_hw3_b200 as kh
     _, reads = _reads(19, 50000, 50, seed=5)
-    with _counter(19, 1000, 1.0) as kc:                                        # 1024 slots for 50 000 k-mers
-        with pytest.raises(kh.KhError) as e:
-            kc.count_reads(reads)
-        assert e.value.status == kh.KH_ERR_TABLE_FULL
+    os.environ["KH_COUNT_GROW"] = "0"
+    try:
+        with _counter(19, 1000, 1.0) as kc:                                    # 1024 slots for 50 000 k-mers, not allowed to grow
+            with pytest.raises(kh.KhError) as e:
+                kc.count_reads(reads)
+            assert e.value.status == kh.KH_ERR_TABLE_FULL
+    finally:
+        os.environ.pop("KH_COUNT_GROW")
     with _counter(19, 100000) as kc:
         kc.count_reads(reads)
         for bad in ((0, 1), (256, 1), (1, 0), (1, 128)):
