@@ -173,12 +173,11 @@ def analyse_reads(reads: bytes | np.ndarray, k: int, min_count: int = 2, min_ext
     r = np.frombuffer(reads, dtype=np.uint8) if not isinstance(reads, np.ndarray) else np.ascontiguousarray(reads)
     n_occ = int(lib().kco_count_occurrences(r.ctypes.data, r.size, k))
     n = C.c_uint64()
-    _check(lib().kco_analyse(r.ctypes.data, r.size, k, min_count, min_ext, None, 0, C.byref(n), None), "analyse(size)")
-    pairs = np.empty((n.value, pair_bytes(k)), dtype=np.uint8)
-    counts = np.empty((n.value, 9), dtype=np.uint32)
-    _check(lib().kco_analyse(r.ctypes.data, r.size, k, min_count, min_ext, pairs.ctypes.data, n.value, C.byref(n),
+    pairs = np.empty((max(n_occ, 1), pair_bytes(k)), dtype=np.uint8)        # distinct k-mers <= occurrences: one pass
+    counts = np.empty((max(n_occ, 1), 9), dtype=np.uint32)
+    _check(lib().kco_analyse(r.ctypes.data, r.size, k, min_count, min_ext, pairs.ctypes.data, max(n_occ, 1), C.byref(n),
                              counts.ctypes.data), "analyse")
-    return pairs, counts, n_occ
+    return pairs[: n.value].copy(), counts[: n.value].copy(), n_occ
 
 
 # ---- the unmodified reference, compiled (oracle/_ref) -------------------------------------

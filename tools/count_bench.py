@@ -93,9 +93,14 @@ def run(k=51, n=4_000_000, coverage=8, read_len=150, reps=5, seed=267, sweep=Fal
         "then_insert_ms_first_call": ts["ms_insert"], "then_assemble_ms_first_call": ts["ms_assemble"], "verified": bool(verified),
         "variants_ms": variants or None,
     })
+    # a bounded piece of the same reads for bench.py's CPU leg (whole lines, about 8 MB); not part of the JSON record
+    cut = int(np.flatnonzero(reads[: 8 << 20] == 10)[-1]) + 1
+    out["_sample"] = reads[:cut]
     return out
 
 
 if __name__ == "__main__":
     a = [int(x) for x in sys.argv[1:] if x != "--sweep"]
-    print(json.dumps(run(*a, sweep="--sweep" in sys.argv)))
+    rec = run(*a, sweep="--sweep" in sys.argv)
+    rec.pop("_sample", None)
+    print(json.dumps(rec))
