@@ -1,9 +1,8 @@
-# What one gpurun call of this round runs: GPU tests, smoke, the bench line, the k-mer analysis bench for K=19/31, and the
-# ncu captures of kc_count_kernel (profiles/r02_count_*).  bash tools/probes/gpu_round_check.sh  (from the repo root)
+# What one gpurun call at the end of the round runs: GPU tests, smoke, the bench line (default workload + the long-contig
+# and K=31 shapes).  bash tools/probes/gpu_round_check.sh  (from the repo root)
 mkdir -p gpurun_out
-timeout 500 python -m pytest tests -m gpu -x -q --durations=15 > gpurun_out/t2_pytest.log 2>&1; echo "pytest rc=$?"; tail -4 gpurun_out/t2_pytest.log
-timeout 90 python -c "import __graft_entry__ as g; g.smoke()" > gpurun_out/t2_smoke.log 2>&1; echo "smoke rc=$?"; tail -3 gpurun_out/t2_smoke.log
-timeout 200 python bench.py --steps 10 --warmup 3 > gpurun_out/t2_bench.json 2> gpurun_out/t2_bench.err; echo "bench rc=$?"
-for k in 19 31; do timeout 60 python tools/count_bench.py $k 4000000 8 150 > gpurun_out/t2_count$k.json 2> gpurun_out/t2_count$k.err; echo "count$k rc=$?"; done
-timeout 120 ncu --set full --clock-control none --import-source on -k regex:kc_count_kernel -s 2 -c 1 -f -o gpurun_out/r02_count_k51 python tools/count_bench.py 51 4000000 8 150 > gpurun_out/t2_ncu.log 2>&1; echo "ncu rc=$?"
-timeout 120 ncu --metrics gpu__time_duration.sum --clock-control none -c 80 --csv --log-file gpurun_out/r02_count_launches.csv python tools/count_bench.py 51 4000000 8 150 > gpurun_out/t2_ncu2.log 2>&1; echo "ncu2 rc=$?"
+timeout 600 python -m pytest tests -m gpu -x -q --durations=15 > gpurun_out/t9_pytest.log 2>&1; echo "pytest rc=$?"; tail -22 gpurun_out/t9_pytest.log
+timeout 120 python -c "import __graft_entry__ as g; g.smoke()" > gpurun_out/t9_smoke.log 2>&1; echo "smoke rc=$?"; tail -3 gpurun_out/t9_smoke.log
+timeout 240 python bench.py --steps 10 --warmup 3 > gpurun_out/t9_bench.json 2> gpurun_out/t9_bench.err; echo "bench rc=$?"
+timeout 120 python bench.py --steps 5 --warmup 3 --workload chr14_k51_long --also --no-cpu-baseline > gpurun_out/t9_bench_long.json 2> gpurun_out/t9_bench_long.err; echo "bench long rc=$?"
+timeout 120 python bench.py --steps 5 --warmup 3 --workload chr14_k31 --also --no-cpu-baseline > gpurun_out/t9_bench_k31.json 2> gpurun_out/t9_bench_k31.err; echo "bench k31 rc=$?"
