@@ -422,3 +422,26 @@ def test_sequence_lines_blanks_headers_and_qualities(tmp_path):
             p = subprocess.run([str(exe), str(piece)], input=blob, capture_output=True, check=True)
             assert p.stderr.decode() == fmt
             assert [x for x in p.stdout.split(b"\n") if x] == reads
+
+
+# ------------------------------------------------------------------------------------- CPU: boundary behaviour
+def test_counter_has_no_cpu_fallback():
+    import cs267_hw3_b200 as kh
+    if kh.device_count() > 0:
+        pytest.skip("a GPU is present")
+    with pytest.raises(kh.KhError) as e:
+        kh.KmerCounter(19, 1000)
+    assert e.value.status == kh.KH_ERR_CUDA
+
+
+def test_kmer_count_cli_usage_and_errors(tmp_path):
+    from cs267_hw3_b200 import build
+    exe = build.build_count_cli()
+    r = subprocess.run([exe], capture_output=True, text=True)
+    assert r.returncode == 1 and r.stderr.startswith("Usage: kmer_count K reads_file")
+    r = subprocess.run([exe, "19", "reads.txt", "--contigs"], capture_output=True, text=True)
+    assert r.returncode == 1 and "Usage" in r.stderr
+    r = subprocess.run([exe, "99", "reads.txt", "out.txt"], capture_output=True, text=True)
+    assert r.returncode == 1 and "K must be 2..61" in r.stderr
+    r = subprocess.run([exe, "19", "/nonexistent/reads.txt", "out.txt"], capture_output=True, text=True)
+    assert r.returncode == -6 and "could not open /nonexistent/reads.txt" in r.stderr      # uncaught runtime_error, like the reference's CLI
