@@ -6,11 +6,13 @@
  * checks cs267_hw3_b200/csrc/count.cu from tests/ (see oracle/kmer_oracle.c for the rules).
  *
  * Parity status: the reference holds NO implementation of this stage ("the
- * Meraculous/HipMer stage this homework assumes done"), so there is nothing of the reference's to
- * pin it to directly: PARITY UNPINNED at the unit level.  It is pinned END TO END instead:
- * tests/test_count.py samples reads from the contigs of a generated data set, runs them through
- * this stage and then through insert + traverse, and the contigs must be the generator's solution --
- * the same solution the unmodified reference (oracle/_ref) reproduces from the generator's k-mer file.
+ * Meraculous/HipMer stage this homework assumes done"), so there is no function of the reference's
+ * to pin it to: PARITY UNPINNED at the unit level.  It is PINNED END TO END on files the UNMODIFIED
+ * reference wrote: tests/test_count.py cuts reads from the contigs in tests/golden/<case>.dat (the
+ * output of oracle/_ref/kmer_hash_ref_<K>, tests/golden/make_golden.py) and this stage must give
+ * back, line for line, the k-mer file <case>.txt that the reference had consumed to produce them
+ * (README.md:27's k=3 example included); and reads cut from a generated contig set, run through
+ * this stage and then through insert + traverse, must give the generator's solution.
  *
  * Definition (what both this file and the CUDA path compute), for k-mer length K:
  *   - a base is one of the bytes 'A' 'C' 'G' 'T'; every other byte ('\n', 'N', lower case, ...)

@@ -445,3 +445,43 @@ def test_kmer_count_cli_usage_and_errors(tmp_path):
     assert r.returncode == 1 and "K must be 2..61" in r.stderr
     r = subprocess.run([exe, "19", "/nonexistent/reads.txt", "out.txt"], capture_output=True, text=True)
     assert r.returncode == -6 and "could not open /nonexistent/reads.txt" in r.stderr      # uncaught runtime_error, like the reference's CLI
+
+
+# ------------------------------------------------------------- pinned to files the unmodified reference wrote
+def _golden_reads(case, k):
+    """Reads tiled over the contigs the UNMODIFIED reference wrote for a golden case (tests/golden/<case>.dat, made by
+    tests/golden/make_golden.py from oracle/_ref) and the k-mer file it had been given (<case>.txt)."""
+    from conftest import GOLDEN
+    with open(os.path.join(GOLDEN, case + ".dat"), "rb") as f:
+        contigs = f.read()
+    with open(os.path.join(GOLDEN, case + ".txt"), "rb") as f:
+        kmer_file = f.read()
+    reads = readgen.tile_reads(contigs, k, read_len=k + (2 if k < 8 else 40), coverage=2, seed=k)
+    return reads, sorted(kmer_file.split(b"\n")[:-1])
+
+
+def _lines_of(pairs, k):
+    pl = (k + 3) // 4
+    return sorted((oracle.unpack_kmer(bytes(p[:pl]), k) + " " + chr(p[pl]) + chr(p[pl + 1])).encode() for p in pairs)
+
+
+GOLDEN_CASES = [("readme_k3", 3), ("k19_a", 19), ("k19_singletons", 19), ("k19_long", 19), ("k31_a", 31), ("k51_a", 51)]
+
+
+@pytest.mark.parametrize("case,k", GOLDEN_CASES)
+def test_oracle_gives_back_the_references_own_input_file(case, k):
+    """Closing the loop on reference-written artefacts: reads cut from the contigs the reference produced, analysed, are
+    line for line the k-mer file the reference had consumed (its README.md:19-21 'first preprocessing stage' undone and
+    redone)."""
+    reads, want = _golden_reads(case, k)
+    assert _lines_of(oracle.analyse_reads(reads, k, 2, 2)[0], k) == want
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("case,k", GOLDEN_CASES)
+def test_gpu_gives_back_the_references_own_input_file(case, k):
+    reads, want = _golden_reads(case, k)
+    with _counter(k, 20000) as kc:
+        kc.count_reads(reads)
+        assert sorted(kc.extract_lines(2, 2).tobytes().split(b"\n")[:-1]) == want
+        assert _lines_of(kc.extract(2, 2), k) == want
