@@ -46,7 +46,7 @@ def build_lib(force: bool = False) -> str:
 
 def build_cli(ks=(19, 31, 51), force: bool = False) -> list[str]:
     """kmer_hash_<K>: the reference's CLI (kmer_hash.cpp:84-152) over the C ABI, one binary per K."""
-    build_lib(force)
+    build_lib()                      # only if stale: `force` is about the binaries
     src = os.path.join(ROOT, "src", "kmer_hash.cpp")
     hdrs = [os.path.join(ROOT, "include", f) for f in os.listdir(os.path.join(ROOT, "include"))]
     outs = []
@@ -61,7 +61,7 @@ def build_cli(ks=(19, 31, 51), force: bool = False) -> list[str]:
 
 def build_count_cli(force: bool = False) -> str:
     """kmer_count: reads -> the reference's k-mer file (or straight to contigs); K is a run-time argument."""
-    build_lib(force)
+    build_lib()
     src = os.path.join(ROOT, "src", "kmer_count.cpp")
     hdrs = [os.path.join(ROOT, "include", "kh_capi.h"), os.path.join(ROOT, "include", "kh", "kmer_counter.hpp")]
     out = os.path.join(ROOT, "kmer_count")
