@@ -247,7 +247,9 @@ int kh_count_create(int k, uint64_t n_distinct_expected, double load_factor, int
 int kh_count_destroy(kh_counter* c);
 int kh_count_clear(kh_counter* c);
 int kh_count_reads(kh_counter* c, const char* reads_host, uint64_t n_bytes);         /* may be called repeatedly */
-int kh_count_reads_device(kh_counter* c, const char* reads_dev, uint64_t n_bytes);  /* enqueues on the counter's stream */
+/* enqueues on the counter's stream: reads_dev (any alignment) must stay valid until the next synchronising call on
+ * this counter (kh_count_get_stats, kh_count_extract*, kh_count_lookup, kh_count_reads) */
+int kh_count_reads_device(kh_counter* c, const char* reads_dev, uint64_t n_bytes);
 /* kmer_pair records (kh_pair_bytes(k) each) of the reported k-mers.  _device: *pairs_dev_out is owned by the
  * counter and valid until its next extract, clear or destroy.  Host variant: pairs_host_out may be NULL to
  * learn *n_out only; with capacity < *n_out nothing is copied and KH_ERR_ARG is returned (*n_out is set). */
