@@ -485,3 +485,50 @@ def test_gpu_gives_back_the_references_own_input_file(case, k):
         kc.count_reads(reads)
         assert sorted(kc.extract_lines(2, 2).tobytes().split(b"\n")[:-1]) == want
         assert _lines_of(kc.extract(2, 2), k) == want
+
+
+def _python_count(reads: bytes, k: int, min_count: int, min_ext: int):
+    """The definition in oracle/kmer_count_oracle.c's header once more, as plain Python over a dict (small cases only)."""
+    acc = {}
+    for p in range(len(reads) - k + 1):
+        kmer = reads[p:p + k]
+        if any(ch not in b"ACGT" for ch in kmer):
+            continue
+        e = acc.setdefault(kmer, [0, {}, {}])
+        e[0] += 1
+        if p > 0 and reads[p - 1:p] in (b"A", b"C", b"G", b"T"):
+            e[1][reads[p - 1:p]] = e[1].get(reads[p - 1:p], 0) + 1
+        if p + k < len(reads) and reads[p + k:p + k + 1] in (b"A", b"C", b"G", b"T"):
+            e[2][reads[p + k:p + k + 1]] = e[2].get(reads[p + k:p + k + 1], 0) + 1
+    out = []
+    for kmer in sorted(acc):
+        n, back, fwd = acc[kmer]
+        if min(n, 255) < min_count:
+            continue
+        ext = b""
+        for side in (back, fwd):
+            q = [b for b in (b"A", b"C", b"G", b"T") if min(side.get(b, 0), 127) >= min_ext]
+            ext += q[0] if len(q) == 1 else b"F"
+        out.append(kmer + b" " + ext)
+    return out
+
+
+@pytest.mark.parametrize("k,min_count,min_ext,seed", [(2, 1, 1, 1), (3, 2, 2, 2), (5, 1, 2, 3), (9, 2, 1, 4), (17, 1, 1, 5), (33, 2, 2, 6), (61, 1, 1, 7)])
+def test_oracle_against_an_independent_python_statement(k, min_count, min_ext, seed):
+    """Two statements of the definition that share nothing (C: sort + run scan; Python: dict): random text over
+    ACGT with separators, N and lower case, short alphabets so that k-mers repeat and fork, saturating repeats."""
+    rng = np.random.default_rng(seed)
+    alphabet = np.frombuffer(b"ACGTACGTACGTACGTN\na", dtype=np.uint8) if k < 12 else np.frombuffer(b"ACGT", dtype=np.uint8)
+    text = alphabet[rng.integers(0, alphabet.size, 3000)]
+    if k >= 12:                                        # long k: repeat a few reads so that counts exceed 1, with point changes
+        base = bytes(text[:400])
+        parts = []
+        for _ in range(12):
+            b = bytearray(base)
+            for pos in rng.integers(0, len(b), 3):
+                b[pos] = b"ACGT"[int(rng.integers(0, 4))]
+            parts.append(bytes(b))
+        text = np.frombuffer(b"\n".join(parts) + b"\n" + b"A" * 400 + b"\n", dtype=np.uint8)
+    blob = bytes(text)
+    pairs, _, _ = oracle.analyse_reads(blob, k, min_count, min_ext)
+    assert _lines_of(pairs, k) == _python_count(blob, k, min_count, min_ext)
