@@ -50,11 +50,6 @@ namespace kh {
 #ifndef KH_CT_MINBLOCKS
 #define KH_CT_MINBLOCKS 2
 #endif
-// 1: successor lookups whose home bucket is full of other keys go to a work list and are finished by the whole block with
-// full warps, instead of every lane looping on its own probe sequence while the rest of its warp idles (phase 2 below)
-#ifndef KH_CT_DENSE_RETRY
-#define KH_CT_DENSE_RETRY 0
-#endif
 template <int W> struct CtBuild {
     // A chunk = one run of buckets that a thread block builds in shared memory.  Shared memory per block:
     //   table | succ u16[node] (later the characters) | (ancestor, distance) u32[node] | ext code + flags u8[node] | pool offset u16[node]
@@ -574,7 +569,7 @@ ct_build_kernel(const typename Slot<W>::value_t* __restrict__ fine, const u32* _
     u32* s_pd = reinterpret_cast<u32*>(s_raw + B::kOffPd);       // (ancestor node << 16) | distance to it; a segment head: (itself << 16) | its segment index
     unsigned short* s_off = reinterpret_cast<unsigned short*>(s_raw + B::kOffOff);
     unsigned char* s_code = s_raw + B::kOffCode;
-    __shared__ u32 s_inserted, s_dups, s_nheads, s_seg0, s_chars, s_err, s_wl_n[2];
+    __shared__ u32 s_inserted, s_dups, s_nheads, s_seg0, s_chars, s_err;
     const u32 c = blockIdx.x;
     const u32 b0 = chunk_base[c], nb = chunk_base[c + 1] - b0;
     const u32 cnt = min(chunk_cursor[c], B::kMaxSlots);
@@ -591,7 +586,7 @@ ct_build_kernel(const typename Slot<W>::value_t* __restrict__ fine, const u32* _
         const u32 i = threadIdx.x + r * kCtBuildThreads;
         v[r] = i < cnt ? fine[ct_fine_index<W>(c, i, g.chunks_per_rank)] : S::zero();
     }
-    if (threadIdx.x == 0) { s_inserted = 0; s_dups = 0; s_nheads = 0; s_chars = 0; s_err = 0; s_wl_n[0] = 0; s_wl_n[1] = 0; }
+    if (threadIdx.x == 0) { s_inserted = 0; s_dups = 0; s_nheads = 0; s_chars = 0; s_err = 0; }
     {
         uint4* s4 = reinterpret_cast<uint4*>(s_raw);
         for (u32 i = threadIdx.x; i < nb * 2u; i += kCtBuildThreads) s4[i] = make_uint4(0, 0, 0, 0);
@@ -629,117 +624,6 @@ ct_build_kernel(const typename Slot<W>::value_t* __restrict__ fine, const u32* _
         if (err) atomicOr(&s_err, err);
     }
     __syncthreads();
-#if KH_CT_DENSE_RETRY
-    // ---- 2. successor of every k-mer, if it lives in this chunk (kmer_hash.cpp:44-51 as an LDS probe) ----
-    // Two k-mers per thread and iteration: both first probes are issued before either is looked at.  A lookup whose home
-    // bucket is full of other keys (a quarter of them with two slots per bucket at load factor 0.5) is not continued by
-    // its lane -- that loop ran with 2 of 32 lanes and was ~12 % of the kernel's warp instructions -- but put on a work
-    // list, (node << 16) | next bucket, in the memory of s_off (unused until phase 5), and the block finishes the list
-    // round by round with full warps.  A list that is full (never at the shipped sizes) sends the lane back to its own loop.
-    {
-        u32* const s_wl = reinterpret_cast<u32*>(s_raw + B::kOffOff);
-        constexpr u32 kWlCap = B::kMaxSlots / 4;                       // two lists of kWlCap entries in kMaxSlots * 2 bytes
-        const u32 lt_mask = (1u << lane_id()) - 1u;
-#pragma unroll 1
-        for (u32 base0 = 0; base0 < cnt; base0 += 2 * kCtBuildThreads) {        // block-uniform trip count (ballots inside)
-            const u32 base = base0 + threadIdx.x;
-            u32 slot[2], b[2], code[2];
-            V key[2];
-            int res[2];
-#pragma unroll
-            for (int q = 0; q < 2; ++q) {
-                const u32 node = base + q * kCtBuildThreads;
-                slot[q] = node < cnt ? (u32)s_succ[node] : kSuccDead;
-            }
-#pragma unroll
-            for (int q = 0; q < 2; ++q) {
-                const V cur = slot[q] != kSuccDead ? s_tab[slot[q]] : S::zero();
-                const u32 f = slot[q] != kSuccDead ? S::fwd(cur) : kExtF;       // a duplicate is not in the table and on no chain
-                code[q] = f | ((slot[q] != kSuccDead && S::back(cur) == kExtF) ? kCodeBackF : 0u);
-                key[q] = S::next_key(CS::strip(cur), k);
-                b[q] = ct_bucket_in_chunk(CS::hash32(key[q]), nb);
-            }
-#pragma unroll
-            for (int q = 0; q < 2; ++q) res[q] = (code[q] & 7u) != kExtF ? ct_find_step<W>(s_base + b[q] * 32u, key[q]) : kFindMiss;
-#pragma unroll
-            for (int q = 0; q < 2; ++q) {
-                const u32 node = base + q * kCtBuildThreads;
-                bool pend = res[q] == kFindNext && nb > 1u;
-                const u32 bal = __ballot_sync(kFullMask, pend);
-                if (bal) {
-                    u32 first = 0;
-                    if (lane_id() == 0) first = atomicAdd(&s_wl_n[0], (u32)__popc(bal));
-                    first = __shfl_sync(kFullMask, first, 0);
-                    const u32 at = first + (u32)__popc(bal & lt_mask);
-                    if (pend && at < kWlCap) {
-                        s_wl[at] = (node << 16) | ((b[q] + 1 == nb) ? 0u : b[q] + 1);
-                    } else if (pend) {                                         // list full: this lane walks its own probe sequence
-                        pend = false;
-                        for (u32 tries = 1; res[q] == kFindNext && tries < nb; ++tries) {
-                            b[q] = (b[q] + 1 == nb) ? 0u : b[q] + 1;
-                            res[q] = ct_find_step<W>(s_base + b[q] * 32u, key[q]);
-                        }
-                    }
-                }
-                if (node >= cnt) continue;
-                s_code[node] = (unsigned char)code[q];
-                if (pend) continue;                                            // s_succ[node] keeps the own slot until the list resolves it
-                u32 sc = slot[q] == kSuccDead ? kSuccDead : kSuccTail;
-                if ((code[q] & 7u) != kExtF) {
-                    if (res[q] < 0) {
-                        sc = kSuccExt | slot[q];
-                    } else {
-                        sc = (u32)res[q];
-                        s_pd[res[q]] = (node << 16) | 1u;       // plain store: with two predecessors one of them wins, phase 3 notices
-                    }
-                }
-                s_succ[node] = (unsigned short)sc;
-            }
-        }
-        __syncthreads();
-        // the list, round by round: entry -> one more bucket; survivors move to the other list.  Probe number `round` of a
-        // lookup happens in round `round`; like the lane loop above, a lookup gives up after nb buckets.
-        u32 cur_list = 0;
-#pragma unroll 1
-        for (u32 round = 1;; ++round) {
-            const u32 n_items = min(s_wl_n[cur_list], kWlCap);
-            if (n_items == 0) break;
-#pragma unroll 1
-            for (u32 i0 = 0; i0 < n_items; i0 += kCtBuildThreads) {
-                const u32 i = i0 + threadIdx.x;
-                bool again = false;
-                u32 entry = 0;
-                if (i < n_items) {
-                    const u32 e = s_wl[cur_list * kWlCap + i];
-                    const u32 node = e >> 16, bq = e & 0xFFFFu;
-                    const u32 slot = s_succ[node];                             // still the k-mer's own slot
-                    const V key = S::next_key(CS::strip(s_tab[slot]), k);
-                    const int res = ct_find_step<W>(s_base + bq * 32u, key);
-                    if (res == kFindNext && round + 1 < nb) {
-                        again = true;
-                        entry = (node << 16) | ((bq + 1 == nb) ? 0u : bq + 1);
-                    } else if (res < 0) {
-                        s_succ[node] = (unsigned short)(kSuccExt | slot);
-                    } else {
-                        s_succ[node] = (unsigned short)res;
-                        s_pd[res] = (node << 16) | 1u;
-                    }
-                }
-                const u32 bal = __ballot_sync(kFullMask, again);
-                if (bal) {
-                    u32 first = 0;
-                    if (lane_id() == 0) first = atomicAdd(&s_wl_n[cur_list ^ 1u], (u32)__popc(bal));
-                    first = __shfl_sync(kFullMask, first, 0);
-                    if (again) s_wl[(cur_list ^ 1u) * kWlCap + first + (u32)__popc(bal & lt_mask)] = entry;      // survivors <= items <= kWlCap
-                }
-            }
-            __syncthreads();                                                   // list cur_list is read, the other one complete
-            if (threadIdx.x == 0) s_wl_n[cur_list] = 0;
-            cur_list ^= 1u;
-            __syncthreads();                                                   // ... and the emptied one may be pushed to again
-        }
-    }
-#else
     // ---- 2. successor of every k-mer, if it lives in this chunk (kmer_hash.cpp:44-51 as an LDS probe) ----
     // Two k-mers per thread and iteration: both first probes are issued before either is looked at.
 #pragma unroll 1
@@ -787,7 +671,6 @@ ct_build_kernel(const typename Slot<W>::value_t* __restrict__ fine, const u32* _
         }
     }
     __syncthreads();
-#endif
     // ---- 3. heads: k-mers no chain of this chunk runs into (or that two run into, or with backward ext 'F') ----
 #pragma unroll 1
     for (u32 node = threadIdx.x; node < cnt; node += kCtBuildThreads) {
