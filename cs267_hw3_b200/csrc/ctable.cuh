@@ -50,6 +50,12 @@ namespace kh {
 #ifndef KH_CT_MINBLOCKS
 #define KH_CT_MINBLOCKS 2
 #endif
+// pointer-jumping passes between two block-wide barriers in phase 4.  The jumps are in place (a stale read is still a
+// valid (ancestor, distance) pair), so several passes per barrier are safe; 3 measured best (build 4.24 -> 4.15 ms at
+// K=51: profiles/r02_build_geometry_variants.txt) -- the kernel is as much barrier- as issue-bound.
+#ifndef KH_CT_JUMPS
+#define KH_CT_JUMPS 3
+#endif
 template <int W> struct CtBuild {
     // A chunk = one run of buckets that a thread block builds in shared memory.  Shared memory per block:
     //   table | succ u16[node] (later the characters) | (ancestor, distance) u32[node] | ext code + flags u8[node] | pool offset u16[node]
@@ -702,8 +708,9 @@ ct_build_kernel(const typename Slot<W>::value_t* __restrict__ fine, const u32* _
     }
     // ---- 4. pointer jumping in shared memory: every k-mer learns its segment head and its distance from it ----
     // In place: a stale read is still a valid (ancestor, distance) pair.  A root's low half is its segment index, which a
-    // child never adds (it stops as soon as its ancestor is a root).  Chains are <= ~40 k-mers: ~6 rounds; a cycle
-    // without a head (no chain enters it: kmer_hash.cpp never visits it) never settles and is cut off after 14 rounds.
+    // child never adds (it stops as soon as its ancestor is a root).  Chains are <= ~40 k-mers: ~6 passes, KH_CT_JUMPS of
+    // them between two barriers; a cycle without a head (no chain enters it: kmer_hash.cpp never visits it) never settles
+    // and is cut off after 14+ passes.
     // A thread keeps a bit per node of its own that has not settled yet: later rounds only touch those.
     u32 active = 0;
 #pragma unroll 1
@@ -711,14 +718,17 @@ ct_build_kernel(const typename Slot<W>::value_t* __restrict__ fine, const u32* _
         const u32 pd = s_pd[node];
         active |= ((pd >> 16) != node) ? (1u << i) : 0u;            // heads and dead nodes are roots already
     }
-    for (int round = 0; round < 14; ++round) {
+    for (int round = 0; round < (14 + KH_CT_JUMPS - 1) / KH_CT_JUMPS; ++round) {
 #pragma unroll 1
-        for (u32 m = active; m; m &= m - 1u) {
-            const u32 i = (u32)__ffs((int)m) - 1u, node = threadIdx.x + i * kCtBuildThreads;
-            const u32 pd = s_pd[node], a = pd >> 16;
-            const u32 pa = s_pd[a], a2 = pa >> 16;
-            if (a2 == a) { active &= ~(1u << i); continue; }        // the ancestor is a root: this node is done
-            s_pd[node] = (a2 << 16) | ((pd + pa) & 0xFFFFu);
+        for (int rep = 0; rep < KH_CT_JUMPS; ++rep) {
+#pragma unroll 1
+            for (u32 m = active; m; m &= m - 1u) {
+                const u32 i = (u32)__ffs((int)m) - 1u, node = threadIdx.x + i * kCtBuildThreads;
+                const u32 pd = s_pd[node], a = pd >> 16;
+                const u32 pa = s_pd[a], a2 = pa >> 16;
+                if (a2 == a) { active &= ~(1u << i); continue; }        // the ancestor is a root: this node is done
+                s_pd[node] = (a2 << 16) | ((pd + pa) & 0xFFFFu);
+            }
         }
         if (!__syncthreads_or(active != 0u)) break;
     }
