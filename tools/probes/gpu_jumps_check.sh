@@ -1,5 +1,7 @@
 # A/B of KH_CT_JUMPS (pointer-jumping passes per block-wide barrier in ct_build_kernel phase 4): the K=51 bench line with
-# 1 / 2 / 3, then the chunk-table parity tests against the fastest of 2 / 3.
+# 1 / 2 / 3, then the chunk-table parity tests against the fastest of 2 / 3.  The three libraries are built beforehand with
+#   for j in 1 2 3; do nvcc -gencode arch=compute_100a,code=sm_100a -O3 -lineinfo -std=c++17 -DKH_CT_JUMPS=$j -Xcompiler -fPIC \
+#     -shared cs267_hw3_b200/csrc/capi.cu cs267_hw3_b200/csrc/count.cu -o tools/probes/variants/libkh_jumps$j.so; done
 mkdir -p gpurun_out
 for j in 1 2 3; do
   KH_LIB_PATH=$PWD/tools/probes/variants/libkh_jumps$j.so timeout 100 python bench.py --steps 10 --warmup 3 --no-e2e --no-cpu-baseline --no-count --also \
