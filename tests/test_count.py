@@ -290,9 +290,10 @@ def test_gpu_count_errors():
             with pytest.raises(kh.KhError) as e:
                 kc.extract(*bad)
             assert e.value.status == kh.KH_ERR_ARG
-        n = __import__("ctypes").c_uint64()
+        import ctypes as C
+        n = C.c_uint64()
         buf = np.empty((10, 7), dtype=np.uint8)
-        rc = kh.lib().kh_count_extract(kc._h, 2, 2, buf.ctypes.data, 10, __import__("ctypes").byref(n))
+        rc = kh.lib().kh_count_extract(kc._h, 2, 2, buf.ctypes.data, 10, C.byref(n))
         assert rc == kh.KH_ERR_ARG and n.value == 50000                        # too small: nothing copied, size reported
     with pytest.raises(kh.KhError):
         kh.KmerCounter(62, 1000)
