@@ -145,7 +145,11 @@ __global__ void ct_barrier_kernel(const CtPeers pe, u32 epoch, Counters* ctr, in
         for (;;) {
             u32 seen;
             asm volatile("ld.acquire.sys.global.u32 %0, [%1];" : "=r"(seen) : "l"(src) : "memory");
-            if ((int)((seen >> 1) - epoch) >= 0) { peer_bit = ((seen >> 1) == epoch) ? (seen & 1u) : 1u; break; }
+            // A NEWER epoch in this slot: the peer has passed this barrier and at least one more of the same parity.  Between
+            // two real barriers parity alternates, so it can only have got there by SKIPPING round barriers (rank_done, the
+            // early return above) -- i.e. it saw every rank's bit of this epoch as 0, its own included.  Reading that as 0
+            // keeps the ranks in agreement (read as 1, this rank would go on alone and wait at a barrier the others skip).
+            if ((int)((seen >> 1) - epoch) >= 0) { peer_bit = ((seen >> 1) == epoch) ? (seen & 1u) : (round >= 0 ? 0u : 1u); break; }
             asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t1));
             if (t1 - t0 > 4000000000ull) { ct_internal(ctr, kSiteBarrier); peer_bit = 1; break; }
             __nanosleep(200);

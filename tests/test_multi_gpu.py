@@ -40,7 +40,7 @@ def test_one_process_per_rank_on_one_gpu():
     if os.environ.get("KH_TEST_TWO_PROCESSES_ONE_GPU") != "1":
         pytest.skip("opt-in (KH_TEST_TWO_PROCESSES_ONE_GPU=1): passed in 12-16 s on B200, but one run of the long-contig case ran into "
                     "the 4 s barrier timeout -- with two time-sliced contexts a rank can be descheduled between its flag store and "
-                    "its flag load, which exposes the skipped-round-barrier parity issue described in DESIGN.md 4.6")
+                    "its flag load, which exposed the skipped-round-barrier parity race described (with its fix) in DESIGN.md 4.6")
     env = dict(os.environ, KH_TEST_ONE_DEVICE="1")
     r = subprocess.run([sys.executable, "-m", "torch.distributed.run", "--nnodes=1", "--nproc-per-node=2",
                         "--master-addr", "127.0.0.1", "--master-port", "29631",
