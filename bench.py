@@ -389,6 +389,7 @@ def measure_shape_n1(args, workload: str, steps: int, warmup: int, local_rank: i
     slot_b = st_last["slot_bits"] // 8
     out = {
         "ms_per_step": ms_per_step, "value": n / (ms_per_step * 1e-3), "ms_each_step": ms,
+        "ms_per_step_median": float(np.median(ms)), "ms_per_step_best": float(np.min(ms)),
         "config": {"workload": workload, "k": k, "n_kmers": n, "n_contigs": c, "load_factor": args.load_factor, "seed": SEED,
                    "table": ("chunk table (csrc/ctable.cuh): one staging pass into per-chunk buffers, every chunk built + contracted in "
                              "shared memory, one HBM lookup per segment, contigs ranked and emitted by per-contig walks"
@@ -458,8 +459,8 @@ def run_b200_arm(args, workload: str) -> dict | None:
         "steps": args.steps, "warmup": args.warmup, "ms_per_step": m["ms_per_step"], "higher_is_better": True,
         "scaling": "weak", "vs_baseline": None, "dtype": "u64" if m["config"]["slot_bytes"] == 8 else "u128", "data": "synthetic",
     }
-    for key in ("config", "stages_ms", "n_segments", "rank_rounds", "assembly_time_s", "wall_s_timed_loop", "gen_s", "verified",
-                "roofline", "e2e", "pack_lines", "gpu_launches", "clocks"):
+    for key in ("ms_per_step_median", "ms_per_step_best", "config", "stages_ms", "n_segments", "rank_rounds", "assembly_time_s",
+                "wall_s_timed_loop", "gen_s", "verified", "roofline", "e2e", "pack_lines", "gpu_launches", "clocks"):
         line[key] = m[key]
     if second:
         line["shapes"] = {}
