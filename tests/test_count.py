@@ -533,3 +533,31 @@ def test_oracle_against_an_independent_python_statement(k, min_count, min_ext, s
     blob = bytes(text)
     pairs, _, _ = oracle.analyse_reads(blob, k, min_count, min_ext)
     assert _lines_of(pairs, k) == _python_count(blob, k, min_count, min_ext)
+
+
+def test_kernel_functions_random_inputs(host_check, tmp_path):
+    """Property run: random K (every slot / window regime), random text with separators and runs, random chunk size and
+    table size (one piece or many, growth in the middle or not), aligned or not -- the kernels' functions always agree
+    with the oracle on records and counters."""
+    rng = np.random.default_rng(20261018)
+    for trial in range(40):
+        k = int(rng.choice([2, 3, 4, 7, 8, 15, 16, 17, 24, 31, 32, 33, 40, 48, 55, 61]))
+        n = int(rng.integers(1, 9000))
+        alpha = np.frombuffer(b"ACGT" * int(rng.integers(1, 12)) + b"N\n", dtype=np.uint8)
+        text = alpha[rng.integers(0, alpha.size, n)].copy()
+        if rng.random() < 0.5 and n > 200:                       # repeats: counters above 1, forks, saturation of small fields
+            piece = text[: int(rng.integers(k + 2, 200))].copy()
+            reps = int(rng.integers(2, 160))
+            text = np.concatenate([text] + [np.concatenate((piece, [10]))] * reps).astype(np.uint8)
+        mc, me = int(rng.integers(1, 4)), int(rng.integers(1, 4))
+        want_p, want_c, n_occ = oracle.analyse_reads(text, k, mc, me)
+        misalign = int(rng.integers(0, 16)) if rng.random() < 0.3 else 0
+        chunk = int(rng.choice([2048, 4096, 8192, 1 << 20]))
+        grow = int(rng.integers(0, 3)) if (misalign == 0 and rng.random() < 0.4) else None
+        n_slots = max(1024, 2 * (n_occ + 1))
+        head, recs, cnts = _run_host(host_check, tmp_path, text, k, chunk=chunk, n_slots=n_slots, min_count=mc, min_ext=me,
+                                     misalign=misalign, grow_after=grow)
+        ctx = f"trial {trial}: k={k} n={text.size} chunk={chunk} misalign={misalign} grow={grow} mc={mc} me={me}"
+        assert head[0] == n_occ and head[3] == 0, ctx
+        assert recs.shape == want_p.shape and (recs == want_p).all(), ctx
+        assert (cnts == want_c).all(), ctx
